@@ -1,0 +1,83 @@
+/*
+ * shenb200.h -- C ABI of libshenb200.so: sm_100a kernels for shenfun's
+ * tensor-product transform-and-solve hot path.
+ *
+ * Conventions
+ *  - every pointer named d_* is a DEVICE pointer owned by the caller
+ *    (torch tensors on the Python side); the library owns only twiddle /
+ *    coefficient tables that it caches per device.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - all functions return 0 on success, a negative shb_status otherwise;
+ *    shb_last_error() gives a human readable message for the calling thread.
+ *  - arrays are C-ordered, fp64 (`double`) or complex128 (`double[2]`).
+ *    An N-D array transformed along `axis` is passed collapsed to 3-D as
+ *    [outer][n][inner] (outer = prod(shape[:axis]), inner = prod(shape[axis+1:])).
+ *
+ * Each entry point names the reference interface it stands in for
+ * (paths relative to the reference checkout, spectralDNS/shenfun v4.3.0).
+ */
+#ifndef SHENB200_H
+#define SHENB200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SHB_API __attribute__((visibility("default")))
+#else
+#define SHB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SHB_OK = 0,
+    SHB_ERR_ARG = -1,      /* invalid argument */
+    SHB_ERR_CUDA = -2,     /* CUDA runtime error (see shb_last_error) */
+    SHB_ERR_UNSUPPORTED = -3,
+    SHB_ERR_NOMEM = -4
+} shb_status;
+
+SHB_API const char *shb_last_error(void);
+SHB_API int shb_version(void);
+/* 1 when a CUDA device of compute capability 10.x is usable, else 0 */
+SHB_API int shb_device_ok(void);
+
+/* ------------------------------------------------------------------ */
+/* Fourier axis transforms (replace mpi4py_fft.fftw.{fftn,ifftn,rfftn,irfftn}
+ * planned in shenfun/fourier/bases.py:218-279 and the pad/truncate/normalise
+ * around them: FourierBase.forward :131-149, R2C._truncation_forward /
+ * _padding_backward :409-435, C2C :570-598).                              */
+
+/* Forward complex DFT of length n_fft along the middle axis, then 3/2-rule
+ * truncation to N (N <= n_fft; N == n_fft means no padding) and scaling:
+ *   out[o][k][c] = scale * trunc_N( sum_j in[o][j][c] exp(-2 pi i j k / n_fft) )
+ * in : complex [outer][n_fft][inner];  out : complex [outer][N][inner].
+ * in == out is allowed when N == n_fft.                                   */
+SHB_API int shb_fft_c2c_forward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
+                        int n_fft, int N, double scale, void *stream);
+
+/* Zero-pad N -> n_fft by the C2C rule (both +-N/2 entries halved when N is
+ * even and N < n_fft), then un-normalised inverse DFT of length n_fft.
+ * in : complex [outer][N][inner];  out : complex [outer][n_fft][inner].
+ * flags bit 0: dealias_direct (2/3-rule zeroing, only with N == n_fft).   */
+SHB_API int shb_fft_c2c_backward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
+                         int n_fft, int N, double scale, int flags, void *stream);
+
+/* Real-to-complex forward DFT of length n_fft, truncation to N//2+1 modes
+ * (Nyquist -> 2*Re when N even and N < n_fft), scaling.
+ * in : real [outer][n_fft][inner];  out : complex [outer][N/2+1][inner].  */
+SHB_API int shb_fft_r2c_forward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
+                        int n_fft, int N, double scale, void *stream);
+
+/* Pad N//2+1 modes to n_fft//2+1 (Nyquist -> 0.5*Re when N even and
+ * N < n_fft), un-normalised complex-to-real inverse DFT of length n_fft.
+ * in : complex [outer][N/2+1][inner];  out : real [outer][n_fft][inner].  */
+SHB_API int shb_fft_c2r_backward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
+                         int n_fft, int N, double scale, int flags, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHENB200_H */

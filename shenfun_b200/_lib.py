@@ -1,0 +1,71 @@
+"""ctypes binding of libshenb200.so (the C ABI declared in include/shenb200.h).
+
+There is no CPU fallback: if the shared library is missing, or a kernel is
+launched without a B200-class device, the call raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libshenb200.so')
+
+_lib = None
+
+
+class ShenB200Error(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    c = ctypes
+    vp, i64, i32, f64 = c.c_void_p, c.c_int64, c.c_int, c.c_double
+    lib.shb_last_error.restype = c.c_char_p
+    lib.shb_last_error.argtypes = []
+    lib.shb_version.restype = i32
+    lib.shb_device_ok.restype = i32
+    sig = {
+        'shb_fft_c2c_forward': [vp, vp, i64, i64, i32, i32, f64, vp],
+        'shb_fft_c2c_backward': [vp, vp, i64, i64, i32, i32, f64, i32, vp],
+        'shb_fft_r2c_forward': [vp, vp, i64, i64, i32, i32, f64, vp],
+        'shb_fft_c2r_backward': [vp, vp, i64, i64, i32, i32, f64, i32, vp],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = i32
+        fn.argtypes = argtypes
+    return sig
+
+
+def load():
+    """Load (once) and return the ctypes handle; raise if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ShenB200Error(
+                f'{LIB_PATH} not found: build it with ./build.sh or '
+                '`python -c "import __graft_entry__ as g; g.build()"` '
+                '(there is no CPU fallback)')
+        lib = ctypes.CDLL(LIB_PATH)
+        lib._signatures = _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().shb_last_error().decode()
+        raise ShenB200Error(f'libshenb200 error {rc}: {msg}')
+
+
+def exported_symbols():
+    """Names declared by include/shenb200.h (used by the CPU-side ABI test)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), 'include', 'shenb200.h')
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r'\b(shb_[a-z0-9_]+)\s*\(', txt)))
+
+
+def stream_ptr():
+    """cudaStream_t of torch's current stream as an integer for the C ABI."""
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,50 @@
+// fft_api.cu -- C ABI entry points for the Fourier axis transforms
+#include "fft_common.cuh"
+#include <stdlib.h>
+
+using namespace shb;
+
+static int dispatch(int mode, const void *in, void *out, int64_t outer, int64_t inner,
+                    int n_fft, int N, double scale, int flags, void *stream) {
+    if (!in || !out) { set_error("fft: null pointer"); return SHB_ERR_ARG; }
+    if (outer < 0 || inner < 0 || n_fft < 1 || N < 1 || N > n_fft) {
+        set_error("fft: bad sizes outer=%lld inner=%lld n_fft=%d N=%d", (long long)outer,
+                  (long long)inner, n_fft, N);
+        return SHB_ERR_ARG;
+    }
+    if ((flags & 1) && N != n_fft) { set_error("fft: dealias_direct requires N == n_fft"); return SHB_ERR_ARG; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    static const bool force_generic = getenv("SHB_FFT_FORCE_GENERIC") != nullptr;
+    if (!force_generic) {
+        int rc = fft_fast_launch(mode, in, out, outer, inner, n_fft, N, scale, flags, st);
+        if (rc != SHB_ERR_UNSUPPORTED) return rc;
+    }
+    if (in == out && !(N == n_fft && (mode == FFT_C2C_FWD || mode == FFT_C2C_BWD))) {
+        set_error("fft: in-place only for unpadded c2c"); return SHB_ERR_ARG;
+    }
+    return fft_generic_launch(mode, in, out, outer, inner, n_fft, N, scale, flags, st);
+}
+
+extern "C" {
+
+int shb_fft_c2c_forward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
+                        int n_fft, int N, double scale, void *stream) {
+    return dispatch(FFT_C2C_FWD, d_in, d_out, outer, inner, n_fft, N, scale, 0, stream);
+}
+
+int shb_fft_c2c_backward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
+                         int n_fft, int N, double scale, int flags, void *stream) {
+    return dispatch(FFT_C2C_BWD, d_in, d_out, outer, inner, n_fft, N, scale, flags, stream);
+}
+
+int shb_fft_r2c_forward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
+                        int n_fft, int N, double scale, void *stream) {
+    return dispatch(FFT_R2C, d_in, d_out, outer, inner, n_fft, N, scale, 0, stream);
+}
+
+int shb_fft_c2r_backward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
+                         int n_fft, int N, double scale, int flags, void *stream) {
+    return dispatch(FFT_C2R, d_in, d_out, outer, inner, n_fft, N, scale, flags, stream);
+}
+
+}  // extern "C"
