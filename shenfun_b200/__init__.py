@@ -1,0 +1,17 @@
+"""shenfun_b200 -- B200-native tensor-product transform-and-solve path with
+shenfun's API (TensorProductSpace.forward/backward, Function/Array,
+inner/project, la solvers).  Kernels live in libshenb200.so (sm_100a, C ABI in
+include/shenb200.h); this package is the host-side mirror of the reference's
+Python interface for that path.
+"""
+from .comm import comm, Comm, init_from_env
+from .config import config
+from .spectralbase import SpectralBase, Domain
+from .fourier import R2C, C2C
+from .functionspace import FunctionSpace
+from .tensorproductspace import TensorProductSpace, VectorSpace, TensorSpace, CompositeSpace
+from .arrays import Function, Array
+from . import ops
+from ._lib import ShenB200Error
+
+__version__ = '0.1.0'

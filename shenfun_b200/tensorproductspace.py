@@ -1,0 +1,624 @@
+"""Tensor-product spaces with fused device transform plans.
+
+Host-side mirror of shenfun/tensorproductspace.py:
+  `TensorProductSpace.__init__` / `configure_backwards` :314-541 (planning),
+  `ForwardTransform` / `BackwardTransform` / `ScalarTransform` :46-259,
+  `get_dealiased` :543-578, `VectorSpace` / `CompositeSpace` :1190-1784,
+  `VectorTransform` :1786-1795.
+
+Differences in *how* (not what):
+  * a plan is a short list of per-axis kernel launches (plus one all-to-all
+    when the space is slab-distributed over several GPUs); pad/truncate,
+    normalisation, stencils and mass solves are fused into those launches, and
+    un-padded complex axes run in place, so the 512^3 R2C x C2C x C2C transform
+    touches each array exactly three times;
+  * vector / tensor valued spaces are transformed in ONE batched launch per
+    axis (the component index is folded into the `outer` batch extent) instead
+    of a Python loop over components;
+  * multi-GPU uses the slab decomposition of mpi4py-fft (`slab=True`,
+    :393-396): physical space sharded on axis (first-transformed+1) % ndim,
+    spectral space on the axis transformed just before it.
+"""
+import numpy as np
+import torch
+
+from .arrays import Function, Array
+from .comm import comm as default_comm
+from . import ops
+
+__all__ = ('TensorProductSpace', 'VectorSpace', 'TensorSpace', 'CompositeSpace')
+
+
+def _block(N, P, i):
+    """Balanced block decomposition used by mpi4py-fft's Pencil (start, length)."""
+    n, r = divmod(N, P)
+    start = i*n + min(i, r)
+    return start, n + (1 if i < r else 0)
+
+
+class _Step:
+    """One stage of a plan: an axis transform or a global exchange."""
+    __slots__ = ('kind', 'axis', 'base', 'in_shape', 'out_shape', 'in_dtype', 'out_dtype',
+                 'inplace_ok', 'exchange')
+
+    def __init__(self, kind, axis, base, in_shape, out_shape, in_dtype, out_dtype,
+                 inplace_ok=False, exchange=None):
+        self.kind = kind
+        self.axis = axis
+        self.base = base
+        self.in_shape = tuple(in_shape)
+        self.out_shape = tuple(out_shape)
+        self.in_dtype = in_dtype
+        self.out_dtype = out_dtype
+        self.inplace_ok = inplace_ok
+        self.exchange = exchange
+
+
+class _WorkPool:
+    """Two flat ping-pong byte buffers, grown on demand and reused by every call."""
+
+    def __init__(self):
+        self.buf = [None, None]
+
+    def get(self, which, shape, dtype, device):
+        nbytes = int(np.prod(shape))*torch.empty((), dtype=dtype).element_size()
+        b = self.buf[which]
+        if b is None or b.numel() < nbytes or b.device != device:
+            b = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+            self.buf[which] = b
+        return b[:nbytes].view(dtype).view(shape)
+
+
+class _Transform:
+    """Callable plan (forward, backward or scalar product) of a space."""
+
+    def __init__(self, space, steps, direction):
+        self.space = space
+        self.steps = steps
+        self.direction = direction
+        self._pool = space._pool
+
+    @property
+    def input_shape(self):
+        return self.steps[0].in_shape
+
+    @property
+    def output_shape(self):
+        return self.steps[-1].out_shape
+
+    def _run(self, u, out, ncomp):
+        """u, out: plain contiguous tensors with a leading component batch folded in."""
+        steps = self.steps
+        n = len(steps)
+        lead = (ncomp,) if ncomp > 1 else ()
+        # destination of every step: the user output if all later steps run in place
+        dest_is_out = [False]*n
+        dest_is_out[n-1] = True
+        for i in range(n-2, -1, -1):
+            s = steps[i+1]
+            dest_is_out[i] = dest_is_out[i+1] and s.inplace_ok and s.in_shape == s.out_shape \
+                and s.in_dtype == s.out_dtype
+        cur = u
+        cur_is_user_input = True
+        which = 0
+        for i, s in enumerate(steps):
+            full_out_shape = lead + s.out_shape
+            can_inplace = (s.inplace_ok and s.in_shape == s.out_shape and s.in_dtype == s.out_dtype
+                           and not cur_is_user_input)
+            if dest_is_out[i]:
+                if can_inplace and cur.data_ptr() == out.data_ptr():
+                    dst = cur
+                else:
+                    dst = out
+            elif can_inplace:
+                dst = cur
+            else:
+                dst = self._pool.get(which, full_out_shape, s.out_dtype, u.device)
+                if dst.data_ptr() == cur.data_ptr():
+                    which ^= 1
+                    dst = self._pool.get(which, full_out_shape, s.out_dtype, u.device)
+                which ^= 1
+            if s.kind == 'exchange':
+                s.exchange(cur, dst, ncomp, self.direction)
+            else:
+                ax = s.axis
+                outer = ncomp*int(np.prod(s.in_shape[:ax], dtype=np.int64))
+                inner = int(np.prod(s.in_shape[ax+1:], dtype=np.int64))
+                if self.direction == 'backward':
+                    s.base._backward_axis(cur, dst, outer, inner)
+                else:
+                    s.base._forward_axis(cur, dst, outer, inner,
+                                         scalar_product=(self.direction == 'scalar_product'))
+            cur = dst
+            cur_is_user_input = False
+        if cur.data_ptr() != out.data_ptr():
+            out.copy_(cur)
+        return out
+
+    def __call__(self, input_array, output_array=None, kind=None, **kw):
+        space = self.space
+        fo = self.direction != 'backward'
+        if output_array is None:
+            output_array = Function(space) if fo else Array(space)
+        u = ops.as_device_tensor(input_array)
+        out = ops.plain(output_array)
+        ncomp = 1
+        in_shape = tuple(u.shape)
+        if in_shape != self.input_shape:
+            if in_shape[1:] == self.input_shape or in_shape[-len(self.input_shape):] == self.input_shape:
+                ncomp = int(np.prod(in_shape[:len(in_shape)-len(self.input_shape)]))
+            else:
+                raise ValueError(f'{self.direction}: input shape {in_shape} does not match plan '
+                                 f'{self.input_shape}')
+        if tuple(out.shape[len(out.shape)-len(self.output_shape):]) != self.output_shape:
+            raise ValueError(f'{self.direction}: output shape {tuple(out.shape)} does not match plan '
+                             f'{self.output_shape}')
+        if u.dtype != self.steps[0].in_dtype:
+            u = u.to(self.steps[0].in_dtype)
+        if not u.is_contiguous():
+            u = u.contiguous()
+        if not out.is_contiguous():
+            raise ValueError('output array must be contiguous')
+        self._run(u, out, ncomp)
+        return output_array
+
+
+class TensorProductSpace:
+    """Cartesian product of 1-D bases with device transforms.
+
+    Parameters follow shenfun/tensorproductspace.py:262-316.
+    """
+
+    def __init__(self, comm, bases, axes=None, dtype=None, slab=True, collapse_fourier=False,
+                 backward_from_pencil=False, coordinates=None, modify_spaces_inplace=False, **kw):
+        self.comm = default_comm if comm is None else comm
+        if not modify_spaces_inplace:
+            bases = [b.get_unplanned() for b in bases]
+        self.bases = tuple(bases)
+        nd = len(self.bases)
+        for i, b in enumerate(self.bases):
+            b.axis = i
+            b.tensorproductspace = self
+        if axes is None:
+            axes = tuple(range(nd))
+        flat = []
+        for a in axes:
+            if isinstance(a, (tuple, list)):
+                flat.extend(int(x) % nd for x in a)
+            else:
+                flat.append(int(a) % nd)
+        assert sorted(flat) == list(range(nd)), 'axes must be a permutation'
+        self.axes = tuple(flat)
+        self._padded_space = {}
+        self._pool = _WorkPool()
+        self.coors = None
+
+        first = self.bases[self.axes[-1]]
+        # tensorproductspace.py:365-385: real input needs an R2C (or a real
+        # polynomial base) transformed first
+        if dtype is None:
+            dtype = first.dtype
+        dtype = np.dtype(dtype)
+        self.physical_dtype = torch.float64 if dtype.kind == 'f' else torch.complex128
+        for ax in self.axes[:-1]:
+            b = self.bases[ax]
+            if b.family() == 'fourier' and b.short_name() == 'R2C' and nd > 1:
+                raise ValueError('an R2C base must be the first transformed axis (last in axes)')
+        if first.family() == 'fourier' and first.short_name() == 'C2C':
+            self.physical_dtype = torch.complex128
+
+        P = self.comm.Get_size()
+        rank = self.comm.Get_rank()
+        self._P, self._rank = P, rank
+        fwd_order = list(reversed(self.axes))
+        self._dist_phys = None
+        self._dist_spec = None
+        if P > 1:
+            assert nd >= 2, 'cannot distribute a 1-D space'
+            dp = (fwd_order[0]+1) % nd
+            i = fwd_order.index(dp)
+            assert i >= 1
+            self._dist_phys = dp
+            self._dist_spec = fwd_order[i-1]
+
+        # global shapes
+        self._gshape_phys = tuple(b.physical_len() for b in self.bases)
+        self._gshape_spec = tuple(b.spectral_len() for b in self.bases)
+        self._build_plans()
+
+    # ---- planning -------------------------------------------------------------------
+    def _local(self, gshape, dist_axis):
+        shape = list(gshape)
+        start = [0]*len(shape)
+        if dist_axis is not None:
+            start[dist_axis], shape[dist_axis] = _block(gshape[dist_axis], self._P, self._rank)
+        return tuple(shape), tuple(start)
+
+    def _build_plans(self):
+        from .transfer import SlabExchange
+        nd = len(self.bases)
+        fwd_order = list(reversed(self.axes))
+        # forward: physical -> spectral
+        gshape = list(self._gshape_phys)
+        dist = self._dist_phys
+        dt = self.physical_dtype
+        fsteps = []
+        for i, ax in enumerate(fwd_order):
+            b = self.bases[ax]
+            if dist is not None and ax == dist:
+                new_dist = fwd_order[i-1]
+                in_shape, _ = self._local(gshape, dist)
+                out_shape, _ = self._local(gshape, new_dist)
+                ex = SlabExchange(self.comm, tuple(gshape), gather_axis=dist, scatter_axis=new_dist)
+                fsteps.append(_Step('exchange', None, None, in_shape, out_shape, dt, dt, exchange=ex))
+                dist = new_dist
+            in_shape, _ = self._local(gshape, dist)
+            gshape[ax] = b.spectral_len()
+            out_shape, _ = self._local(gshape, dist)
+            odt = b.spectral_dtype_for(dt)
+            fsteps.append(_Step('axis', ax, b, in_shape, out_shape, dt, odt, inplace_ok=b.inplace_ok()))
+            dt = odt
+        self.spectral_dtype = dt
+        assert dist == self._dist_spec
+        # backward = mirror image
+        bsteps = []
+        for s in reversed(fsteps):
+            bsteps.append(_Step(s.kind, s.axis, s.base, s.out_shape, s.in_shape, s.out_dtype, s.in_dtype,
+                                inplace_ok=s.inplace_ok, exchange=s.exchange))
+        self.forward = _Transform(self, fsteps, 'forward')
+        self.backward = _Transform(self, bsteps, 'backward')
+        self.scalar_product = _Transform(self, fsteps, 'scalar_product')
+
+    # ---- bookkeeping API (mpi4py_fft.PFFT + tensorproductspace.py:580-1180) ------------
+    @property
+    def dimensions(self):
+        return len(self.bases)
+
+    @property
+    def rank(self):
+        return 0
+
+    @property
+    def is_composite_space(self):
+        return 0
+
+    @property
+    def is_padded(self):
+        return any(b.is_padded for b in self.bases)
+
+    def num_components(self):
+        return 1
+
+    def flatten(self):
+        return [self]
+
+    def __len__(self):
+        return len(self.bases)
+
+    def __getitem__(self, i):
+        return self.bases[i]
+
+    def __iter__(self):
+        return iter(self.bases)
+
+    def global_shape(self, forward_output=False):
+        return self._gshape_spec if forward_output else self._gshape_phys
+
+    def shape(self, forward_output=True):
+        """Local shape of this rank's block."""
+        if forward_output:
+            return self._local(self._gshape_spec, self._dist_spec)[0]
+        return self._local(self._gshape_phys, self._dist_phys)[0]
+
+    def local_shape(self, forward_output=True):
+        return self.shape(forward_output)
+
+    def local_slice(self, forward_output=True):
+        if forward_output:
+            shape, start = self._local(self._gshape_spec, self._dist_spec)
+        else:
+            shape, start = self._local(self._gshape_phys, self._dist_phys)
+        return tuple(slice(s, s+n) for s, n in zip(start, shape))
+
+    def dims(self):
+        return tuple(b.dim() for b in self.bases)
+
+    def dim(self):
+        return int(np.prod(self.dims()))
+
+    def size(self, forward_output=False):
+        return int(np.prod(self.shape(forward_output)))
+
+    def slice(self):
+        return tuple(b.slice() for b in self.bases)
+
+    def get_nonperiodic_axes(self):
+        return [i for i, b in enumerate(self.bases) if b.family() != 'fourier']
+
+    def get_nondiagonal_axes(self):
+        return self.get_nonperiodic_axes()
+
+    def is_orthogonal(self):
+        return all(getattr(b, 'is_orthogonal', True) for b in self.bases)
+
+    def destroy(self):
+        self._pool.buf = [None, None]
+        for sp in self._padded_space.values():
+            sp.destroy()
+
+    # ---- meshes and wavenumbers --------------------------------------------------------
+    def mesh(self, map_true_domain=True):
+        return [b.mesh(bcast=True, map_true_domain=map_true_domain) for b in self.bases]
+
+    def local_mesh(self, bcast=False, map_true_domain=True, device=False):
+        """tensorproductspace.py:950-983.  Host numpy arrays by default; device=True
+        gives float64 CUDA tensors (broadcastable) for on-device initialisation."""
+        sl = self.local_slice(False)
+        X = [x[tuple(s if i == ax else slice(None) for i in range(self.dimensions))]
+             for ax, (x, s) in enumerate(zip(self.mesh(map_true_domain), sl))]
+        if bcast:
+            X = [np.broadcast_to(x, self.shape(False)) for x in X]
+        if device:
+            X = [ops.as_device_tensor(np.ascontiguousarray(x)) for x in X]
+        return X
+
+    def wavenumbers(self, scaled=False, eliminate_highest_freq=False):
+        return [b.wavenumbers(bcast=True, scaled=scaled, eliminate_highest_freq=eliminate_highest_freq)
+                for b in self.bases]
+
+    def local_wavenumbers(self, broadcast=False, scaled=False, eliminate_highest_freq=False, device=False):
+        """tensorproductspace.py:1018-1052"""
+        sl = self.local_slice(True)
+        K = self.wavenumbers(scaled=scaled, eliminate_highest_freq=eliminate_highest_freq)
+        K = [k[tuple(s if i == ax else slice(None) for i in range(self.dimensions))]
+             for ax, (k, s) in enumerate(zip(K, sl))]
+        if broadcast:
+            K = [np.broadcast_to(k, self.shape(True)) for k in K]
+        if device:
+            K = [ops.as_device_tensor(np.ascontiguousarray(k, dtype=float)) for k in K]
+        return K
+
+    def get_mask_nyquist(self):
+        """tensorproductspace.py:1063-1076: product of the per-axis Nyquist masks (local)."""
+        sl = self.local_slice(True)
+        mask = None
+        for ax, b in enumerate(self.bases):
+            f = b.get_mask_nyquist(bcast=True)
+            if f is None:
+                continue
+            f = f[tuple(sl[ax] if i == ax else slice(None) for i in range(self.dimensions))]
+            mask = f if mask is None else mask*f
+        return mask
+
+    def mask_nyquist(self, u_hat, mask=None):
+        """Zero Nyquist coefficients in place (utilities/__init__.py:441-444 `apply_mask`)."""
+        if mask is None:
+            mask = self._device_mask()
+        if mask is not None:
+            t = ops.plain(u_hat)
+            if not isinstance(mask, torch.Tensor):
+                mask = ops.as_device_tensor(np.ascontiguousarray(mask, dtype=float))
+            t.mul_(mask)
+        return u_hat
+
+    def _device_mask(self):
+        if not hasattr(self, '_mask_dev'):
+            m = self.get_mask_nyquist()
+            self._mask_dev = None if m is None else ops.as_device_tensor(
+                np.ascontiguousarray(np.broadcast_to(m, self.shape(True)), dtype=float))
+        return self._mask_dev
+
+    # ---- derived spaces ----------------------------------------------------------------
+    def get_dealiased(self, padding_factor=1.5, dealias_direct=False):
+        """tensorproductspace.py:543-578: padded twin with the same spectral layout."""
+        if isinstance(padding_factor, (int, float)):
+            padding_factor = (padding_factor,)*len(self.bases)
+        padding_factor = tuple(float(p) for p in padding_factor)
+        key = (padding_factor, bool(dealias_direct))
+        if key in self._padded_space:
+            return self._padded_space[key]
+        if all(abs(p-1) < 1e-8 for p in padding_factor) and not dealias_direct:
+            return self
+        bases = [b.get_dealiased(padding_factor=p, dealias_direct=dealias_direct)
+                 for b, p in zip(self.bases, padding_factor)]
+        sp = TensorProductSpace(self.comm, bases, axes=self.axes, modify_spaces_inplace=True)
+        assert sp.shape(True) == self.shape(True)
+        self._padded_space[key] = sp
+        return sp
+
+    def get_unplanned(self, **kw):
+        return TensorProductSpace(self.comm, [b.get_unplanned(**kw) for b in self.bases], axes=self.axes)
+
+    def get_refined(self, N):
+        return TensorProductSpace(self.comm, [b.get_refined(n) for b, n in zip(self.bases, N)], axes=self.axes)
+
+    def get_orthogonal(self):
+        return TensorProductSpace(self.comm, [b.get_orthogonal() for b in self.bases], axes=self.axes)
+
+
+class CompositeSpace:
+    """Product of tensor-product spaces (tensorproductspace.py:1190-1560).
+
+    Components must share local shapes so that the component index can be folded
+    into the batch extent of every axis kernel.
+    """
+
+    def __init__(self, spaces):
+        self.spaces = list(spaces)
+        s0 = self.flatten()[0]
+        for s in self.flatten():
+            if s.shape(True) != s0.shape(True) or s.shape(False) != s0.shape(False):
+                raise NotImplementedError('components with different shapes')
+        self.comm = s0.comm
+        self._padded_space = {}
+        self.forward = _CompositeTransform(self, 'forward')
+        self.backward = _CompositeTransform(self, 'backward')
+        self.scalar_product = _CompositeTransform(self, 'scalar_product')
+
+    @property
+    def physical_dtype(self):
+        return self.flatten()[0].physical_dtype
+
+    @property
+    def spectral_dtype(self):
+        return self.flatten()[0].spectral_dtype
+
+    @property
+    def dimensions(self):
+        return self.flatten()[0].dimensions
+
+    @property
+    def rank(self):
+        return 1
+
+    @property
+    def is_composite_space(self):
+        return 1
+
+    @property
+    def tensor_rank(self):
+        return 1
+
+    def num_components(self):
+        return len(self.flatten())
+
+    def flatten(self):
+        out = []
+        for s in self.spaces:
+            out.extend(s.flatten())
+        return out
+
+    def __getitem__(self, i):
+        return self.spaces[i]
+
+    def __len__(self):
+        return len(self.spaces)
+
+    def __iter__(self):
+        return iter(self.spaces)
+
+    def _lead(self):
+        return (len(self.spaces),)
+
+    def shape(self, forward_output=True):
+        return self._lead() + tuple(self.spaces[0].shape(forward_output))
+
+    def local_shape(self, forward_output=True):
+        return self.shape(forward_output)
+
+    def global_shape(self, forward_output=False):
+        return self._lead() + tuple(self.spaces[0].global_shape(forward_output))
+
+    def local_slice(self, forward_output=True):
+        return tuple(slice(0, n) for n in self._lead()) + tuple(self.flatten()[0].local_slice(forward_output))
+
+    def local_mesh(self, *a, **k):
+        return self.flatten()[0].local_mesh(*a, **k)
+
+    def mesh(self, *a, **k):
+        return self.flatten()[0].mesh(*a, **k)
+
+    def local_wavenumbers(self, *a, **k):
+        return self.flatten()[0].local_wavenumbers(*a, **k)
+
+    def get_mask_nyquist(self):
+        return self.flatten()[0].get_mask_nyquist()
+
+    def mask_nyquist(self, u_hat, mask=None):
+        return self.flatten()[0].mask_nyquist(u_hat, mask)
+
+    def get_dealiased(self, padding_factor=1.5, dealias_direct=False):
+        key = (str(padding_factor), bool(dealias_direct))
+        if key not in self._padded_space:
+            cache = {}
+            new = []
+            for s in self.spaces:
+                if id(s) not in cache:
+                    cache[id(s)] = s.get_dealiased(padding_factor, dealias_direct)
+                new.append(cache[id(s)])
+            self._padded_space[key] = type(self)(new) if type(self) is CompositeSpace else type(self)(new[0])
+        return self._padded_space[key]
+
+    def get_orthogonal(self):
+        return type(self)([s.get_orthogonal() for s in self.spaces]) if type(self) is CompositeSpace \
+            else type(self)(self.spaces[0].get_orthogonal())
+
+    def destroy(self):
+        for s in self.flatten():
+            s.destroy()
+
+
+class _CompositeTransform:
+    """Batched transform of all components (replaces the per-component loop of
+    `VectorTransform.__call__`, tensorproductspace.py:1786-1795)."""
+
+    def __init__(self, space, direction):
+        self.space = space
+        self.direction = direction
+
+    def __call__(self, input_array, output_array=None, kind=None, **kw):
+        space = self.space
+        fo = self.direction != 'backward'
+        if output_array is None:
+            output_array = Function(space) if fo else Array(space)
+        flat = space.flatten()
+        same = all(s is flat[0] for s in flat)
+        if same:
+            getattr(flat[0], self.direction)(input_array, output_array, kind=kind)
+        else:
+            u = ops.plain(input_array) if isinstance(input_array, torch.Tensor) else input_array
+            out = ops.plain(output_array)
+            ncomp = len(flat)
+            u = u.reshape((ncomp,) + tuple(u.shape[-space.dimensions:]))
+            out_v = out.view((ncomp,) + tuple(out.shape[-space.dimensions:]))
+            for i, s in enumerate(flat):
+                getattr(s, self.direction)(u[i], out_v[i], kind=kind)
+        return output_array
+
+
+class VectorSpace(CompositeSpace):
+    """`ndim` copies of one scalar space (tensorproductspace.py:1563-1650)."""
+
+    def __init__(self, space):
+        if isinstance(space, (list, tuple)):
+            spaces = list(space)
+        else:
+            spaces = [space]*space.dimensions
+        CompositeSpace.__init__(self, spaces)
+
+    def get_dealiased(self, padding_factor=1.5, dealias_direct=False):
+        key = (str(padding_factor), bool(dealias_direct))
+        if key not in self._padded_space:
+            if all(s is self.spaces[0] for s in self.spaces):
+                self._padded_space[key] = VectorSpace(self.spaces[0].get_dealiased(padding_factor, dealias_direct))
+            else:
+                self._padded_space[key] = VectorSpace([s.get_dealiased(padding_factor, dealias_direct)
+                                                       for s in self.spaces])
+        return self._padded_space[key]
+
+
+class TensorSpace(CompositeSpace):
+    """ndim x ndim copies of one scalar space (tensorproductspace.py:1652-1784)."""
+
+    def __init__(self, space):
+        self._scalar = space
+        nd = space.dimensions
+        CompositeSpace.__init__(self, [space]*(nd*nd))
+
+    @property
+    def rank(self):
+        return 2
+
+    @property
+    def tensor_rank(self):
+        return 2
+
+    def _lead(self):
+        nd = self._scalar.dimensions
+        return (nd, nd)
+
+    def get_dealiased(self, padding_factor=1.5, dealias_direct=False):
+        key = (str(padding_factor), bool(dealias_direct))
+        if key not in self._padded_space:
+            self._padded_space[key] = TensorSpace(self._scalar.get_dealiased(padding_factor, dealias_direct))
+        return self._padded_space[key]

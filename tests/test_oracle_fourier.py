@@ -1,0 +1,34 @@
+"""Pin the numpy oracle (oracle/fourier.py, oracle/tensorproduct.py) against the
+golden vectors produced by the reference's own sources (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l2
+from oracle import tensorproduct as otp
+
+CASES = ['f3d_14_15_16', 'f3d_16_16_16', 'f3d_12_9_10', 'f2d_16_12', 'f2d_c_10_12']
+TOL = 1e-14
+
+
+def descs(g, pf=1.0):
+    N = g['N']
+    dts = str(g['dtypes'])
+    return [('C2C' if dt == 'D' else 'R2C', int(n), int(np.floor(pf*n))) for n, dt in zip(N, dts)]
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_forward_backward_match_reference(name):
+    g = load_golden(name)
+    d = descs(g)
+    assert rel_l2(otp.forward(g['u'], d), g['u_hat']) < TOL
+    assert rel_l2(otp.backward(g['v_hat'], d), g['v']) < TOL
+
+
+@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('pf', [1.5, 2.0])
+def test_padded_match_reference(name, pf):
+    g = load_golden(name)
+    tag = str(pf).replace('.', '')
+    d = descs(g, pf)
+    assert rel_l2(otp.backward(g['v_hat'], d), g[f'v_pad{tag}']) < TOL
+    assert rel_l2(otp.forward(g[f'w_pad{tag}'], d), g[f'w_hat_pad{tag}']) < TOL
