@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- 512^3 fp64 forward+backward transform pairs/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one TensorProductSpace.forward + one .backward of a 512^3 real
+field on T = C2C(512) x C2C(512) x R2C(512)  (SURVEY.md 8d, M1).  At N > 1 the
+same global 512^3 problem is slab-distributed over the ranks (strong scaling),
+one process per GPU, NCCL all-to-all between the axis passes.
+
+The JSON line also carries: `e2e` (same pair through the public API from/to
+pinned HOST buffers), `roofline` of the dominant kernel (live CUDA-event
+timing), `cpu_baseline` (the numpy/scipy oracle on this box's host cores),
+and secondary workloads (`padded_pair`, `ns`) as extra keys.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = (512, 512, 512)
+METRIC = '512^3 fp64 fwd+bwd transform pairs/s'
+# algorithmic bytes of one un-padded 512^3 pair: 3 axis passes each way
+REAL_B = 512**3*8
+SPEC_B = 512*512*257*16
+PAIR_BYTES = 2*((REAL_B+SPEC_B) + 2*(2*SPEC_B))
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return json.load(open(p)).get('hbm_gbs', 6650.0), 'measured'
+    return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_pair_time(shape, reps, workers):
+    """The oracle port (numpy + scipy.fft) of the same pair on host cores."""
+    from oracle import tensorproduct as otp
+    from oracle import fourier as of
+    of.WORKERS = workers
+    d = [('C2C', shape[0], shape[0]), ('C2C', shape[1], shape[1]), ('R2C', shape[2], shape[2])]
+    u = np.random.default_rng(1234).standard_normal(shape)
+    uh = otp.forward(u, d)
+    otp.backward(uh, d)          # warm-up (pocketfft plan cache, page faults)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        uh = otp.forward(u, d)
+        otp.backward(uh, d)
+    return (time.perf_counter()-t0)/reps
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port: the reference's Python
+    cannot travel to the GPU box and its FFTW/mpi4py-fft stack is absent) on host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    times = []
+    for i in range(args.warmup+args.steps):
+        t = cpu_pair_time(SHAPE, 1, cores)
+        if i >= args.warmup:
+            times.append(t)
+    ms = 1e3*float(np.mean(times))
+    val = 1e3/ms
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'pairs/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'TensorProductSpace(C2C(512),C2C(512),R2C(512)) forward+backward, 512^3 real fp64',
+                   'global_shape': list(SHAPE)},
+        'cpu_baseline': {'value': val, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+                         'sample': 'one full 512^3 forward+backward pair per step, scipy.fft (pocketfft) '
+                                   f'workers={cores}, oracle/tensorproduct.py'},
+        'e2e': {'value': val, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-extras', action='store_true', help='skip secondary workloads')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import shenfun_b200 as sf
+    from shenfun_b200 import ops
+
+    comm = sf.init_from_env('nccl')
+    world = comm.Get_size()
+    rank = comm.Get_rank()
+    if world == 1:
+        torch.cuda.set_device(0)
+    dev = torch.device('cuda', torch.cuda.current_device())
+
+    bases = [sf.FunctionSpace(SHAPE[0], 'F', dtype='D'), sf.FunctionSpace(SHAPE[1], 'F', dtype='D'),
+             sf.FunctionSpace(SHAPE[2], 'F', dtype='d')]
+    T = sf.TensorProductSpace(comm, bases)
+    g = torch.Generator(device=dev).manual_seed(1234+rank)
+    u = sf.Array(T)
+    u.v.copy_(torch.randn(T.shape(False), dtype=torch.float64, device=dev, generator=g))
+    uh = sf.Function(T)
+    ub = sf.Array(T)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        T.forward(u, uh)
+        T.backward(uh, ub)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    l0 = ops.LAUNCHES
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES-l0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()/args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # parity guard inside the bench (cheap): round trip must reproduce the input
+    rt = (torch.linalg.vector_norm(ub.v-u.v)/torch.linalg.vector_norm(u.v)).item()
+
+    # ---- e2e: host pinned -> device -> forward -> backward -> host pinned ---------
+    h_in = torch.empty(T.shape(False), dtype=torch.float64).pin_memory()
+    h_in.copy_(u.v)
+    h_out = torch.empty(T.shape(False), dtype=torch.float64).pin_memory()
+    d_in = sf.Array(T)
+
+    def e2e_step():
+        d_in.v.copy_(h_in, non_blocking=True)
+        T.forward(d_in, uh)
+        T.backward(uh, ub)
+        h_out.copy_(ub.v, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    n_e2e = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item()/n_e2e
+
+    # ---- roofline of the dominant kernel (live CUDA events around single launches) --
+    peak, peak_src = peaks()
+    roof = None
+    if world == 1:
+        roof = dominant_kernel_roofline(T, u, uh, peak, peak_src)
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = secondary_workloads(T, uh, args, peak)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        tcpu = cpu_pair_time(SHAPE, 1, cores)
+        cpu = {'value': 1.0/tcpu, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+               'sample': f'1 full 512^3 forward+backward pair (after 1 warm-up pair), scipy.fft workers={cores}, '
+                         'oracle/tensorproduct.py'}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': 1e3/ms, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'TensorProductSpace(C2C(512),C2C(512),R2C(512)) forward+backward, 512^3 real fp64',
+                       'global_shape': list(SHAPE), 'decomposition': 'slab' if world > 1 else 'single',
+                       'l2_policy': 'working set 2.15 GB per pass >> 126 MB L2 (no flush needed)',
+                       'seed': 1234},
+            'pair_hbm_frac_of_measured': (PAIR_BYTES/world/(ms*1e-3)/1e9)/peak,
+            'roundtrip_rel_err': rt,
+            'clocks': clocks,
+            'e2e': {'value': 1e3/e2e_ms, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(np.prod(T.shape(False)))*8,
+                    'd2h_bytes_per_step': int(np.prod(T.shape(False)))*8, 'ms_per_step': e2e_ms},
+            'gpu_launches': launches,
+            'roofline': roof,
+            'cpu_baseline': cpu,
+        }
+        line.update(extras)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _time_launch(fn, reps=10):
+    import torch
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)/reps
+
+
+def dominant_kernel_roofline(T, u, uh, peak, peak_src):
+    """Per-stage timing of the forward plan; the slowest axis pass is reported."""
+    import torch
+    from shenfun_b200 import ops
+    stages = {}
+    w = torch.empty(T.shape(True), dtype=torch.complex128, device=u.device)
+    b2, b1, b0 = T.bases[2], T.bases[1], T.bases[0]
+    stages['r2c_axis2'] = (_time_launch(lambda: b2._forward_axis(u.v, w, 512*512, 1)), REAL_B+SPEC_B)
+    stages['c2c_axis1'] = (_time_launch(lambda: b1._forward_axis(w, w, 512, 257)), 2*SPEC_B)
+    stages['c2c_axis0'] = (_time_launch(lambda: b0._forward_axis(w, w, 1, 512*257)), 2*SPEC_B)
+    name = max(stages, key=lambda k: stages[k][0])
+    ms, nbytes = stages[name]
+    ach = nbytes/(ms*1e-3)/1e9
+    return {'bound': 'hbm', 'kernel': name, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach/peak,
+            'peak_source': peak_src, 'traffic': None, 'algorithmic_bytes_per_launch': nbytes,
+            'avg_launch_ms': ms,
+            'all_stages_gbs': {k: v[1]/(v[0]*1e-3)/1e9 for k, v in stages.items()}}
+
+
+def secondary_workloads(T, uh, args, peak):
+    """3/2-padded pair (S 512x512x257 <-> P 768^3), reported beside the headline."""
+    import torch
+    import shenfun_b200 as sf
+    out = {}
+    try:
+        Tp = T.get_dealiased((1.5, 1.5, 1.5))
+        up = sf.Array(Tp)
+        wh = sf.Function(T)
+
+        def step():
+            Tp.backward(uh, up)
+            Tp.forward(up, wh)
+        ms = _time_launch(step, reps=max(3, args.steps//2))
+        pad_bytes = 2*((SPEC_B+1.5*SPEC_B) + (1.5*SPEC_B+2.25*SPEC_B) + (2.25*SPEC_B+768**3*8))
+        out['padded_pair'] = {'value': 1e3/ms, 'unit': 'pairs/s', 'ms_per_step': ms,
+                              'hbm_frac_of_measured': pad_bytes/(ms*1e-3)/1e9/peak,
+                              'workload': 'S 512x512x257 <-> P 768^3 (3/2 rule), backward+forward'}
+        del up, wh
+        Tp.destroy()
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out['padded_pair'] = {'error': repr(e)}
+    try:
+        from shenfun_b200.demos import navier_stokes
+        out['ns'] = navier_stokes.bench(512, steps=max(2, min(args.steps, 5)), warmup=1)
+    except ImportError:
+        pass
+    except Exception as e:  # noqa: BLE001
+        out['ns'] = {'error': repr(e)}
+    return out
+
+
+if __name__ == '__main__':
+    main()
