@@ -14,13 +14,13 @@ static int dispatch(int mode, const void *in, void *out, int64_t outer, int64_t 
     }
     if ((flags & 1) && N != n_fft) { set_error("fft: dealias_direct requires N == n_fft"); return SHB_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (in == out && !(N == n_fft && (mode == FFT_C2C_FWD || mode == FFT_C2C_BWD))) {
+        set_error("fft: in-place only for unpadded c2c"); return SHB_ERR_ARG;
+    }
     static const bool force_generic = getenv("SHB_FFT_FORCE_GENERIC") != nullptr;
     if (!force_generic) {
         int rc = fft_fast_launch(mode, in, out, outer, inner, n_fft, N, scale, flags, st);
         if (rc != SHB_ERR_UNSUPPORTED) return rc;
-    }
-    if (in == out && !(N == n_fft && (mode == FFT_C2C_FWD || mode == FFT_C2C_BWD))) {
-        set_error("fft: in-place only for unpadded c2c"); return SHB_ERR_ARG;
     }
     return fft_generic_launch(mode, in, out, outer, inner, n_fft, N, scale, flags, st);
 }

@@ -1,11 +1,445 @@
-// fft_fast.cu -- register-resident Stockham kernels for the headline sizes
-// (placeholder until the first parity run; see fft_generic.cu)
+// fft_fast.cu -- register-resident Stockham FFT kernels for the headline sizes.
+//
+// A line of M = R0*R1[*R2] complex points is transformed by P = max(M/Ri)
+// threads; each thread runs at most one radix-Ri butterfly per stage with the
+// Ri operands in registers.  Stage 0 reads its operands straight from global
+// memory (fused zero-padding / Hermitian pre-twiddle), the last stage writes
+// straight to global memory (fused truncation / Nyquist rules / scaling / real
+// split), so data crosses shared memory only for the (stages-1) exchanges.
+//
+//   kernel A (fft_strided_kernel): transform axis is strided ([outer][M][inner],
+//     inner > 1).  A CTA owns T consecutive columns; lanes run along the
+//     contiguous `inner` index so every global access is a T*16 B segment and
+//     the [pos][column] shared layout is bank-conflict free by construction.
+//   kernel B (fft_contig_kernel): lines are contiguous (inner == 1): C2C, R2C
+//     (half-length complex FFT + split) and C2R.  Lanes run along the line;
+//     shared positions are skewed (pos + pos/8) against bank conflicts.
+//
+// Reference semantics: see fft_generic.cu (same C ABI, same results).
 #include "fft_common.cuh"
+#include "butterfly.cuh"
 
 namespace shb {
 
-int fft_fast_launch(int, const void *, void *, int64_t, int64_t, int, int, double, int, cudaStream_t) {
-    return SHB_ERR_UNSUPPORTED;
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+template <int M_, int R0_, int R1_, int R2_>
+struct Sched {
+    static constexpr int M = M_, R0 = R0_, R1 = R1_, R2 = R2_;
+    static_assert(R0_ * R1_ * R2_ == M_, "radices must multiply to M");
+    static constexpr int NST = (R2_ > 1) ? 3 : 2;
+    static constexpr int NB0 = M / R0, NB1 = M / R1, NB2 = (R2_ > 1) ? M / R2 : 0;
+    static constexpr int P = cmax(NB0, cmax(NB1, NB2));
+    static constexpr int RMAX = cmax(R0, cmax(R1, R2));
+    static constexpr int RL = (NST == 3) ? R2 : R1;     // radix of the last stage
+    static constexpr int NBL = (NST == 3) ? NB2 : NB1;  // butterflies in the last stage
+};
+
+// Stages after the operands of stage 0 are in v[0..R0).  On return the thread
+// (if j < NBL) holds X[j + m*NBL], m < RL, in v.  `S` maps a line position to
+// shared memory for this thread's line.
+template <class SC, bool INV, class S>
+__device__ __forceinline__ void fft_stages(cplx *v, const int j, S s, const cplx *__restrict__ tw) {
+    constexpr int R0 = SC::R0, R1 = SC::R1, R2 = SC::R2, M = SC::M;
+    if (j < SC::NB0) {
+        Bfly<R0, INV>::run(v);
+#pragma unroll
+        for (int m = 0; m < R0; ++m) s(j * R0 + m) = v[m];
+    }
+    __syncthreads();
+    if (j < SC::NB1) {
+#pragma unroll
+        for (int m = 0; m < R1; ++m) v[m] = s(j + m * SC::NB1);
+        const int k = j % R0;
+#pragma unroll
+        for (int m = 1; m < R1; ++m) {
+            const cplx w = __ldg(&tw[k * m * R2]);
+            v[m] = INV ? cmulc(v[m], w) : cmul(v[m], w);
+        }
+        Bfly<R1, INV>::run(v);
+    }
+    if constexpr (SC::NST == 3) {
+        __syncthreads();
+        if (j < SC::NB1) {
+            const int k = j % R0;
+            const int j0 = (j / R0) * (R0 * R1) + k;
+#pragma unroll
+            for (int m = 0; m < R1; ++m) s(j0 + m * R0) = v[m];
+        }
+        __syncthreads();
+        if (j < SC::NB2) {
+#pragma unroll
+            for (int m = 0; m < R2; ++m) v[m] = s(j + m * SC::NB2);
+#pragma unroll
+            for (int m = 1; m < R2; ++m) {
+                const cplx w = __ldg(&tw[j * m]);
+                v[m] = INV ? cmulc(v[m], w) : cmul(v[m], w);
+            }
+            Bfly<R2, INV>::run(v);
+        }
+    }
+}
+
+struct FastDesc {
+    const void *in;
+    void *out;
+    int64_t outer, inner, nlines;
+    int n_fft, N, n_in, n_out, flags;
+    double scale;
+    const cplx *tw, *tw2;
+};
+
+// ---- kernel A ---------------------------------------------------------------------
+template <class SC, int MODE, int T>
+__global__ void __launch_bounds__(SC::P *T) fft_strided_kernel(const __grid_constant__ FastDesc d) {
+    constexpr bool INV = (MODE == FFT_C2C_BWD);
+    constexpr int M = SC::M;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *sm = reinterpret_cast<cplx *>(smem_raw);
+    const int c = threadIdx.x % T;
+    const int j = threadIdx.x / T;
+    const int64_t line = (int64_t)blockIdx.x * T + c;
+    const bool valid = line < d.nlines;
+    const int64_t o = valid ? line / d.inner : 0, cc = valid ? line % d.inner : 0;
+    const int64_t stride = d.inner;
+    const cplx *__restrict__ in = reinterpret_cast<const cplx *>(d.in) + (o * d.n_in * d.inner + cc);
+    cplx *__restrict__ out = reinterpret_cast<cplx *>(d.out) + (o * d.n_out * d.inner + cc);
+    const int N = d.N;
+    const bool padded = (N < M);
+    const bool evenN = (N % 2 == 0);
+    const int h = N / 2;
+
+    cplx v[SC::RMAX];
+    if (j < SC::NB0) {
+#pragma unroll
+        for (int m = 0; m < SC::R0; ++m) {
+            const int r = j + m * SC::NB0;
+            cplx x = make_double2(0.0, 0.0);
+            if (valid) {
+                if (MODE == FFT_C2C_FWD) {
+                    x = in[(int64_t)r * stride];
+                } else if (!padded) {
+                    x = in[(int64_t)r * stride];
+                    if ((d.flags & 1) && r >= N / 3 && r <= N - N / 3) x = make_double2(0.0, 0.0);
+                } else {
+                    if (r <= h) {
+                        x = in[(int64_t)r * stride];
+                        if (evenN && r == h) x = cscale(x, 0.5);
+                    } else if (r >= M - h) {
+                        x = in[(int64_t)(r - M + N) * stride];
+                        if (evenN && r == M - h) x = cscale(x, 0.5);
+                    }
+                }
+            }
+            v[m] = x;
+        }
+    }
+    auto s = [&](int pos) -> cplx & { return sm[pos * T + c]; };
+    fft_stages<SC, INV>(v, j, s, d.tw);
+
+    const double scale = d.scale;
+    if (MODE == FFT_C2C_FWD && padded && evenN) {
+        // fold X[M-h] into row h: pass it through shared memory (one value per column)
+        __syncthreads();
+        if (j < SC::NBL) {
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m)
+                if (j + m * SC::NBL == M - h) sm[c] = v[m];
+        }
+        __syncthreads();
+    }
+    if (j < SC::NBL && valid) {
+#pragma unroll
+        for (int m = 0; m < SC::RL; ++m) {
+            const int r = j + m * SC::NBL;
+            if (MODE == FFT_C2C_BWD || !padded) {
+                out[(int64_t)r * stride] = cscale(v[m], scale);
+            } else {
+                if (r <= h) {
+                    cplx x = v[m];
+                    if (evenN && r == h) x = cadd(x, sm[c]);
+                    out[(int64_t)r * stride] = cscale(x, scale);
+                } else if (r > M - h || (!evenN && r == M - h)) {
+                    out[(int64_t)(r - M + N) * stride] = cscale(v[m], scale);
+                }
+            }
+        }
+    }
+}
+
+// ---- kernel B ---------------------------------------------------------------------
+__device__ __forceinline__ int skew(int pos) { return pos + (pos >> 3); }
+
+template <class SC, int MODE, int TL>
+__global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_constant__ FastDesc d) {
+    constexpr bool INV = (MODE == FFT_C2C_BWD || MODE == FFT_C2R);
+    constexpr int M = SC::M;
+    constexpr int LP = M + (M >> 3) + 2;        // shared pitch of one line
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int j = threadIdx.x % SC::P;
+    const int l = threadIdx.x / SC::P;
+    cplx *sm = reinterpret_cast<cplx *>(smem_raw) + (size_t)l * LP;
+    const int64_t line = (int64_t)blockIdx.x * TL + l;
+    const bool valid = line < d.nlines;
+    const int N = d.N;
+    const int n_fft = d.n_fft;
+    const bool padded = (N < n_fft);
+    const bool evenN = (N % 2 == 0);
+    const int h = N / 2;
+    const double scale = d.scale;
+    auto s = [&](int pos) -> cplx & { return sm[skew(pos)]; };
+
+    cplx v[SC::RMAX];
+    if (MODE == FFT_C2C_FWD || MODE == FFT_C2C_BWD) {
+        const cplx *__restrict__ in = reinterpret_cast<const cplx *>(d.in) + line * d.n_in;
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m) {
+                const int r = j + m * SC::NB0;
+                cplx x = make_double2(0.0, 0.0);
+                if (valid) {
+                    if (MODE == FFT_C2C_FWD) x = in[r];
+                    else if (!padded) {
+                        x = in[r];
+                        if ((d.flags & 1) && r >= N / 3 && r <= N - N / 3) x = make_double2(0.0, 0.0);
+                    } else if (r <= h) {
+                        x = in[r];
+                        if (evenN && r == h) x = cscale(x, 0.5);
+                    } else if (r >= M - h) {
+                        x = in[r - M + N];
+                        if (evenN && r == M - h) x = cscale(x, 0.5);
+                    }
+                }
+                v[m] = x;
+            }
+        }
+    } else if (MODE == FFT_R2C) {
+        const double2 *__restrict__ in = reinterpret_cast<const double2 *>(
+            reinterpret_cast<const double *>(d.in) + line * (int64_t)n_fft);
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m)
+                v[m] = valid ? in[j + m * SC::NB0] : make_double2(0.0, 0.0);
+        }
+    } else {   // FFT_C2R: stage the stored modes, then build Y[n] = (X[n]+conj X[M-n]) + i e^{+i pi n/M}(X[n]-conj X[M-n])
+        const cplx *__restrict__ in = reinterpret_cast<const cplx *>(d.in) + line * d.n_in;
+        const int ns = h + 1;
+        for (int k = j; k <= M; k += SC::P) {
+            cplx x = make_double2(0.0, 0.0);
+            if (valid && k < ns) {
+                x = in[k];
+                if ((d.flags & 1) && !padded && k >= N / 3) x = make_double2(0.0, 0.0);
+                if (padded && evenN && k == ns - 1) x = make_double2(0.5 * x.x, 0.0);
+            }
+            if (k == 0 || k == M) x.y = 0.0;
+            s(k) = x;
+        }
+        __syncthreads();
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m) {
+                const int n = j + m * SC::NB0;
+                const cplx xk = s(n), xc = cconj(s(M - n));
+                const cplx sum = cadd(xk, xc), df = csub(xk, xc);
+                const cplx w = __ldg(&d.tw2[n]);               // e^{-i pi n / M}
+                const cplx iw = make_double2(w.y, w.x);        // i * conj(w)
+                v[m] = cadd(sum, cmul(iw, df));
+            }
+        }
+        __syncthreads();
+    }
+
+    fft_stages<SC, INV>(v, j, s, d.tw);
+
+    if (MODE == FFT_C2C_BWD || (MODE == FFT_C2C_FWD && !padded)) {
+        cplx *__restrict__ out = reinterpret_cast<cplx *>(d.out) + line * d.n_out;
+        if (j < SC::NBL && valid) {
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) out[j + m * SC::NBL] = cscale(v[m], scale);
+        }
+    } else if (MODE == FFT_C2C_FWD) {
+        cplx *__restrict__ out = reinterpret_cast<cplx *>(d.out) + line * d.n_out;
+        if (evenN) {
+            __syncthreads();
+            if (j < SC::NBL) {
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m)
+                    if (j + m * SC::NBL == M - h) sm[0] = v[m];
+            }
+            __syncthreads();
+        }
+        if (j < SC::NBL && valid) {
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) {
+                const int r = j + m * SC::NBL;
+                if (r <= h) {
+                    cplx x = v[m];
+                    if (evenN && r == h) x = cadd(x, sm[0]);
+                    out[r] = cscale(x, scale);
+                } else if (r > M - h || (!evenN && r == M - h)) {
+                    out[r - M + N] = cscale(v[m], scale);
+                }
+            }
+        }
+    } else if (MODE == FFT_R2C) {
+        // X[k] = E + e^{-i pi k/M} O,  E = (Z[k]+conj Z[M-k])/2,  O = -i (Z[k]-conj Z[M-k])/2
+        cplx *__restrict__ out = reinterpret_cast<cplx *>(d.out) + line * d.n_out;
+        __syncthreads();
+        if (j < SC::NBL) {
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) s(j + m * SC::NBL) = v[m];
+        }
+        __syncthreads();
+        if (j < SC::NBL && valid) {
+            const int ns = h + 1;
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) {
+                const int k = j + m * SC::NBL;
+                if (k < ns) {
+                    const cplx zk = v[m];
+                    const cplx zc = cconj(s(k == 0 ? 0 : M - k));
+                    const cplx e = cscale(cadd(zk, zc), 0.5);
+                    const cplx df = cscale(csub(zk, zc), 0.5);
+                    const cplx o_ = make_double2(df.y, -df.x);
+                    const cplx w = __ldg(&d.tw2[k]);
+                    cplx x = cadd(e, cmul(w, o_));
+                    if (padded && evenN && k == h) x = make_double2(2.0 * x.x, 0.0);
+                    out[k] = cscale(x, scale);
+                }
+            }
+            if (j == 0 && ns - 1 == M) {    // un-padded Nyquist: X[M] = Re Z0 - Im Z0
+                const cplx z0 = v[0];
+                out[M] = make_double2((z0.x - z0.y) * scale, 0.0);
+            }
+        }
+    } else {   // FFT_C2R
+        double2 *__restrict__ out = reinterpret_cast<double2 *>(
+            reinterpret_cast<double *>(d.out) + line * (int64_t)n_fft);
+        if (j < SC::NBL && valid) {
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) out[j + m * SC::NBL] = cscale(v[m], scale);
+        }
+    }
+}
+
+// ---- host-side dispatch ---------------------------------------------------------------
+template <class SC, int MODE, int T>
+static int launch_strided(const FastDesc &d, cudaStream_t st) {
+    constexpr size_t smem = (size_t)SC::M * T * sizeof(cplx);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SHB_CUDA(cudaFuncSetAttribute(fft_strided_kernel<SC, MODE, T>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int64_t ntiles = (d.nlines + T - 1) / T;
+    fft_strided_kernel<SC, MODE, T><<<(unsigned)ntiles, SC::P * T, smem, st>>>(d);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+template <class SC, int MODE, int TL>
+static int launch_contig(const FastDesc &d, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(SC::M + (SC::M >> 3) + 2) * TL * sizeof(cplx);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SHB_CUDA(cudaFuncSetAttribute(fft_contig_kernel<SC, MODE, TL>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int64_t ntiles = (d.nlines + TL - 1) / TL;
+    fft_contig_kernel<SC, MODE, TL><<<(unsigned)ntiles, SC::P * TL, smem, st>>>(d);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+// Schedules.  Backward (zero-padded input) puts the widest radix first so the
+// all-zero operands are never loaded; forward (truncated output) puts it last.
+#define SHB_STRIDED_CASES(MODE, FIRSTWIDE)                                                          \
+    switch (M) {                                                                                    \
+    case 64:   return launch_strided<Sched<64, 8, 8, 1>, MODE, 8>(d, st);                           \
+    case 128:  return launch_strided<Sched<128, 8, 4, 4>, MODE, 8>(d, st);                          \
+    case 256:  return launch_strided<Sched<256, 8, 8, 4>, MODE, 8>(d, st);                          \
+    case 512:  return launch_strided<Sched<512, 8, 8, 8>, MODE, 8>(d, st);                          \
+    case 1024: return launch_strided<Sched<1024, 16, 8, 8>, MODE, 4>(d, st);                        \
+    case 96:   return FIRSTWIDE ? launch_strided<Sched<96, 12, 8, 1>, MODE, 8>(d, st)               \
+                                : launch_strided<Sched<96, 8, 12, 1>, MODE, 8>(d, st);              \
+    case 192:  return FIRSTWIDE ? launch_strided<Sched<192, 6, 8, 4>, MODE, 8>(d, st)               \
+                                : launch_strided<Sched<192, 4, 8, 6>, MODE, 8>(d, st);              \
+    case 384:  return FIRSTWIDE ? launch_strided<Sched<384, 6, 8, 8>, MODE, 8>(d, st)               \
+                                : launch_strided<Sched<384, 8, 8, 6>, MODE, 8>(d, st);              \
+    case 768:  return FIRSTWIDE ? launch_strided<Sched<768, 12, 8, 8>, MODE, 8>(d, st)              \
+                                : launch_strided<Sched<768, 8, 8, 12>, MODE, 8>(d, st);             \
+    case 1536: return FIRSTWIDE ? launch_strided<Sched<1536, 12, 16, 8>, MODE, 4>(d, st)            \
+                                : launch_strided<Sched<1536, 8, 16, 12>, MODE, 4>(d, st);           \
+    case 1152: return launch_strided<Sched<1152, 12, 12, 8>, MODE, 4>(d, st);                       \
+    default: return SHB_ERR_UNSUPPORTED;                                                            \
+    }
+
+#define SHB_CONTIG_CASES(MODE)                                                                      \
+    switch (M) {                                                                                    \
+    case 32:   return launch_contig<Sched<32, 8, 4, 1>, MODE, 16>(d, st);                           \
+    case 64:   return launch_contig<Sched<64, 8, 8, 1>, MODE, 16>(d, st);                           \
+    case 128:  return launch_contig<Sched<128, 16, 8, 1>, MODE, 16>(d, st);                         \
+    case 256:  return launch_contig<Sched<256, 16, 16, 1>, MODE, 16>(d, st);                        \
+    case 512:  return launch_contig<Sched<512, 8, 8, 8>, MODE, 4>(d, st);                           \
+    case 1024: return launch_contig<Sched<1024, 16, 8, 8>, MODE, 2>(d, st);                         \
+    case 48:   return launch_contig<Sched<48, 6, 8, 1>, MODE, 16>(d, st);                           \
+    case 96:   return launch_contig<Sched<96, 12, 8, 1>, MODE, 16>(d, st);                          \
+    case 192:  return launch_contig<Sched<192, 12, 16, 1>, MODE, 16>(d, st);                        \
+    case 384:  return launch_contig<Sched<384, 6, 8, 8>, MODE, 4>(d, st);                           \
+    case 768:  return launch_contig<Sched<768, 12, 8, 8>, MODE, 2>(d, st);                          \
+    case 576:  return launch_contig<Sched<576, 6, 12, 8>, MODE, 4>(d, st);                          \
+    default: return SHB_ERR_UNSUPPORTED;                                                            \
+    }
+
+static int strided_fwd(int M, const FastDesc &d, cudaStream_t st) { SHB_STRIDED_CASES(FFT_C2C_FWD, false) }
+static int strided_bwd(int M, const FastDesc &d, cudaStream_t st) { SHB_STRIDED_CASES(FFT_C2C_BWD, true) }
+static int contig_c2c_fwd(int M, const FastDesc &d, cudaStream_t st) { SHB_CONTIG_CASES(FFT_C2C_FWD) }
+static int contig_c2c_bwd(int M, const FastDesc &d, cudaStream_t st) { SHB_CONTIG_CASES(FFT_C2C_BWD) }
+static int contig_r2c(int M, const FastDesc &d, cudaStream_t st) { SHB_CONTIG_CASES(FFT_R2C) }
+static int contig_c2r(int M, const FastDesc &d, cudaStream_t st) { SHB_CONTIG_CASES(FFT_C2R) }
+
+int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner,
+                    int n_fft, int N, double scale, int flags, cudaStream_t st) {
+    FastDesc d;
+    d.in = in; d.out = out; d.outer = outer; d.inner = inner; d.nlines = outer * inner;
+    d.n_fft = n_fft; d.N = N; d.flags = flags; d.scale = scale;
+    if (d.nlines == 0) return SHB_OK;
+    const int ns = N / 2 + 1;
+    int M;
+    switch (mode) {
+    case FFT_C2C_FWD: M = n_fft; d.n_in = n_fft; d.n_out = N; break;
+    case FFT_C2C_BWD: M = n_fft; d.n_in = N; d.n_out = n_fft; break;
+    case FFT_R2C: if (n_fft % 2 || inner != 1) return SHB_ERR_UNSUPPORTED;
+                  M = n_fft / 2; d.n_in = n_fft; d.n_out = ns; break;
+    case FFT_C2R: if (n_fft % 2 || inner != 1) return SHB_ERR_UNSUPPORTED;
+                  M = n_fft / 2; d.n_in = ns; d.n_out = n_fft; break;
+    default: return SHB_ERR_UNSUPPORTED;
+    }
+    // cheap support test before touching the twiddle cache
+    auto supported = [&](int m, bool strided) {
+        static const int a[] = {64, 128, 256, 512, 1024, 96, 192, 384, 768, 1536, 1152};
+        static const int b[] = {32, 64, 128, 256, 512, 1024, 48, 96, 192, 384, 768, 576};
+        if (strided) { for (int x : a) if (x == m) return true; }
+        else { for (int x : b) if (x == m) return true; }
+        return false;
+    };
+    const bool strided = inner > 1;
+    if (!supported(M, strided)) return SHB_ERR_UNSUPPORTED;
+    d.tw = twiddle_table(0, M);
+    d.tw2 = (mode == FFT_R2C || mode == FFT_C2R) ? twiddle_table(1, M) : nullptr;
+    if (!d.tw || ((mode == FFT_R2C || mode == FFT_C2R) && !d.tw2)) {
+        set_error("fft: twiddle table allocation failed");
+        return SHB_ERR_NOMEM;
+    }
+    if (strided) return mode == FFT_C2C_FWD ? strided_fwd(M, d, st) : strided_bwd(M, d, st);
+    switch (mode) {
+    case FFT_C2C_FWD: return contig_c2c_fwd(M, d, st);
+    case FFT_C2C_BWD: return contig_c2c_bwd(M, d, st);
+    case FFT_R2C: return contig_r2c(M, d, st);
+    default: return contig_c2r(M, d, st);
+    }
 }
 
 }  // namespace shb

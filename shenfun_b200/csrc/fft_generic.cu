@@ -13,81 +13,9 @@
 //   shenfun/fourier/bases.py:404-435 (R2C pad/truncate, Nyquist rules)
 //   shenfun/fourier/bases.py:570-598 (C2C pad/truncate)
 #include "fft_common.cuh"
+#include "butterfly.cuh"
 
 namespace shb {
-
-// ---- butterflies ---------------------------------------------------------------
-template <bool INV> __device__ __forceinline__ void bfly2(cplx &a, cplx &b) {
-    cplx t = csub(a, b);
-    a = cadd(a, b);
-    b = t;
-}
-
-template <bool INV> __device__ __forceinline__ void bfly4(cplx &a0, cplx &a1, cplx &a2, cplx &a3) {
-    cplx s02 = cadd(a0, a2), d02 = csub(a0, a2);
-    cplx s13 = cadd(a1, a3), d13 = mul_mi<INV>(csub(a1, a3));
-    a0 = cadd(s02, s13);
-    a2 = csub(s02, s13);
-    a1 = cadd(d02, d13);
-    a3 = csub(d02, d13);
-}
-
-template <bool INV> __device__ __forceinline__ void bfly3(cplx &a0, cplx &a1, cplx &a2) {
-    const double s60 = 0.86602540378443864676372317075294;
-    cplx s = cadd(a1, a2);
-    cplx d = csub(a1, a2);
-    cplx m = make_double2(fma(-0.5, s.x, a0.x), fma(-0.5, s.y, a0.y));
-    // forward: a1 = m - i*s60*d ; a2 = m + i*s60*d   (inverse: swapped)
-    cplx r = INV ? make_double2(-s60 * d.y, s60 * d.x) : make_double2(s60 * d.y, -s60 * d.x);
-    a0 = cadd(a0, s);
-    a1 = cadd(m, r);
-    a2 = csub(m, r);
-}
-
-template <bool INV> __device__ __forceinline__ void bfly5(cplx &a0, cplx &a1, cplx &a2, cplx &a3, cplx &a4) {
-    const double c1 = 0.30901699437494742410229341718282;   // cos(2pi/5)
-    const double c2 = -0.80901699437494742410229341718282;  // cos(4pi/5)
-    const double s1 = 0.95105651629515357211643933337938;   // sin(2pi/5)
-    const double s2 = 0.58778525229247312916870595463907;   // sin(4pi/5)
-    cplx p14 = cadd(a1, a4), m14 = csub(a1, a4);
-    cplx p23 = cadd(a2, a3), m23 = csub(a2, a3);
-    cplx t1 = make_double2(a0.x + c1 * p14.x + c2 * p23.x, a0.y + c1 * p14.y + c2 * p23.y);
-    cplx t2 = make_double2(a0.x + c2 * p14.x + c1 * p23.x, a0.y + c2 * p14.y + c1 * p23.y);
-    // u1 = s1*m14 + s2*m23 ; u2 = s2*m14 - s1*m23 ; forward out_k = t -/+ i u
-    cplx u1 = make_double2(s1 * m14.x + s2 * m23.x, s1 * m14.y + s2 * m23.y);
-    cplx u2 = make_double2(s2 * m14.x - s1 * m23.x, s2 * m14.y - s1 * m23.y);
-    cplx iu1 = mul_mi<INV>(u1);   // -i*u (fwd) / +i*u (inv)
-    cplx iu2 = mul_mi<INV>(u2);
-    a0 = cadd(a0, cadd(p14, p23));
-    a1 = cadd(t1, iu1);
-    a4 = csub(t1, iu1);
-    a2 = cadd(t2, iu2);
-    a3 = csub(t2, iu2);
-}
-
-template <bool INV> __device__ __forceinline__ void bfly8(cplx (&v)[8]) {
-    const double h = 0.70710678118654752440084436210485;
-    // three radix-2 layers (decimation in time on bit-reversed sub-blocks)
-    bfly4<INV>(v[0], v[2], v[4], v[6]);
-    bfly4<INV>(v[1], v[3], v[5], v[7]);
-    // twiddles W8^k on odd half: k=1: (1-i)/sqrt2 (fwd), k=2: -i, k=3: (-1-i)/sqrt2
-    cplx t1 = INV ? make_double2(h * (v[3].x - v[3].y), h * (v[3].x + v[3].y))
-                  : make_double2(h * (v[3].x + v[3].y), h * (v[3].y - v[3].x));
-    cplx t2 = mul_mi<INV>(v[5]);
-    cplx t3 = INV ? make_double2(-h * (v[7].x + v[7].y), h * (v[7].x - v[7].y))
-                  : make_double2(h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y));
-    // after bfly4 on (0,2,4,6): v0=E0, v2=E1, v4=E2, v6=E3 ; (1,3,5,7): v1=O0, v3=O1, v5=O2, v7=O3
-    cplx e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
-    cplx o0 = v[1];
-    v[0] = cadd(e0, o0);
-    v[4] = csub(e0, o0);
-    v[1] = cadd(e1, t1);
-    v[5] = csub(e1, t1);
-    v[2] = cadd(e2, t2);
-    v[6] = csub(e2, t2);
-    v[3] = cadd(e3, t3);
-    v[7] = csub(e3, t3);
-}
 
 // ---- one Stockham stage over a tile held in shared memory ----------------------
 // src/dst: [M][PT] complex, this thread works on column c with P threads per line.
@@ -109,14 +37,7 @@ __device__ __forceinline__ void stage_fixed(const cplx *__restrict__ src, cplx *
                 v[m] = INV ? cmulc(v[m], w) : cmul(v[m], w);
             }
         }
-        if constexpr (R == 2) bfly2<INV>(v[0], v[1]);
-        else if constexpr (R == 3) bfly3<INV>(v[0], v[1], v[2]);
-        else if constexpr (R == 4) bfly4<INV>(v[0], v[1], v[2], v[3]);
-        else if constexpr (R == 5) bfly5<INV>(v[0], v[1], v[2], v[3], v[4]);
-        else if constexpr (R == 8) {
-            cplx (&w8)[8] = reinterpret_cast<cplx (&)[8]>(v);
-            bfly8<INV>(w8);
-        }
+        Bfly<R, INV>::run(v);
         const int j0 = (b / Ns) * Ns * R + k;
 #pragma unroll
         for (int m = 0; m < R; ++m) dst[(size_t)(j0 + m * Ns) * PT + c] = v[m];
