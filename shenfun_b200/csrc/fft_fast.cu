@@ -1,8 +1,8 @@
 // fft_fast.cu -- register-resident Stockham FFT kernels for the headline sizes.
 //
-// A line of M = R0*R1[*R2] complex points is transformed by P = max(M/Ri)
-// threads; each thread runs at most one radix-Ri butterfly per stage with the
-// Ri operands in registers.  Stage 0 reads its operands straight from global
+// A line of M = R0*R1[*R2] complex points is transformed by P threads; each
+// thread runs M/(Ri*P) radix-Ri butterflies per stage with the operands in
+// registers.  Stage 0 reads its operands straight from global
 // memory (fused zero-padding / Hermitian pre-twiddle), the last stage writes
 // straight to global memory (fused truncation / Nyquist rules / scaling / real
 // split), so data crosses shared memory only for the (stages-1) exchanges.
@@ -23,62 +23,105 @@ namespace shb {
 
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
-template <int M_, int R0_, int R1_, int R2_>
+// A schedule: M = R0*R1[*R2] computed by P threads per line.  Stage i has
+// NBi = M/Ri butterflies; a thread runs Bi = NBi/P of them (NBi a multiple of
+// P) or at most one (NBi < P, threads j >= NBi idle in that stage).
+template <int M_, int R0_, int R1_, int R2_, int P_>
 struct Sched {
-    static constexpr int M = M_, R0 = R0_, R1 = R1_, R2 = R2_;
+    static constexpr int M = M_, R0 = R0_, R1 = R1_, R2 = R2_, P = P_;
     static_assert(R0_ * R1_ * R2_ == M_, "radices must multiply to M");
     static constexpr int NST = (R2_ > 1) ? 3 : 2;
     static constexpr int NB0 = M / R0, NB1 = M / R1, NB2 = (R2_ > 1) ? M / R2 : 0;
-    static constexpr int P = cmax(NB0, cmax(NB1, NB2));
-    static constexpr int RMAX = cmax(R0, cmax(R1, R2));
-    static constexpr int RL = (NST == 3) ? R2 : R1;     // radix of the last stage
-    static constexpr int NBL = (NST == 3) ? NB2 : NB1;  // butterflies in the last stage
+    static constexpr int bpt(int nb) { return nb >= P_ ? nb / P_ : 1; }
+    static_assert(NB0 < P_ || NB0 % P_ == 0, "stage 0 butterflies vs threads");
+    static_assert(NB1 < P_ || NB1 % P_ == 0, "stage 1 butterflies vs threads");
+    static_assert(NB2 < P_ || NB2 % P_ == 0, "stage 2 butterflies vs threads");
+    static constexpr int B0 = bpt(NB0), B1 = bpt(NB1), B2 = (R2_ > 1) ? bpt(NB2) : 0;
+    static constexpr int EMAX = cmax(B0 * R0, cmax(B1 * R1, B2 * R2));
+    static constexpr int RL = (NST == 3) ? R2 : R1;     // last stage: radix,
+    static constexpr int NBL = (NST == 3) ? NB2 : NB1;  //   butterflies per line,
+    static constexpr int BL = (NST == 3) ? B2 : B1;     //   butterflies per thread
 };
 
-// Stages after the operands of stage 0 are in v[0..R0).  On return the thread
-// (if j < NBL) holds X[j + m*NBL], m < RL, in v.  `S` maps a line position to
-// shared memory for this thread's line.
-template <class SC, bool INV, class S>
-__device__ __forceinline__ void fft_stages(cplx *v, const int j, S s, const cplx *__restrict__ tw) {
-    constexpr int R0 = SC::R0, R1 = SC::R1, R2 = SC::R2, M = SC::M;
+// Stages after the operands of stage 0 are in v: butterfly q of this thread
+// (line butterfly b = j + q*P) has operand m at v[q*R0+m] = x[b + m*NB0].  On
+// return v[q*RL+m] = X[b + m*NBL].  `S` maps a line position to shared memory
+// for this thread's line, `Y` synchronises the threads that share the line.
+template <class SC, bool INV, class S, class Y>
+__device__ __forceinline__ void fft_stages(cplx *v, const int j, S s, Y sync, const cplx *__restrict__ tw) {
+    constexpr int R0 = SC::R0, R1 = SC::R1, R2 = SC::R2, P = SC::P;
     if (j < SC::NB0) {
-        Bfly<R0, INV>::run(v);
 #pragma unroll
-        for (int m = 0; m < R0; ++m) s(j * R0 + m) = v[m];
+        for (int q = 0; q < SC::B0; ++q) {
+            Bfly<R0, INV>::run(v + q * R0);
+#pragma unroll
+            for (int m = 0; m < R0; ++m) s((j + q * P) * R0 + m) = v[q * R0 + m];
+        }
     }
-    __syncthreads();
+    sync();
     if (j < SC::NB1) {
 #pragma unroll
-        for (int m = 0; m < R1; ++m) v[m] = s(j + m * SC::NB1);
-        const int k = j % R0;
+        for (int q = 0; q < SC::B1; ++q) {
+            const int b = j + q * P;
 #pragma unroll
-        for (int m = 1; m < R1; ++m) {
-            const cplx w = __ldg(&tw[k * m * R2]);
-            v[m] = INV ? cmulc(v[m], w) : cmul(v[m], w);
+            for (int m = 0; m < R1; ++m) v[q * R1 + m] = s(b + m * SC::NB1);
         }
-        Bfly<R1, INV>::run(v);
+#pragma unroll
+        for (int q = 0; q < SC::B1; ++q) {
+            const int k = (j + q * P) % R0;
+#pragma unroll
+            for (int m = 1; m < R1; ++m) {
+                const cplx w = __ldg(&tw[k * m * R2]);
+                v[q * R1 + m] = INV ? cmulc(v[q * R1 + m], w) : cmul(v[q * R1 + m], w);
+            }
+            Bfly<R1, INV>::run(v + q * R1);
+        }
     }
     if constexpr (SC::NST == 3) {
-        __syncthreads();
+        sync();
         if (j < SC::NB1) {
-            const int k = j % R0;
-            const int j0 = (j / R0) * (R0 * R1) + k;
 #pragma unroll
-            for (int m = 0; m < R1; ++m) s(j0 + m * R0) = v[m];
+            for (int q = 0; q < SC::B1; ++q) {
+                const int b = j + q * P;
+                const int k = b % R0;
+                const int j0 = (b / R0) * (R0 * R1) + k;
+#pragma unroll
+                for (int m = 0; m < R1; ++m) s(j0 + m * R0) = v[q * R1 + m];
+            }
         }
-        __syncthreads();
+        sync();
         if (j < SC::NB2) {
 #pragma unroll
-            for (int m = 0; m < R2; ++m) v[m] = s(j + m * SC::NB2);
+            for (int q = 0; q < SC::B2; ++q) {
+                const int b = j + q * P;
 #pragma unroll
-            for (int m = 1; m < R2; ++m) {
-                const cplx w = __ldg(&tw[j * m]);
-                v[m] = INV ? cmulc(v[m], w) : cmul(v[m], w);
+                for (int m = 0; m < R2; ++m) v[q * R2 + m] = s(b + m * SC::NB2);
             }
-            Bfly<R2, INV>::run(v);
+#pragma unroll
+            for (int q = 0; q < SC::B2; ++q) {
+                const int b = j + q * P;
+#pragma unroll
+                for (int m = 1; m < R2; ++m) {
+                    const cplx w = __ldg(&tw[b * m]);
+                    v[q * R2 + m] = INV ? cmulc(v[q * R2 + m], w) : cmul(v[q * R2 + m], w);
+                }
+                Bfly<R2, INV>::run(v + q * R2);
+            }
         }
     }
 }
+
+// threads sharing a line: a warp (P == 32), a few warps (named barrier) or the CTA
+template <int P> struct GroupSync {
+    int id;
+    __device__ __forceinline__ void operator()() const {
+        if constexpr (P == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(P) : "memory");
+    }
+};
+struct CtaSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
 
 struct FastDesc {
     const void *in;
@@ -89,11 +132,31 @@ struct FastDesc {
     const cplx *tw, *tw2;
 };
 
+// zero-padding rule of the C2C backward transform as a branch-free gather:
+// row r of the padded line comes from row `src` of the stored line times f.
+struct PadMap {
+    int N, M, h;
+    bool padded, evenN, dd;
+    __device__ __forceinline__ PadMap(int N_, int M_, int flags)
+        : N(N_), M(M_), h(N_ / 2), padded(N_ < M_), evenN(N_ % 2 == 0), dd((flags & 1) != 0) {}
+    __device__ __forceinline__ bool map(int r, int &src, double &f) const {
+        src = r;
+        f = 1.0;
+        if (padded) {
+            const bool lo = (r <= h), hi = (r >= M - h);
+            src = lo ? r : r - M + N;
+            if (evenN && (r == h || r == M - h)) f = 0.5;
+            return lo || hi;
+        }
+        return !(dd && r >= N / 3 && r <= N - N / 3);
+    }
+};
+
 // ---- kernel A ---------------------------------------------------------------------
 template <class SC, int MODE, int T>
 __global__ void __launch_bounds__(SC::P *T) fft_strided_kernel(const __grid_constant__ FastDesc d) {
     constexpr bool INV = (MODE == FFT_C2C_BWD);
-    constexpr int M = SC::M;
+    constexpr int M = SC::M, P = SC::P;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *sm = reinterpret_cast<cplx *>(smem_raw);
     const int c = threadIdx.x % T;
@@ -108,34 +171,28 @@ __global__ void __launch_bounds__(SC::P *T) fft_strided_kernel(const __grid_cons
     const bool padded = (N < M);
     const bool evenN = (N % 2 == 0);
     const int h = N / 2;
+    const PadMap pm(N, M, d.flags);
 
-    cplx v[SC::RMAX];
+    cplx v[SC::EMAX];
     if (j < SC::NB0) {
+        // branch-free operand fetch: all loads are issued back to back
 #pragma unroll
-        for (int m = 0; m < SC::R0; ++m) {
-            const int r = j + m * SC::NB0;
-            cplx x = make_double2(0.0, 0.0);
-            if (valid) {
-                if (MODE == FFT_C2C_FWD) {
-                    x = in[(int64_t)r * stride];
-                } else if (!padded) {
-                    x = in[(int64_t)r * stride];
-                    if ((d.flags & 1) && r >= N / 3 && r <= N - N / 3) x = make_double2(0.0, 0.0);
-                } else {
-                    if (r <= h) {
-                        x = in[(int64_t)r * stride];
-                        if (evenN && r == h) x = cscale(x, 0.5);
-                    } else if (r >= M - h) {
-                        x = in[(int64_t)(r - M + N) * stride];
-                        if (evenN && r == M - h) x = cscale(x, 0.5);
-                    }
-                }
+        for (int q = 0; q < SC::B0; ++q) {
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m) {
+                const int r = (j + q * P) + m * SC::NB0;
+                bool ok = valid;
+                int src = r;
+                double f = 1.0;
+                if (MODE == FFT_C2C_BWD) ok = pm.map(r, src, f) && valid;
+                cplx x = make_double2(0.0, 0.0);
+                if (ok) x = in[(int64_t)src * stride];
+                v[q * SC::R0 + m] = (MODE == FFT_C2C_BWD) ? make_double2(x.x * f, x.y * f) : x;
             }
-            v[m] = x;
         }
     }
     auto s = [&](int pos) -> cplx & { return sm[pos * T + c]; };
-    fft_stages<SC, INV>(v, j, s, d.tw);
+    fft_stages<SC, INV>(v, j, s, CtaSync(), d.tw);
 
     const double scale = d.scale;
     if (MODE == FFT_C2C_FWD && padded && evenN) {
@@ -143,24 +200,30 @@ __global__ void __launch_bounds__(SC::P *T) fft_strided_kernel(const __grid_cons
         __syncthreads();
         if (j < SC::NBL) {
 #pragma unroll
-            for (int m = 0; m < SC::RL; ++m)
-                if (j + m * SC::NBL == M - h) sm[c] = v[m];
+            for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m)
+                    if ((j + q * P) + m * SC::NBL == M - h) sm[c] = v[q * SC::RL + m];
         }
         __syncthreads();
     }
     if (j < SC::NBL && valid) {
 #pragma unroll
-        for (int m = 0; m < SC::RL; ++m) {
-            const int r = j + m * SC::NBL;
-            if (MODE == FFT_C2C_BWD || !padded) {
-                out[(int64_t)r * stride] = cscale(v[m], scale);
-            } else {
-                if (r <= h) {
-                    cplx x = v[m];
-                    if (evenN && r == h) x = cadd(x, sm[c]);
-                    out[(int64_t)r * stride] = cscale(x, scale);
-                } else if (r > M - h || (!evenN && r == M - h)) {
-                    out[(int64_t)(r - M + N) * stride] = cscale(v[m], scale);
+        for (int q = 0; q < SC::BL; ++q) {
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) {
+                const int r = (j + q * P) + m * SC::NBL;
+                const cplx x0 = v[q * SC::RL + m];
+                if (MODE == FFT_C2C_BWD || !padded) {
+                    out[(int64_t)r * stride] = cscale(x0, scale);
+                } else {
+                    if (r <= h) {
+                        cplx x = x0;
+                        if (evenN && r == h) x = cadd(x, sm[c]);
+                        out[(int64_t)r * stride] = cscale(x, scale);
+                    } else if (r > M - h || (!evenN && r == M - h)) {
+                        out[(int64_t)(r - M + N) * stride] = cscale(x0, scale);
+                    }
                 }
             }
         }
@@ -173,11 +236,13 @@ __device__ __forceinline__ int skew(int pos) { return pos + (pos >> 3); }
 template <class SC, int MODE, int TL>
 __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_constant__ FastDesc d) {
     constexpr bool INV = (MODE == FFT_C2C_BWD || MODE == FFT_C2R);
-    constexpr int M = SC::M;
+    constexpr int M = SC::M, P = SC::P;
+    static_assert(P % 32 == 0, "a line is owned by whole warps");
+    static_assert(P == 32 || TL <= 15, "one named barrier per line");
     constexpr int LP = M + (M >> 3) + 2;        // shared pitch of one line
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int j = threadIdx.x % SC::P;
-    const int l = threadIdx.x / SC::P;
+    const int j = threadIdx.x % P;
+    const int l = threadIdx.x / P;
     cplx *sm = reinterpret_cast<cplx *>(smem_raw) + (size_t)l * LP;
     const int64_t line = (int64_t)blockIdx.x * TL + l;
     const bool valid = line < d.nlines;
@@ -188,29 +253,26 @@ __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_cons
     const int h = N / 2;
     const double scale = d.scale;
     auto s = [&](int pos) -> cplx & { return sm[skew(pos)]; };
+    const GroupSync<P> sync{l + 1};
 
-    cplx v[SC::RMAX];
+    cplx v[SC::EMAX];
     if (MODE == FFT_C2C_FWD || MODE == FFT_C2C_BWD) {
         const cplx *__restrict__ in = reinterpret_cast<const cplx *>(d.in) + line * d.n_in;
+        const PadMap pm(N, M, d.flags);
         if (j < SC::NB0) {
 #pragma unroll
-            for (int m = 0; m < SC::R0; ++m) {
-                const int r = j + m * SC::NB0;
-                cplx x = make_double2(0.0, 0.0);
-                if (valid) {
-                    if (MODE == FFT_C2C_FWD) x = in[r];
-                    else if (!padded) {
-                        x = in[r];
-                        if ((d.flags & 1) && r >= N / 3 && r <= N - N / 3) x = make_double2(0.0, 0.0);
-                    } else if (r <= h) {
-                        x = in[r];
-                        if (evenN && r == h) x = cscale(x, 0.5);
-                    } else if (r >= M - h) {
-                        x = in[r - M + N];
-                        if (evenN && r == M - h) x = cscale(x, 0.5);
-                    }
+            for (int q = 0; q < SC::B0; ++q) {
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int r = (j + q * P) + m * SC::NB0;
+                    bool ok = valid;
+                    int src = r;
+                    double f = 1.0;
+                    if (MODE == FFT_C2C_BWD) ok = pm.map(r, src, f) && valid;
+                    cplx x = make_double2(0.0, 0.0);
+                    if (ok) x = in[src];
+                    v[q * SC::R0 + m] = (MODE == FFT_C2C_BWD) ? make_double2(x.x * f, x.y * f) : x;
                 }
-                v[m] = x;
             }
         }
     } else if (MODE == FFT_R2C) {
@@ -218,93 +280,118 @@ __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_cons
             reinterpret_cast<const double *>(d.in) + line * (int64_t)n_fft);
         if (j < SC::NB0) {
 #pragma unroll
-            for (int m = 0; m < SC::R0; ++m)
-                v[m] = valid ? in[j + m * SC::NB0] : make_double2(0.0, 0.0);
+            for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m)
+                    v[q * SC::R0 + m] = valid ? in[(j + q * P) + m * SC::NB0] : make_double2(0.0, 0.0);
         }
-    } else {   // FFT_C2R: stage the stored modes, then build Y[n] = (X[n]+conj X[M-n]) + i e^{+i pi n/M}(X[n]-conj X[M-n])
+    } else {   // FFT_C2R: Y[n] = (X[n]+conj X[M-n]) + i e^{+i pi n/M} (X[n]-conj X[M-n])
+        // X[n] and X[M-n] are both read straight from global memory: the mirrored
+        // read is coalesced too (descending addresses) and hits L1/L2.
         const cplx *__restrict__ in = reinterpret_cast<const cplx *>(d.in) + line * d.n_in;
         const int ns = h + 1;
-        for (int k = j; k <= M; k += SC::P) {
-            cplx x = make_double2(0.0, 0.0);
-            if (valid && k < ns) {
-                x = in[k];
-                if ((d.flags & 1) && !padded && k >= N / 3) x = make_double2(0.0, 0.0);
-                if (padded && evenN && k == ns - 1) x = make_double2(0.5 * x.x, 0.0);
-            }
-            if (k == 0 || k == M) x.y = 0.0;
-            s(k) = x;
-        }
-        __syncthreads();
+        const bool dd = (d.flags & 1) && !padded;
         if (j < SC::NB0) {
 #pragma unroll
-            for (int m = 0; m < SC::R0; ++m) {
-                const int n = j + m * SC::NB0;
-                const cplx xk = s(n), xc = cconj(s(M - n));
-                const cplx sum = cadd(xk, xc), df = csub(xk, xc);
-                const cplx w = __ldg(&d.tw2[n]);               // e^{-i pi n / M}
-                const cplx iw = make_double2(w.y, w.x);        // i * conj(w)
-                v[m] = cadd(sum, cmul(iw, df));
+            for (int q = 0; q < SC::B0; ++q) {
+                cplx xa[SC::R0], xb[SC::R0];
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int n = (j + q * P) + m * SC::NB0;
+                    const int nm = M - n;
+                    xa[m] = (valid && n < ns) ? in[n] : make_double2(0.0, 0.0);
+                    xb[m] = (valid && nm < ns) ? in[nm] : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int n = (j + q * P) + m * SC::NB0;
+                    const int nm = M - n;
+                    cplx xk = xa[m], xc = xb[m];
+                    if (dd && n >= N / 3) xk = make_double2(0.0, 0.0);
+                    if (dd && nm >= N / 3) xc = make_double2(0.0, 0.0);
+                    if (padded && evenN && n == ns - 1) xk = make_double2(0.5 * xk.x, 0.0);
+                    if (padded && evenN && nm == ns - 1) xc = make_double2(0.5 * xc.x, 0.0);
+                    if (n == 0) { xk.y = 0.0; xc.y = 0.0; }      // DC and Nyquist (X[M]) are real
+                    xc.y = -xc.y;
+                    const cplx sum = cadd(xk, xc), df = csub(xk, xc);
+                    const cplx w = __ldg(&d.tw2[n]);               // e^{-i pi n / M}
+                    const cplx iw = make_double2(w.y, w.x);        // i * conj(w)
+                    v[q * SC::R0 + m] = cadd(sum, cmul(iw, df));
+                }
             }
         }
-        __syncthreads();
     }
 
-    fft_stages<SC, INV>(v, j, s, d.tw);
+    fft_stages<SC, INV>(v, j, s, sync, d.tw);
 
     if (MODE == FFT_C2C_BWD || (MODE == FFT_C2C_FWD && !padded)) {
         cplx *__restrict__ out = reinterpret_cast<cplx *>(d.out) + line * d.n_out;
         if (j < SC::NBL && valid) {
 #pragma unroll
-            for (int m = 0; m < SC::RL; ++m) out[j + m * SC::NBL] = cscale(v[m], scale);
+            for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m)
+                    out[(j + q * P) + m * SC::NBL] = cscale(v[q * SC::RL + m], scale);
         }
     } else if (MODE == FFT_C2C_FWD) {
         cplx *__restrict__ out = reinterpret_cast<cplx *>(d.out) + line * d.n_out;
         if (evenN) {
-            __syncthreads();
+            sync();
             if (j < SC::NBL) {
 #pragma unroll
-                for (int m = 0; m < SC::RL; ++m)
-                    if (j + m * SC::NBL == M - h) sm[0] = v[m];
+                for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                    for (int m = 0; m < SC::RL; ++m)
+                        if ((j + q * P) + m * SC::NBL == M - h) sm[0] = v[q * SC::RL + m];
             }
-            __syncthreads();
+            sync();
         }
         if (j < SC::NBL && valid) {
 #pragma unroll
-            for (int m = 0; m < SC::RL; ++m) {
-                const int r = j + m * SC::NBL;
-                if (r <= h) {
-                    cplx x = v[m];
-                    if (evenN && r == h) x = cadd(x, sm[0]);
-                    out[r] = cscale(x, scale);
-                } else if (r > M - h || (!evenN && r == M - h)) {
-                    out[r - M + N] = cscale(v[m], scale);
+            for (int q = 0; q < SC::BL; ++q) {
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m) {
+                    const int r = (j + q * P) + m * SC::NBL;
+                    const cplx x0 = v[q * SC::RL + m];
+                    if (r <= h) {
+                        cplx x = x0;
+                        if (evenN && r == h) x = cadd(x, sm[0]);
+                        out[r] = cscale(x, scale);
+                    } else if (r > M - h || (!evenN && r == M - h)) {
+                        out[r - M + N] = cscale(x0, scale);
+                    }
                 }
             }
         }
     } else if (MODE == FFT_R2C) {
         // X[k] = E + e^{-i pi k/M} O,  E = (Z[k]+conj Z[M-k])/2,  O = -i (Z[k]-conj Z[M-k])/2
         cplx *__restrict__ out = reinterpret_cast<cplx *>(d.out) + line * d.n_out;
-        __syncthreads();
+        sync();
         if (j < SC::NBL) {
 #pragma unroll
-            for (int m = 0; m < SC::RL; ++m) s(j + m * SC::NBL) = v[m];
+            for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m) s((j + q * P) + m * SC::NBL) = v[q * SC::RL + m];
         }
-        __syncthreads();
+        sync();
         if (j < SC::NBL && valid) {
             const int ns = h + 1;
 #pragma unroll
-            for (int m = 0; m < SC::RL; ++m) {
-                const int k = j + m * SC::NBL;
-                if (k < ns) {
-                    const cplx zk = v[m];
-                    const cplx zc = cconj(s(k == 0 ? 0 : M - k));
-                    const cplx e = cscale(cadd(zk, zc), 0.5);
-                    const cplx df = cscale(csub(zk, zc), 0.5);
-                    const cplx o_ = make_double2(df.y, -df.x);
-                    const cplx w = __ldg(&d.tw2[k]);
-                    cplx x = cadd(e, cmul(w, o_));
-                    if (padded && evenN && k == h) x = make_double2(2.0 * x.x, 0.0);
-                    out[k] = cscale(x, scale);
+            for (int q = 0; q < SC::BL; ++q) {
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m) {
+                    const int k = (j + q * P) + m * SC::NBL;
+                    if (k < ns) {
+                        const cplx zk = v[q * SC::RL + m];
+                        const cplx zc = cconj(s(k == 0 ? 0 : M - k));
+                        const cplx e = cscale(cadd(zk, zc), 0.5);
+                        const cplx df = cscale(csub(zk, zc), 0.5);
+                        const cplx o_ = make_double2(df.y, -df.x);
+                        const cplx w = __ldg(&d.tw2[k]);
+                        cplx x = cadd(e, cmul(w, o_));
+                        if (padded && evenN && k == h) x = make_double2(2.0 * x.x, 0.0);
+                        out[k] = cscale(x, scale);
+                    }
                 }
             }
             if (j == 0 && ns - 1 == M) {    // un-padded Nyquist: X[M] = Re Z0 - Im Z0
@@ -317,7 +404,10 @@ __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_cons
             reinterpret_cast<double *>(d.out) + line * (int64_t)n_fft);
         if (j < SC::NBL && valid) {
 #pragma unroll
-            for (int m = 0; m < SC::RL; ++m) out[j + m * SC::NBL] = cscale(v[m], scale);
+            for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m)
+                    out[(j + q * P) + m * SC::NBL] = cscale(v[q * SC::RL + m], scale);
         }
     }
 }
@@ -357,39 +447,38 @@ static int launch_contig(const FastDesc &d, cudaStream_t st) {
 // all-zero operands are never loaded; forward (truncated output) puts it last.
 #define SHB_STRIDED_CASES(MODE, FIRSTWIDE)                                                          \
     switch (M) {                                                                                    \
-    case 64:   return launch_strided<Sched<64, 8, 8, 1>, MODE, 8>(d, st);                           \
-    case 128:  return launch_strided<Sched<128, 8, 4, 4>, MODE, 8>(d, st);                          \
-    case 256:  return launch_strided<Sched<256, 8, 8, 4>, MODE, 8>(d, st);                          \
-    case 512:  return launch_strided<Sched<512, 8, 8, 8>, MODE, 8>(d, st);                          \
-    case 1024: return launch_strided<Sched<1024, 16, 8, 8>, MODE, 4>(d, st);                        \
-    case 96:   return FIRSTWIDE ? launch_strided<Sched<96, 12, 8, 1>, MODE, 8>(d, st)               \
-                                : launch_strided<Sched<96, 8, 12, 1>, MODE, 8>(d, st);              \
-    case 192:  return FIRSTWIDE ? launch_strided<Sched<192, 6, 8, 4>, MODE, 8>(d, st)               \
-                                : launch_strided<Sched<192, 4, 8, 6>, MODE, 8>(d, st);              \
-    case 384:  return FIRSTWIDE ? launch_strided<Sched<384, 6, 8, 8>, MODE, 8>(d, st)               \
-                                : launch_strided<Sched<384, 8, 8, 6>, MODE, 8>(d, st);              \
-    case 768:  return FIRSTWIDE ? launch_strided<Sched<768, 12, 8, 8>, MODE, 8>(d, st)              \
-                                : launch_strided<Sched<768, 8, 8, 12>, MODE, 8>(d, st);             \
-    case 1536: return FIRSTWIDE ? launch_strided<Sched<1536, 12, 16, 8>, MODE, 4>(d, st)            \
-                                : launch_strided<Sched<1536, 8, 16, 12>, MODE, 4>(d, st);           \
-    case 1152: return launch_strided<Sched<1152, 12, 12, 8>, MODE, 4>(d, st);                       \
+    case 64:   return launch_strided<Sched<64, 8, 8, 1, 8>, MODE, 8>(d, st);                        \
+    case 128:  return launch_strided<Sched<128, 8, 4, 4, 32>, MODE, 8>(d, st);                      \
+    case 256:  return launch_strided<Sched<256, 8, 8, 4, 32>, MODE, 8>(d, st);                      \
+    case 512:  return launch_strided<Sched<512, 8, 8, 8, 64>, MODE, 8>(d, st);                      \
+    case 1024: return launch_strided<Sched<1024, 16, 8, 8, 128>, MODE, 4>(d, st);                   \
+    case 96:   return FIRSTWIDE ? launch_strided<Sched<96, 12, 8, 1, 12>, MODE, 8>(d, st)           \
+                                : launch_strided<Sched<96, 8, 12, 1, 12>, MODE, 8>(d, st);          \
+    case 192:  return FIRSTWIDE ? launch_strided<Sched<192, 6, 8, 4, 48>, MODE, 8>(d, st)           \
+                                : launch_strided<Sched<192, 4, 8, 6, 48>, MODE, 8>(d, st);          \
+    case 384:  return FIRSTWIDE ? launch_strided<Sched<384, 6, 8, 8, 64>, MODE, 8>(d, st)           \
+                                : launch_strided<Sched<384, 8, 8, 6, 64>, MODE, 8>(d, st);          \
+    case 768:  return FIRSTWIDE ? launch_strided<Sched<768, 12, 8, 8, 96>, MODE, 8>(d, st)          \
+                                : launch_strided<Sched<768, 8, 8, 12, 96>, MODE, 8>(d, st);         \
+    case 1536: return FIRSTWIDE ? launch_strided<Sched<1536, 12, 16, 8, 192>, MODE, 4>(d, st)       \
+                                : launch_strided<Sched<1536, 8, 16, 12, 192>, MODE, 4>(d, st);      \
+    case 1152: return launch_strided<Sched<1152, 12, 12, 8, 144>, MODE, 4>(d, st);                  \
     default: return SHB_ERR_UNSUPPORTED;                                                            \
     }
 
 #define SHB_CONTIG_CASES(MODE)                                                                      \
     switch (M) {                                                                                    \
-    case 32:   return launch_contig<Sched<32, 8, 4, 1>, MODE, 16>(d, st);                           \
-    case 64:   return launch_contig<Sched<64, 8, 8, 1>, MODE, 16>(d, st);                           \
-    case 128:  return launch_contig<Sched<128, 16, 8, 1>, MODE, 16>(d, st);                         \
-    case 256:  return launch_contig<Sched<256, 16, 16, 1>, MODE, 16>(d, st);                        \
-    case 512:  return launch_contig<Sched<512, 8, 8, 8>, MODE, 4>(d, st);                           \
-    case 1024: return launch_contig<Sched<1024, 16, 8, 8>, MODE, 2>(d, st);                         \
-    case 48:   return launch_contig<Sched<48, 6, 8, 1>, MODE, 16>(d, st);                           \
-    case 96:   return launch_contig<Sched<96, 12, 8, 1>, MODE, 16>(d, st);                          \
-    case 192:  return launch_contig<Sched<192, 12, 16, 1>, MODE, 16>(d, st);                        \
-    case 384:  return launch_contig<Sched<384, 6, 8, 8>, MODE, 4>(d, st);                           \
-    case 768:  return launch_contig<Sched<768, 12, 8, 8>, MODE, 2>(d, st);                          \
-    case 576:  return launch_contig<Sched<576, 6, 12, 8>, MODE, 4>(d, st);                          \
+    case 32:   return launch_contig<Sched<32, 8, 4, 1, 32>, MODE, 8>(d, st);                        \
+    case 64:   return launch_contig<Sched<64, 8, 8, 1, 32>, MODE, 8>(d, st);                        \
+    case 128:  return launch_contig<Sched<128, 8, 4, 4, 32>, MODE, 8>(d, st);                       \
+    case 256:  return launch_contig<Sched<256, 8, 8, 4, 32>, MODE, 8>(d, st);                       \
+    case 512:  return launch_contig<Sched<512, 8, 8, 8, 64>, MODE, 4>(d, st);                       \
+    case 1024: return launch_contig<Sched<1024, 16, 8, 8, 128>, MODE, 2>(d, st);                    \
+    case 96:   return launch_contig<Sched<96, 12, 8, 1, 32>, MODE, 8>(d, st);                       \
+    case 192:  return launch_contig<Sched<192, 6, 8, 4, 64>, MODE, 4>(d, st);                       \
+    case 384:  return launch_contig<Sched<384, 6, 8, 8, 64>, MODE, 4>(d, st);                       \
+    case 768:  return launch_contig<Sched<768, 12, 8, 8, 96>, MODE, 4>(d, st);                      \
+    case 576:  return launch_contig<Sched<576, 6, 12, 8, 96>, MODE, 4>(d, st);                      \
     default: return SHB_ERR_UNSUPPORTED;                                                            \
     }
 
@@ -420,7 +509,7 @@ int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t 
     // cheap support test before touching the twiddle cache
     auto supported = [&](int m, bool strided) {
         static const int a[] = {64, 128, 256, 512, 1024, 96, 192, 384, 768, 1536, 1152};
-        static const int b[] = {32, 64, 128, 256, 512, 1024, 48, 96, 192, 384, 768, 576};
+        static const int b[] = {32, 64, 128, 256, 512, 1024, 96, 192, 384, 768, 576};
         if (strided) { for (int x : a) if (x == m) return true; }
         else { for (int x : b) if (x == m) return true; }
         return false;
