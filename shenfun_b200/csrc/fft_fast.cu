@@ -18,6 +18,7 @@
 // Reference semantics: see fft_generic.cu (same C ABI, same results).
 #include "fft_common.cuh"
 #include "butterfly.cuh"
+#include <stdlib.h>
 
 namespace shb {
 
