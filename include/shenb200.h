@@ -77,6 +77,38 @@ SHB_API int shb_fft_r2c_forward(const void *d_in, void *d_out, int64_t outer, in
 SHB_API int shb_fft_c2r_backward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
                          int n_fft, int N, double scale, int flags, void *stream);
 
+/* ------------------------------------------------------------------ */
+/* Point-wise kernels of the Navier-Stokes path.                        */
+
+/* c = a x b on [3][n] arrays (real fp64 or complex128).  Replaces
+ * shenfun/optimization/cython/cross.pyx:25-40 (`cross3D`), reached through
+ * shenfun/utilities/__init__.py:177-210 (`cross`).                        */
+SHB_API int shb_cross3d(const void *d_a, const void *d_b, void *d_c, int64_t n, int is_complex, void *stream);
+
+/* out = i k x u on [3][n0][n1][n2] complex with per-axis wavenumber vectors:
+ * what `project(curl(U_hat), TV)` evaluates for Fourier^3
+ * (demo/NavierStokes.py:37; shenfun/fourier/matrices.py:149-176).          */
+SHB_API int shb_curl_hat(const void *d_u, void *d_out, const double *d_k0, const double *d_k1,
+                         const double *d_k2, int n0, int n1, int n2, void *stream);
+
+/* One Runge-Kutta stage of the triply periodic Navier-Stokes demo, fused:
+ * pressure solve + gradient (demo/NavierStokes.py:41-43), viscous term and
+ * the RK4 stage update (shenfun/utilities/integrators.py:590-598).
+ * d_P may be NULL.                                                          */
+SHB_API int shb_ns_rk_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, void *d_P,
+                            const double *d_k0, const double *d_k1, const double *d_k2,
+                            int n0, int n1, int n2, double nu, double a_dt, double b_dt, int last,
+                            void *stream);
+
+/* Generic RK4 stage on [ncomp][n] complex arrays with a real diagonal linear
+ * operator L[n] (may be NULL): integrators.py:590-598.                      */
+SHB_API int shb_rk4_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, const double *d_L,
+                          int64_t n, int ncomp, double a_dt, double b_dt, int last, void *stream);
+
+/* u *= mask on [ncomp][n] complex (Nyquist masking): replaces
+ * shenfun/optimization/cython/applymask.pyx:15-169 (`apply_mask`).          */
+SHB_API int shb_apply_mask(void *d_u, const double *d_mask, int64_t n, int ncomp, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,10 @@ from .functionspace import FunctionSpace
 from .tensorproductspace import TensorProductSpace, VectorSpace, TensorSpace, CompositeSpace
 from .arrays import Function, Array
 from . import ops
+from .forms import (Expr, TestFunction, TrialFunction, Dx, grad, div, curl, inner, project)
+from .matrices import TPMatrix, SparseMatrix, get_simplified_tpmatrices
+from .integrators import RK4, IntegratorBase
+from .utilities import cross, apply_mask, dx
 from ._lib import ShenB200Error
 
 __version__ = '0.1.0'

@@ -1,0 +1,231 @@
+// pointwise.cu -- memory-bound element-wise kernels of the Navier-Stokes path:
+// cross product in physical space, spectral curl, pressure projection fused
+// with the Runge-Kutta stage update, Nyquist masking and generic RK4 axpy.
+//
+// Reference semantics restated:
+//   shenfun/optimization/cython/cross.pyx:25-40 (cross3D),
+//   shenfun/optimization/cython/applymask.pyx:15-169 (apply_mask),
+//   demo/NavierStokes.py:35-44 (NonlinearRHS: curl, cross, div-free projection),
+//   shenfun/utilities/integrators.py:587-599 (RK4 stage algebra),
+//   shenfun/fourier/matrices.py:149-176 (diagonal Fourier matrices (ik)^n).
+#include "common.cuh"
+
+namespace shb {
+
+constexpr int PW_THREADS = 256;
+
+static inline int pw_blocks(int64_t n, int per_thread = 1) {
+    int64_t b = (n + (int64_t)PW_THREADS * per_thread - 1) / ((int64_t)PW_THREADS * per_thread);
+    int64_t cap = (int64_t)sm_count() * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// c = a x b, real, two points per thread (double2 loads)
+__global__ void __launch_bounds__(PW_THREADS) cross3d_real_kernel(
+    const double2 *__restrict__ a, const double2 *__restrict__ b, double2 *__restrict__ c, int64_t n2) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 a0 = a[i], a1 = a[n2 + i], a2 = a[2 * n2 + i];
+        const double2 b0 = b[i], b1 = b[n2 + i], b2 = b[2 * n2 + i];
+        double2 c0, c1, c2;
+        c0.x = a1.x * b2.x - a2.x * b1.x;  c0.y = a1.y * b2.y - a2.y * b1.y;
+        c1.x = a2.x * b0.x - a0.x * b2.x;  c1.y = a2.y * b0.y - a0.y * b2.y;
+        c2.x = a0.x * b1.x - a1.x * b0.x;  c2.y = a0.y * b1.y - a1.y * b0.y;
+        c[i] = c0; c[n2 + i] = c1; c[2 * n2 + i] = c2;
+    }
+}
+
+__global__ void __launch_bounds__(PW_THREADS) cross3d_real_tail_kernel(
+    const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ c, int64_t n, int64_t start) {
+    for (int64_t i = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a0 = a[i], a1 = a[n + i], a2 = a[2 * n + i];
+        const double b0 = b[i], b1 = b[n + i], b2 = b[2 * n + i];
+        c[i] = a1 * b2 - a2 * b1;
+        c[n + i] = a2 * b0 - a0 * b2;
+        c[2 * n + i] = a0 * b1 - a1 * b0;
+    }
+}
+
+__global__ void __launch_bounds__(PW_THREADS) cross3d_cplx_kernel(
+    const cplx *__restrict__ a, const cplx *__restrict__ b, cplx *__restrict__ c, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const cplx a0 = a[i], a1 = a[n + i], a2 = a[2 * n + i];
+        const cplx b0 = b[i], b1 = b[n + i], b2 = b[2 * n + i];
+        c[i] = csub(cmul(a1, b2), cmul(a2, b1));
+        c[n + i] = csub(cmul(a2, b0), cmul(a0, b2));
+        c[2 * n + i] = csub(cmul(a0, b1), cmul(a1, b0));
+    }
+}
+
+// out = i k x u  on [3][n0][n1][n2] complex
+__global__ void __launch_bounds__(PW_THREADS) curl_hat_kernel(
+    const cplx *__restrict__ u, cplx *__restrict__ out, const double *__restrict__ k0,
+    const double *__restrict__ k1, const double *__restrict__ k2, int n0, int n1, int n2) {
+    const int64_t n = (int64_t)n0 * n1 * n2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int i2 = (int)(i % n2);
+        const int64_t r = i / n2;
+        const int i1 = (int)(r % n1);
+        const int i0 = (int)(r / n1);
+        const double kx = __ldg(&k0[i0]), ky = __ldg(&k1[i1]), kz = __ldg(&k2[i2]);
+        const cplx ux = u[i], uy = u[n + i], uz = u[2 * n + i];
+        // (k x u) then times i:  i*(a+ib) = (-b, a)
+        const cplx cx = make_double2(ky * uz.x - kz * uy.x, ky * uz.y - kz * uy.y);
+        const cplx cy = make_double2(kz * ux.x - kx * uz.x, kz * ux.y - kx * uz.y);
+        const cplx cz = make_double2(kx * uy.x - ky * ux.x, kx * uy.y - ky * ux.y);
+        out[i] = make_double2(-cx.y, cx.x);
+        out[n + i] = make_double2(-cy.y, cy.x);
+        out[2 * n + i] = make_double2(-cz.y, cz.x);
+    }
+}
+
+// Fused: pressure projection + viscous term + RK4 stage update.
+//   dU   <- W_hat - k (k.W_hat)/k^2 - nu k^2 u_hat        (demo/NavierStokes.py:41-43, integrators.py:592-593)
+//   P    <- i (k.W_hat)/k^2                                (optional)
+//   U1   <- U1 + a_dt*dU ;  u_hat <- U0 + b_dt*dU (stages 0..2)  or  u_hat <- U1 (last stage)
+__global__ void __launch_bounds__(PW_THREADS) ns_rk_stage_kernel(
+    cplx *__restrict__ dU, cplx *__restrict__ u_hat, const cplx *__restrict__ U0, cplx *__restrict__ U1,
+    cplx *__restrict__ P, const double *__restrict__ k0, const double *__restrict__ k1,
+    const double *__restrict__ k2, int n0, int n1, int n2, double nu, double a_dt, double b_dt, int last) {
+    const int64_t n = (int64_t)n0 * n1 * n2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int i2 = (int)(i % n2);
+        const int64_t r = i / n2;
+        const int i1 = (int)(r % n1);
+        const int i0 = (int)(r / n1);
+        const double kx = __ldg(&k0[i0]), ky = __ldg(&k1[i1]), kz = __ldg(&k2[i2]);
+        const double kk = kx * kx + ky * ky + kz * kz;
+        const double ikk = kk > 0.0 ? 1.0 / kk : 0.0;
+        cplx w[3] = {dU[i], dU[n + i], dU[2 * n + i]};
+        const cplx kd = make_double2(kx * w[0].x + ky * w[1].x + kz * w[2].x,
+                                     kx * w[0].y + ky * w[1].y + kz * w[2].y);
+        const cplx p = make_double2(-kd.y * ikk, kd.x * ikk);       // i*kd/k^2
+        if (P) P[i] = p;
+        const double kv[3] = {kx, ky, kz};
+        const double lin = -nu * kk;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const cplx uh = u_hat[c * n + i];
+            // dU_c + i k_c P  =  dU_c + (-k_c p.y, k_c p.x)
+            cplx d = make_double2(w[c].x - kv[c] * p.y, w[c].y + kv[c] * p.x);
+            d.x = fma(lin, uh.x, d.x);
+            d.y = fma(lin, uh.y, d.y);
+            dU[c * n + i] = d;
+            cplx u1 = U1[c * n + i];
+            u1.x = fma(a_dt, d.x, u1.x);
+            u1.y = fma(a_dt, d.y, u1.y);
+            U1[c * n + i] = u1;
+            if (last) {
+                u_hat[c * n + i] = u1;
+            } else {
+                const cplx u0 = U0[c * n + i];
+                u_hat[c * n + i] = make_double2(fma(b_dt, d.x, u0.x), fma(b_dt, d.y, u0.y));
+            }
+        }
+    }
+}
+
+// generic RK4 stage: dU += L*u_hat (L real, broadcast over ncomp); U1 += a_dt dU; u_hat = U0 + b_dt dU | U1
+__global__ void __launch_bounds__(PW_THREADS) rk4_stage_kernel(
+    cplx *__restrict__ dU, cplx *__restrict__ u_hat, const cplx *__restrict__ U0, cplx *__restrict__ U1,
+    const double *__restrict__ L, int64_t n, int ncomp, double a_dt, double b_dt, int last) {
+    const int64_t tot = n * ncomp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+        cplx d = dU[i];
+        const cplx uh = u_hat[i];
+        if (L) {
+            const double l = L[i % n];
+            d.x = fma(l, uh.x, d.x);
+            d.y = fma(l, uh.y, d.y);
+            dU[i] = d;
+        }
+        cplx u1 = U1[i];
+        u1.x = fma(a_dt, d.x, u1.x);
+        u1.y = fma(a_dt, d.y, u1.y);
+        U1[i] = u1;
+        if (last) u_hat[i] = u1;
+        else {
+            const cplx u0 = U0[i];
+            u_hat[i] = make_double2(fma(b_dt, d.x, u0.x), fma(b_dt, d.y, u0.y));
+        }
+    }
+}
+
+// u *= mask (mask real, same shape as one component)
+__global__ void __launch_bounds__(PW_THREADS) apply_mask_kernel(cplx *__restrict__ u, const double *__restrict__ mask,
+                                                                int64_t n, int ncomp) {
+    const int64_t tot = n * ncomp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+        const double m = mask[i % n];
+        cplx x = u[i];
+        u[i] = make_double2(x.x * m, x.y * m);
+    }
+}
+
+}  // namespace shb
+
+using namespace shb;
+
+extern "C" {
+
+int shb_cross3d(const void *d_a, const void *d_b, void *d_c, int64_t n, int is_complex, void *stream) {
+    SHB_REQUIRE(d_a && d_b && d_c && n >= 0, "bad arguments");
+    if (n == 0) return SHB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (is_complex) {
+        cross3d_cplx_kernel<<<pw_blocks(n), PW_THREADS, 0, st>>>(
+            (const cplx *)d_a, (const cplx *)d_b, (cplx *)d_c, n);
+    } else if (n % 2 == 0) {
+        cross3d_real_kernel<<<pw_blocks(n / 2), PW_THREADS, 0, st>>>(
+            (const double2 *)d_a, (const double2 *)d_b, (double2 *)d_c, n / 2);
+    } else {
+        cross3d_real_tail_kernel<<<pw_blocks(n), PW_THREADS, 0, st>>>(
+            (const double *)d_a, (const double *)d_b, (double *)d_c, n, 0);
+    }
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_curl_hat(const void *d_u, void *d_out, const double *d_k0, const double *d_k1, const double *d_k2,
+                 int n0, int n1, int n2, void *stream) {
+    SHB_REQUIRE(d_u && d_out && d_k0 && d_k1 && d_k2, "null pointer");
+    const int64_t n = (int64_t)n0 * n1 * n2;
+    if (n == 0) return SHB_OK;
+    curl_hat_kernel<<<pw_blocks(n), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const cplx *)d_u, (cplx *)d_out, d_k0, d_k1, d_k2, n0, n1, n2);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_ns_rk_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, void *d_P,
+                    const double *d_k0, const double *d_k1, const double *d_k2, int n0, int n1, int n2,
+                    double nu, double a_dt, double b_dt, int last, void *stream) {
+    SHB_REQUIRE(d_dU && d_u_hat && d_U0 && d_U1 && d_k0 && d_k1 && d_k2, "null pointer");
+    const int64_t n = (int64_t)n0 * n1 * n2;
+    if (n == 0) return SHB_OK;
+    ns_rk_stage_kernel<<<pw_blocks(n), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (cplx *)d_dU, (cplx *)d_u_hat, (const cplx *)d_U0, (cplx *)d_U1, (cplx *)d_P, d_k0, d_k1, d_k2,
+        n0, n1, n2, nu, a_dt, b_dt, last);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_rk4_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, const double *d_L,
+                  int64_t n, int ncomp, double a_dt, double b_dt, int last, void *stream) {
+    SHB_REQUIRE(d_dU && d_u_hat && d_U0 && d_U1 && n >= 0 && ncomp >= 1, "bad arguments");
+    if (n == 0) return SHB_OK;
+    rk4_stage_kernel<<<pw_blocks(n * ncomp), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (cplx *)d_dU, (cplx *)d_u_hat, (const cplx *)d_U0, (cplx *)d_U1, d_L, n, ncomp, a_dt, b_dt, last);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_apply_mask(void *d_u, const double *d_mask, int64_t n, int ncomp, void *stream) {
+    SHB_REQUIRE(d_u && d_mask && n >= 0 && ncomp >= 1, "bad arguments");
+    if (n == 0) return SHB_OK;
+    apply_mask_kernel<<<pw_blocks(n * ncomp), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (cplx *)d_u, d_mask, n, ncomp);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+}  // extern "C"

@@ -52,6 +52,24 @@ class FourierBase(SpectralBase):
     def l2_norm_sq(self, i=None):
         return np.ones(self.N) if i is None else 1
 
+    def is_orthogonal_basis(self):
+        return True
+
+    def spectral_matrix(self, d_test, d_trial, trial=None):
+        """(phi_l^(d_trial), phi_k^(d_test))_w: diagonal (fourier/matrices.py:149-176,
+        with the domain scaling of matrixbase.py:690-691)."""
+        from .matrices import SparseMatrix
+        k = self.wavenumbers(bcast=False, scaled=False, eliminate_highest_freq=False).astype(float)
+        n = d_test+d_trial
+        if n > 0:
+            val = (1j*k)**d_trial*(-1j*k)**d_test
+            if n % 2 == 0:
+                val = val.real
+            val = val*float(self.domain_factor())**n
+        else:
+            val = np.ones(len(k))
+        return SparseMatrix({0: val}, (len(k), len(k)))
+
 
 class R2C(FourierBase):
     """Real-to-complex Fourier space (fourier/bases.py:283-497)."""

@@ -65,3 +65,46 @@ def fft_r2c_forward(u, out, outer, inner, n_fft, N, scale):
 def fft_c2r_backward(uh, out, outer, inner, n_fft, N, scale=1.0, dealias_direct=False):
     _call('shb_fft_c2r_backward', _req(uh, C128, 'in'), _req(out, F64, 'out'),
           outer, inner, n_fft, N, scale, int(dealias_direct), _lib.stream_ptr())
+
+
+def cross3d(a, b, c):
+    """c = a x b on (3, ...) arrays (utilities/__init__.py:177-210 `cross`)."""
+    assert a.shape == b.shape == c.shape and a.shape[0] == 3
+    n = a[0].numel()
+    dt = a.dtype
+    _call('shb_cross3d', _req(a, dt, 'a'), _req(b, dt, 'b'), _req(c, dt, 'c'), n, int(dt.is_complex),
+          _lib.stream_ptr())
+    return c
+
+
+def curl_hat(u_hat, out, k0, k1, k2):
+    n0, n1, n2 = u_hat.shape[1:]
+    _call('shb_curl_hat', _req(u_hat, C128, 'u_hat'), _req(out, C128, 'out'), _req(k0, F64, 'k0'),
+          _req(k1, F64, 'k1'), _req(k2, F64, 'k2'), n0, n1, n2, _lib.stream_ptr())
+    return out
+
+
+def ns_rk_stage(dU, u_hat, U0, U1, P, k0, k1, k2, nu, a_dt, b_dt, last):
+    n0, n1, n2 = u_hat.shape[1:]
+    _call('shb_ns_rk_stage', _req(dU, C128, 'dU'), _req(u_hat, C128, 'u_hat'), _req(U0, C128, 'U0'),
+          _req(U1, C128, 'U1'), None if P is None else _req(P, C128, 'P'), _req(k0, F64, 'k0'),
+          _req(k1, F64, 'k1'), _req(k2, F64, 'k2'), n0, n1, n2, float(nu), float(a_dt), float(b_dt),
+          int(last), _lib.stream_ptr())
+
+
+def rk4_stage(dU, u_hat, U0, U1, L, a_dt, b_dt, last):
+    ncomp = 1
+    n = u_hat.numel()
+    if L is not None:
+        n = L.numel()
+        ncomp = u_hat.numel()//n
+    _call('shb_rk4_stage', _req(dU, C128, 'dU'), _req(u_hat, C128, 'u_hat'), _req(U0, C128, 'U0'),
+          _req(U1, C128, 'U1'), None if L is None else _req(L, F64, 'L'), n, ncomp, float(a_dt),
+          float(b_dt), int(last), _lib.stream_ptr())
+
+
+def apply_mask(u_hat, mask):
+    n = mask.numel()
+    _call('shb_apply_mask', _req(u_hat, C128, 'u_hat'), _req(mask, F64, 'mask'), n, u_hat.numel()//n,
+          _lib.stream_ptr())
+    return u_hat
