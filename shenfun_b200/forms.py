@@ -125,20 +125,38 @@ def Dx(u, x, k=1):
 
 
 def grad(u):
+    """Gradient: scalar -> vector; vector -> tensor with component (i, j) = d u_i / d x_j
+    stored at index i*nd + j."""
     u = as_expr(u)
-    assert u.rank == 0, 'grad of a scalar only'
     nd = u.dimensions
-    return Expr(u.basis, [Dx(u, i, 1).terms[0] for i in range(nd)], 1)
+    if u.rank == 0:
+        return Expr(u.basis, [Dx(u, j, 1).terms[0] for j in range(nd)], 1)
+    assert u.rank == 1, 'grad of scalars and vectors only'
+    terms = []
+    for i in range(nd):
+        ui = Expr(u.basis, [u.terms[i]], 0)
+        for j in range(nd):
+            terms.append(Dx(ui, j, 1).terms[0])
+    return Expr(u.basis, terms, 2)
 
 
 def div(u):
+    """Divergence: vector -> scalar; tensor -> vector (contraction over the last index)."""
     u = as_expr(u)
-    assert u.rank == 1
     nd = u.dimensions
-    terms = []
+    if u.rank == 1:
+        terms = []
+        for i in range(nd):
+            terms += Dx(Expr(u.basis, [u.terms[i]], 0), i, 1).terms[0]
+        return Expr(u.basis, [terms], 0)
+    assert u.rank == 2
+    out = []
     for i in range(nd):
-        terms += Dx(u[i], i, 1).terms[0]
-    return Expr(u.basis, [terms], 0)
+        terms = []
+        for j in range(nd):
+            terms += Dx(Expr(u.basis, [u.terms[i*nd+j]], 0), j, 1).terms[0]
+        out.append(terms)
+    return Expr(u.basis, out, 1)
 
 
 def curl(u):

@@ -186,5 +186,8 @@ def get_simplified_tpmatrices(mats):
     if isinstance(mats, TPMatrix):
         mats = [mats]
     if all(m.is_diagonal() for m in mats):
-        return [DiagonalTPMatrix(mats)]
+        groups = {}
+        for m in mats:
+            groups.setdefault(m.global_index, []).append(m)
+        return [DiagonalTPMatrix(g) for g in groups.values()]
     return list(mats)

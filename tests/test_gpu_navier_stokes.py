@@ -48,7 +48,7 @@ def test_cross_and_curl_kernels_against_numpy():
     b = rng.standard_normal((3, 9, 7, 5))
     c = torch.empty(3, 9, 7, 5, dtype=torch.float64, device='cuda')
     sf.ops.cross3d(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), c)
-    assert np.array_equal(c.cpu().numpy(), np.cross(a, b, axis=0))
+    assert rel_l2(c.cpu().numpy(), np.cross(a, b, axis=0)) < 1e-15
     ac = a+1j*rng.standard_normal(a.shape)
     bc = b+1j*rng.standard_normal(a.shape)
     cc = torch.empty(3, 9, 7, 5, dtype=torch.complex128, device='cuda')
@@ -62,8 +62,8 @@ def test_cross_and_curl_kernels_against_numpy():
 
 
 def test_full_size_divergence_free_and_energy_decay():
-    """512^3 with 3/2 padding (BASELINE size): one step keeps the field solenoidal and
-    dissipates energy at the viscous rate (size-independent properties)."""
+    """128^3 with 3/2 padding: one step keeps the field solenoidal and dissipates energy
+    at the viscous rate (size-independent properties; 512^3 runs in bench.py)."""
     s = ns.FusedNS((128, 128, 128), dt=0.001, padding_factor=1.5).initialize()
     k0 = s.energy()
     s.step()
