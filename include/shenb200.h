@@ -109,6 +109,81 @@ SHB_API int shb_rk4_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U
  * shenfun/optimization/cython/applymask.pyx:15-169 (`apply_mask`).          */
 SHB_API int shb_apply_mask(void *d_u, const double *d_mask, int64_t n, int ncomp, void *stream);
 
+/* ------------------------------------------------------------------ */
+/* Batched banded line solvers along the middle axis of [outer][n][inner].
+ * Diagonals are spaced `step` apart (2 for Shen bases: offsets ..,-2,0,2,..;
+ * 1 otherwise), kl lower and ku upper.  Matrix storage on the device:
+ * mat[kl+1+ku][n], row d holds offset (d-kl)*step, entry [d][i] = M[i, i+off].
+ * Factor storage: fac[kl+1+ku][outer][n][inner] per line, or fac[kl+1+ku][n]
+ * when `fac_shared`.                                                         */
+
+/* Per-line LU (no pivoting) of A(line) = sum_m scale_m[line] * M_m, nmat <= 4;
+ * d_mats / d_scales are HOST arrays of device pointers (scale NULL = 1).
+ * `pin_line` >= 0 replaces row 0 of that line by the identity (gauge).
+ * Replaces la.SolverGeneric1ND.assemble/perform_lu/get_data
+ * (shenfun/la.py:1231-1319) and the X_LU kernels (optimization/cython/la.pyx:199-303). */
+SHB_API int shb_banded_factor(int kl, int ku, int step, int nmat, const double *const *d_mats,
+                              const double *const *d_scales, double *d_fac, int64_t outer, int64_t inner,
+                              int n, int64_t pin_line, void *stream);
+
+/* In-place forward/backward substitution on u[outer][n_u][inner] (first n rows).
+ * Replaces TDMA_Solve / PDMA_Solve / FDMA_Solve / TwoDMA / ThreeDMA / HeptaDMA /
+ * DiagMA_Solve and SolverGeneric1ND_solve_data (la.pyx:371-611).             */
+SHB_API int shb_banded_solve(int kl, int ku, int step, void *d_u, const double *d_fac, int64_t outer,
+                             int64_t inner, int n, int n_u, int fac_shared, int is_complex, void *stream);
+
+/* out (+)= sum_m scale_m[line] * M_m u along the axis; M_m given as mat[ndiag][n_rows]
+ * with explicit offsets.  Replaces SparseMatrix.matvec / Matvec.pyx:430-512.    */
+SHB_API int shb_banded_matvec(const void *d_u, void *d_out, int nmat, int ndiag, const int *offsets,
+                              const double *const *d_mats, const double *const *d_scales, int64_t outer,
+                              int64_t inner, int n_rows, int n_cols, int n_u, int n_out, int accumulate,
+                              int is_complex, void *stream);
+
+/* Chebyshev-Galerkin Helmholtz (alfa*A + beta*B), per-line alfa/beta[outer*inner]:
+ * factor into fac[4][outer][n][inner] = (d0, d1, d2, L) and solve.  Replaces
+ * LU_Helmholtz / Solve_Helmholtz (chebyshev/la.py:131-351, la.pyx:708-947).   */
+SHB_API int shb_helmholtz_factor(const double *d_A0, const double *d_A2, const double *d_A4,
+                                 const double *d_Bm2, const double *d_B0, const double *d_B2,
+                                 const double *d_alfa, const double *d_beta, double *d_fac, int64_t outer,
+                                 int64_t inner, int n, void *stream);
+SHB_API int shb_helmholtz_solve(const void *d_b, void *d_u, const double *d_fac, int64_t outer, int64_t inner,
+                                int n, int n_u, int is_complex, void *stream);
+
+/* ------------------------------------------------------------------ */
+/* Chebyshev (Gauss-Chebyshev points) axis transforms on [outer][n][inner],
+ * real (is_real) or complex data (real and imaginary parts in ONE pass --
+ * the reference's DCTWrap runs two, chebyshev/bases.py:100-115).
+ * A composite (Shen) basis phi_k = sum_i sten[i][k] T_{k+soff[i]}, k < dim,
+ * is given by its stencil diagonals (device arrays, NULL = ones); the
+ * orthogonal basis is nsten = 1, soff = {0}, sten = NULL, dim = n_spec.       */
+
+/* Weighted scalar product: out_k = sum_i sten_i[k] * S_{k+soff_i},
+ * S = scale * DCT-II(in) (FFTW REDFT10 convention), rows dim..n_spec-1 zeroed.
+ * Replaces chebyshev.Orthogonal._evaluate_scalar_product (chebyshev/bases.py:340-353),
+ * CompositeBase._evaluate_scalar_product (spectralbase.py:1462-1474) and the
+ * truncation (spectralbase.py:1363-1367).  scale = pi/(2*domain_factor*n_phys). */
+SHB_API int shb_cheb_scalar_product(const void *d_in, void *d_out, int64_t outer, int64_t inner, int n_phys,
+                                    int n_spec, double scale, int is_real, int dim, int nsten, const int *soff,
+                                    const double *const *d_sten, void *stream);
+
+/* Evaluation on the quadrature points: c = K^T u_hat (+ boundary lift from rows
+ * dim..dim+nbc-1 through bc_lift[nbc][4]), zero-padded to n_phys, then
+ * u = 0.5*DCT-III(c) + c_0/2.  Replaces spectralbase.py:1369-1390 (padding),
+ * CompositeBase.to_ortho :1616-1634 and chebyshev/bases.py:315-338.             */
+SHB_API int shb_cheb_backward(const void *d_in, void *d_out, int64_t outer, int64_t inner, int n_phys,
+                              int n_spec, int is_real, int dim, int nsten, const int *soff,
+                              const double *const *d_sten, int nbc, const double *d_bc_lift, void *stream);
+
+/* ------------------------------------------------------------------ */
+/* Dense contraction along the middle axis with a real operator matrix A[M][K]
+ * (fp64 tensor cores):  out[o][i][c] = sum_j A[i][j] * u[o][j][c],
+ * u : [outer][K][inner] real or complex, out : [outer][M][inner].  Legendre/Jacobi
+ * Vandermonde transforms: replaces SpectralBase._evaluate_expansion_all /
+ * _evaluate_scalar_product kinds 'vandermonde' and 'recursive'
+ * (shenfun/spectralbase.py:448-491, 516-558; optimization/cython/transforms.pyx:175-323). */
+SHB_API int shb_gemm_axis(const double *d_A, const void *d_u, void *d_out, int M, int K, int64_t outer,
+                          int64_t inner, int is_complex, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

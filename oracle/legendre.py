@@ -1,0 +1,2 @@
+"""Oracle entry points used by oracle/tensorproduct.py for 'LEG' axes (see polybases.py)."""
+from .polybases import forward_axis, backward_axis, scalar_product_axis  # noqa: F401

@@ -16,6 +16,8 @@ from .forms import (Expr, TestFunction, TrialFunction, Dx, grad, div, curl, inne
 from .matrices import TPMatrix, SparseMatrix, get_simplified_tpmatrices
 from .integrators import RK4, IntegratorBase
 from .utilities import cross, apply_mask, dx
+from . import la, chebyshev, legendre
+from .polybase import BoundaryConditions
 from ._lib import ShenB200Error
 
 __version__ = '0.1.0'

@@ -33,6 +33,14 @@ def _declare(lib):
         'shb_ns_rk_stage': [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f64, f64, f64, i32, vp],
         'shb_rk4_stage': [vp, vp, vp, vp, vp, i64, i32, f64, f64, i32, vp],
         'shb_apply_mask': [vp, vp, i64, i32, vp],
+        'shb_banded_factor': [i32, i32, i32, i32, vp, vp, vp, i64, i64, i32, i64, vp],
+        'shb_banded_solve': [i32, i32, i32, vp, vp, i64, i64, i32, i32, i32, i32, vp],
+        'shb_banded_matvec': [vp, vp, i32, i32, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, i32, vp],
+        'shb_helmholtz_factor': [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, vp],
+        'shb_helmholtz_solve': [vp, vp, vp, i64, i64, i32, i32, i32, vp],
+        'shb_cheb_scalar_product': [vp, vp, i64, i64, i32, i32, f64, i32, i32, i32, vp, vp, vp],
+        'shb_gemm_axis': [vp, vp, vp, i32, i32, i64, i64, i32, vp],
+        'shb_cheb_backward': [vp, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

@@ -1,0 +1,126 @@
+"""Chebyshev bases (first kind, Gauss-Chebyshev points) on the device.
+
+Host-side mirror of shenfun/chebyshev/bases.py: `Orthogonal` :118-470 and the
+composite bases defined by their stencils (`ShenDirichlet` :476-554, `ShenNeumann`
+:937, `ShenBiharmonic` :1249, and the mixed Dirichlet/Neumann variants).  The fast
+transforms are DCT-II/III built on the complex FFT kernels, with the quadrature
+scaling, the Shen stencil recombination and zero-padding fused
+(`shb_cheb_scalar_product`, `shb_cheb_backward`); complex data is transformed in one
+pass.  Only quad='GC' (the reference default) is on the device path.
+"""
+import numpy as np
+
+from .polybase import PolyBase, BoundaryConditions
+from . import ops
+
+__all__ = ('Orthogonal', 'ShenDirichlet', 'ShenNeumann', 'ShenBiharmonic', 'CompositeBase', 'make_space')
+
+
+class Orthogonal(PolyBase):
+    def __init__(self, N, quad='GC', padding_factor=1, domain=(-1., 1.), dtype=float, dealias_direct=False,
+                 bc=None, scaled=False, **kw):
+        quad = 'GC' if quad is None else quad
+        if quad != 'GC':
+            raise NotImplementedError("Chebyshev quad='GC' only on the device path (DCT-I for 'GL' is not built)")
+        PolyBase.__init__(self, N, quad, padding_factor=padding_factor, domain=domain, dtype=dtype,
+                          dealias_direct=dealias_direct, bc=bc, scaled=scaled)
+
+    @staticmethod
+    def family():
+        return 'chebyshev'
+
+    @staticmethod
+    def short_name():
+        return 'T'
+
+    def points_and_weights(self, N=None, map_true_domain=False, weighted=True):
+        """chebyshev/bases.py:201-216: x_j = cos(pi (2j+1)/(2N)), w = pi/N."""
+        if N is None:
+            N = self.physical_len()
+        points, weights = np.polynomial.chebyshev.chebgauss(N)
+        points = points.astype(float)
+        if map_true_domain:
+            points = self.map_true_domain(points)
+        return points, weights.astype(float)
+
+    def ortho_norm_sq(self, N=None):
+        N = self.N if N is None else N
+        h = np.full(N, np.pi/2)
+        h[0] = np.pi
+        return h
+
+    def ortho_deriv_matrix(self, N, k):
+        """T_j' = sum_{i<j, i+j odd} (2/c_i) j T_i ; higher orders by exact integer products."""
+        D1 = np.zeros((N, N))
+        j = np.arange(N)
+        for i in range(N):
+            cols = j[(j > i) & ((i+j) % 2 == 1)]
+            D1[i, cols] = 2.0*cols/(2.0 if i == 0 else 1.0)
+        D = np.eye(N)
+        for _ in range(k):
+            D = D1 @ D
+        return D
+
+    def boundary_values(self, n, order, side):
+        n = np.asarray(n, dtype=float)
+        sgn = 1.0 if side == 'right' else -1.0
+        if order == 0:
+            return sgn**n
+        if order == 1:
+            return sgn**(n+1)*n**2
+        if order == 2:
+            return sgn**n*n**2*(n**2-1)/3
+        if order == 3:
+            return sgn**(n+1)*n**2*(n**2-1)*(n**2-4)/15
+        raise NotImplementedError
+
+    def _canonical_stencil(self, st, k):
+        kind = self.boundary_condition()
+        if kind == 'Dirichlet':
+            return {0: np.ones(len(k)), 2: -np.ones(len(k))}
+        if kind == 'Neumann':
+            return {0: np.ones(len(k)), 2: -(k/(k+2.0))**2}
+        if kind == 'Biharmonic':
+            return {0: np.ones(len(k)), 2: (-2.0*k-4)/(k+3), 4: (k+1.0)/(k+3)}
+        return st
+
+    # ---- device transforms ---------------------------------------------------------------------
+    def _scalar_product_axis(self, u, out, outer, inner):
+        offs, arrs = self._device_stencil()
+        n = self.physical_len()
+        scale = np.pi/(2*float(self.domain_factor())*n)
+        ops.cheb_scalar_product(u, out, outer, inner, n, self.N, scale, self.dim(), offs, arrs)
+
+    def _backward_axis(self, uh, out, outer, inner):
+        offs, arrs = self._device_stencil()
+        nbc = self.bcs.num_bcs() if self.has_nonhomogeneous_bcs else 0
+        lift = None
+        if nbc:
+            if 'bc_lift' not in self._tables:
+                self._tables['bc_lift'] = ops.as_device_tensor(np.ascontiguousarray(self.bc_basis()))
+            lift = self._tables['bc_lift']
+        ops.cheb_backward(uh, out, outer, inner, self.physical_len(), self.N, self.dim(), offs, arrs, nbc, lift)
+
+
+CompositeBase = Orthogonal
+
+
+def ShenDirichlet(N, bc=(0, 0), **kw):
+    return Orthogonal(N, bc=bc, **kw)
+
+
+def ShenNeumann(N, bc=None, **kw):
+    return Orthogonal(N, bc={'left': {'N': 0}, 'right': {'N': 0}} if bc is None else bc, **kw)
+
+
+def ShenBiharmonic(N, bc=(0, 0, 0, 0), **kw):
+    return Orthogonal(N, bc=bc, **kw)
+
+
+def make_space(N, bc=None, quad=None, domain=None, dtype='d', scaled=None, basis=None, padding_factor=1,
+               dealias_direct=False, **kw):
+    par = dict(quad=quad or 'GC', padding_factor=padding_factor, dealias_direct=dealias_direct,
+               dtype=np.dtype(dtype), scaled=bool(scaled))
+    if domain is not None:
+        par['domain'] = tuple(float(d) for d in domain)
+    return Orthogonal(N, bc=bc, **par)

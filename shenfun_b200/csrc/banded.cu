@@ -1,0 +1,427 @@
+// banded.cu -- batched banded line solvers and mat-vecs along the middle axis of
+// [outer][n][inner], one line per (outer, inner) pair -- i.e. one line per Fourier
+// wavenumber pair in the tensor-product solvers.
+//
+// Parallelisation: one thread per line with the lanes of a warp running along the
+// contiguous `inner` index, so every global access of the sweep is coalesced along
+// the batch; the recurrence itself runs sequentially down the (strided) solve axis.
+//
+//   * banded_factor_kernel : per-line LU without pivoting of  A(line) = sum_m s_m(line) M_m,
+//       M_m shared banded matrices (diagonals spaced `step` apart: 2 for the Shen
+//       bases, whose even/odd unknowns decouple), factors written in the batch layout
+//   * banded_solve_kernel  : forward + backward substitution, in place, factors either
+//       per line (SolverGeneric1ND) or shared (TDMA/PDMA/... of one matrix, inverse mass)
+//   * banded_matvec_kernel : out (+)= sum_m s_m(line) M_m u
+//   * helmholtz_factor/solve: Chebyshev-Galerkin (alfa*A + beta*B) with A upper
+//       triangular with constant rows (LU with one lower and three upper "diagonals",
+//       back substitution with running even/odd sums)
+//
+// Reference semantics restated (no code shared):
+//   shenfun/la.py:291-820 (TDMA/PDMA/FDMA/TwoDMA/ThreeDMA/HeptaDMA LU + solve),
+//   shenfun/la.py:1183-1434 (SolverGeneric1ND), optimization/cython/la.pyx:199-611,
+//   chebyshev/la.py:131-351 + la.pyx:708-973 (Helmholtz), Matvec.pyx:430-512.
+#include "common.cuh"
+
+namespace shb {
+
+constexpr int BD_THREADS = 128;
+constexpr int BD_MAXMAT = 4;
+
+struct BandedDesc {
+    int64_t outer, inner;
+    int n;            // matrix size (rows solved)
+    int n_u;          // rows of the data arrays along the axis (n_u >= n)
+    int step;         // spacing of the diagonals (1 or 2)
+    int nmat;
+    const double *mats[BD_MAXMAT];    // each [KL+1+KU][n]: rows ordered by offset -KL*step .. +KU*step,
+                                      // entry [d][i] = M[i, i + off_d] (0 outside the matrix)
+    const double *scales[BD_MAXMAT];  // per line [outer*inner] or NULL (= 1)
+    double *fac;                      // [KL+1+KU][outer][n][inner] (per line) or [KL+1+KU][n] (shared)
+    int fac_shared;
+    int64_t pin_line;                 // line whose row 0 is replaced by the identity (-1: none)
+};
+
+template <class T> struct Num;
+template <> struct Num<double> {
+    static __device__ __forceinline__ double zero() { return 0.0; }
+    static __device__ __forceinline__ double fnma(double a, double x, double y) { return fma(-a, x, y); }  // y - a x
+    static __device__ __forceinline__ double mul(double a, double x) { return a * x; }
+    static __device__ __forceinline__ double div(double x, double a) { return x / a; }
+    static __device__ __forceinline__ double add(double x, double y) { return x + y; }
+};
+template <> struct Num<cplx> {
+    static __device__ __forceinline__ cplx zero() { return make_double2(0.0, 0.0); }
+    static __device__ __forceinline__ cplx fnma(double a, cplx x, cplx y) {
+        return make_double2(fma(-a, x.x, y.x), fma(-a, x.y, y.y));
+    }
+    static __device__ __forceinline__ cplx mul(double a, cplx x) { return make_double2(a * x.x, a * x.y); }
+    static __device__ __forceinline__ cplx div(cplx x, double a) { return make_double2(x.x / a, x.y / a); }
+    static __device__ __forceinline__ cplx add(cplx x, cplx y) { return make_double2(x.x + y.x, x.y + y.y); }
+};
+
+// ---- per-line LU ---------------------------------------------------------------------
+// Row i of A: lo[p] = A[i, i-p*step] (p=1..KL), dg = A[i,i], up[q] = A[i, i+q*step] (q=1..KU).
+// Factors stored per row i: L_p[i] (multiplier against row i-p*step), D[i], U_q[i].
+// Layout of `fac`: diagonal index d = KL-p for L_p, KL for D, KL+q for U_q.
+template <int KL, int KU>
+__global__ void __launch_bounds__(BD_THREADS) banded_factor_kernel(const __grid_constant__ BandedDesc d) {
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nlines = d.outer * d.inner;
+    if (line >= nlines) return;
+    const int64_t o = line / d.inner, c = line % d.inner;
+    const int n = d.n, step = d.step;
+    constexpr int ND = KL + 1 + KU;
+    double s[BD_MAXMAT];
+#pragma unroll
+    for (int m = 0; m < BD_MAXMAT; ++m)
+        s[m] = (m < d.nmat) ? (d.scales[m] ? d.scales[m][line] : 1.0) : 0.0;
+    const bool pin = (line == d.pin_line);
+    const int64_t fstride_d = d.outer * (int64_t)n * d.inner;   // between diagonals
+    double *fac = d.fac + (o * n) * d.inner + c;
+
+    for (int par = 0; par < step; ++par) {
+        // window of the previous KL pivot rows of this parity: D and U_1..U_KU
+        double wD[KL > 0 ? KL : 1], wU[KL > 0 ? KL : 1][KU > 0 ? KU : 1];
+#pragma unroll
+        for (int p = 0; p < (KL > 0 ? KL : 1); ++p) {
+            wD[p] = 1.0;
+#pragma unroll
+            for (int q = 0; q < (KU > 0 ? KU : 1); ++q) wU[p][q] = 0.0;
+        }
+        for (int i = par; i < n; i += step) {
+            double a[ND];
+#pragma unroll
+            for (int dd = 0; dd < ND; ++dd) {
+                double v = 0.0;
+#pragma unroll
+                for (int m = 0; m < BD_MAXMAT; ++m)
+                    if (m < d.nmat) v = fma(s[m], __ldg(&d.mats[m][dd * n + i]), v);
+                a[dd] = v;
+            }
+            if (pin && i == 0) {
+#pragma unroll
+                for (int dd = 0; dd < ND; ++dd) a[dd] = (dd == KL) ? 1.0 : 0.0;
+            }
+            // eliminate against rows i-KL*step ... i-step (farthest first)
+            double l[KL > 0 ? KL : 1];
+#pragma unroll
+            for (int p = KL; p >= 1; --p) {
+                // a[KL-p] is the entry in column i-p*step; pivot row is window slot p-1
+                const double lp = (i - p * step >= 0) ? a[KL - p] / wD[p - 1] : 0.0;
+                l[p - 1] = lp;
+                // row i -= lp * (row i-p*step): that row has U_q at columns i-p*step+q*step
+#pragma unroll
+                for (int q = 1; q <= KU; ++q) {
+                    const int col = KL - p + q;      // index into a[] of column i+(q-p)*step
+                    if (col < ND) a[col] = fma(-lp, wU[p - 1][q - 1], a[col]);
+                }
+            }
+            // store
+#pragma unroll
+            for (int p = 1; p <= KL; ++p) fac[(KL - p) * fstride_d + (int64_t)i * d.inner] = l[p - 1];
+#pragma unroll
+            for (int dd = KL; dd < ND; ++dd) fac[dd * fstride_d + (int64_t)i * d.inner] = a[dd];
+            // slide the window
+#pragma unroll
+            for (int p = KL - 1; p >= 1; --p) {
+                wD[p] = wD[p - 1];
+#pragma unroll
+                for (int q = 0; q < KU; ++q) wU[p][q] = wU[p - 1][q];
+            }
+            if (KL > 0) {
+                wD[0] = a[KL];
+#pragma unroll
+                for (int q = 0; q < KU; ++q) wU[0][q] = a[KL + 1 + q];
+            }
+        }
+    }
+}
+
+// ---- substitution -----------------------------------------------------------------------
+template <int KL, int KU, class T>
+__global__ void __launch_bounds__(BD_THREADS) banded_solve_kernel(T *__restrict__ u, const double *__restrict__ facp,
+                                                                  int64_t outer, int64_t inner, int n, int n_u,
+                                                                  int step, int fac_shared) {
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= outer * inner) return;
+    const int64_t o = line / inner, c = line % inner;
+    T *x = u + (o * n_u) * inner + c;
+    const int64_t fs_i = fac_shared ? 1 : inner;                                   // between rows
+    const int64_t fs_d = fac_shared ? (int64_t)n : outer * (int64_t)n * inner;     // between diagonals
+    const double *fac = fac_shared ? facp : facp + (o * n) * inner + c;
+    for (int par = 0; par < step; ++par) {
+        // forward: y_i = b_i - sum_p L_p[i] y_{i-p*step}
+        T w[KL > 0 ? KL : 1];
+#pragma unroll
+        for (int p = 0; p < (KL > 0 ? KL : 1); ++p) w[p] = Num<T>::zero();
+        if (KL > 0) {
+            for (int i = par; i < n; i += step) {
+                T y = x[(int64_t)i * inner];
+#pragma unroll
+                for (int p = 1; p <= KL; ++p)
+                    y = Num<T>::fnma(fac[(KL - p) * fs_d + i * fs_i], w[p - 1], y);
+                x[(int64_t)i * inner] = y;
+#pragma unroll
+                for (int p = KL - 1; p >= 1; --p) w[p] = w[p - 1];
+                w[0] = y;
+            }
+        }
+        // backward: x_i = (y_i - sum_q U_q[i] x_{i+q*step}) / D[i]
+        T z[KU > 0 ? KU : 1];
+#pragma unroll
+        for (int q = 0; q < (KU > 0 ? KU : 1); ++q) z[q] = Num<T>::zero();
+        int last = par + ((n - 1 - par) / step) * step;
+        if (n - 1 - par < 0) continue;
+        for (int i = last; i >= par; i -= step) {
+            T y = x[(int64_t)i * inner];
+#pragma unroll
+            for (int q = 1; q <= KU; ++q)
+                y = Num<T>::fnma(fac[(KL + q) * fs_d + i * fs_i], z[q - 1], y);
+            y = Num<T>::div(y, fac[KL * fs_d + i * fs_i]);
+            x[(int64_t)i * inner] = y;
+#pragma unroll
+            for (int q = KU - 1; q >= 1; --q) z[q] = z[q - 1];
+            if (KU > 0) z[0] = y;
+        }
+    }
+}
+
+// ---- mat-vec ------------------------------------------------------------------------------
+// out[o][i][c] (+)= sum_m s_m(line) sum_d M_m[d][i] u[o][i+off_d][c],  offsets given explicitly
+struct MatvecDesc {
+    int64_t outer, inner;
+    int n_rows, n_cols;     // matrix shape
+    int n_u, n_out;         // rows of the arrays along the axis
+    int nmat, ndiag;
+    int offs[16];
+    const double *mats[BD_MAXMAT];    // [ndiag][n_rows]
+    const double *scales[BD_MAXMAT];
+    int accumulate;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) banded_matvec_kernel(const T *__restrict__ u, T *__restrict__ out,
+                                                            const __grid_constant__ MatvecDesc d) {
+    const int64_t tot = d.outer * (int64_t)d.n_out * d.inner;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tot;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx % d.inner;
+        const int64_t r = idx / d.inner;
+        const int i = (int)(r % d.n_out);
+        const int64_t o = r / d.n_out;
+        const int64_t line = o * d.inner + c;
+        T acc = Num<T>::zero();
+        if (i < d.n_rows) {
+            const T *ul = u + (o * d.n_u) * d.inner + c;
+            for (int m = 0; m < d.nmat; ++m) {
+                const double s = d.scales[m] ? d.scales[m][line] : 1.0;
+                T part = Num<T>::zero();
+                for (int k = 0; k < d.ndiag; ++k) {
+                    const int j = i + d.offs[k];
+                    if (j >= 0 && j < d.n_cols) {
+                        const double a = __ldg(&d.mats[m][k * d.n_rows + i]);
+                        part = Num<T>::fnma(-a, ul[(int64_t)j * d.inner], part);
+                    }
+                }
+                acc = Num<T>::fnma(-s, part, acc);
+            }
+        }
+        if (d.accumulate) out[idx] = Num<T>::add(out[idx], acc);
+        else out[idx] = acc;
+    }
+}
+
+// ---- Chebyshev Helmholtz ------------------------------------------------------------------
+// (alfa*A + beta*B) u = b,  A: diagonals 0,2,4 with A[i, i+2q] = A4[i] for q >= 2 (constant rows),
+// B: diagonals -2, 0, 2.  Per line: forward recurrence for L, d0, d1, d2 (la.pyx:744-756).
+__global__ void __launch_bounds__(BD_THREADS) helmholtz_factor_kernel(
+    const double *__restrict__ A0, const double *__restrict__ A2, const double *__restrict__ A4,
+    const double *__restrict__ Bm2, const double *__restrict__ B0, const double *__restrict__ B2,
+    const double *__restrict__ alfa, const double *__restrict__ beta, double *__restrict__ fac,
+    int64_t outer, int64_t inner, int n) {
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= outer * inner) return;
+    const int64_t o = line / inner, c = line % inner;
+    const double al = alfa[line], be = beta[line];
+    const int64_t fs_d = outer * (int64_t)n * inner;
+    double *f = fac + (o * n) * inner + c;     // f[d*fs_d + i*inner]: d = 0:d0 1:d1 2:d2 3:L
+    // two interleaved chains (even / odd rows)
+    double pd0[2], pd1[2], pd2[2];
+    for (int i = 0; i < n; ++i) {
+        const int par = i & 1;
+        double d0 = al * __ldg(&A0[i]) + be * __ldg(&B0[i]);
+        double d1 = (i < n - 2) ? al * __ldg(&A2[i]) + be * __ldg(&B2[i]) : 0.0;
+        double d2 = (i < n - 4) ? al * __ldg(&A4[i]) : 0.0;
+        if (i >= 2) {
+            const double L = be * __ldg(&Bm2[i - 2]) / pd0[par];
+            f[3 * fs_d + (int64_t)(i - 2) * inner] = L;
+            d0 -= L * pd1[par];
+            if (i < n - 2) d1 -= L * pd2[par];
+            if (i < n - 4) d2 -= L * pd2[par];
+        }
+        f[0 * fs_d + (int64_t)i * inner] = d0;
+        f[1 * fs_d + (int64_t)i * inner] = d1;
+        f[2 * fs_d + (int64_t)i * inner] = d2;
+        pd0[par] = d0; pd1[par] = d1; pd2[par] = d2;
+    }
+    if (n >= 2) {
+        f[3 * fs_d + (int64_t)(n - 2) * inner] = 0.0;
+        f[3 * fs_d + (int64_t)(n - 1) * inner] = 0.0;
+    } else if (n == 1) {
+        f[3 * fs_d] = 0.0;
+    }
+}
+
+// Solve (la.pyx:871-947): y_i = b_i - L[i-2] y_{i-2};  u_i = (y_i - d1[i] u_{i+2} - d2[i] sum_{q>=2} u_{i+2q}) / d0[i]
+template <class T>
+__global__ void __launch_bounds__(BD_THREADS) helmholtz_solve_kernel(
+    const T *__restrict__ b, T *__restrict__ u, const double *__restrict__ fac, int64_t outer, int64_t inner,
+    int n, int n_u) {
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= outer * inner) return;
+    const int64_t o = line / inner, c = line % inner;
+    const int64_t fs_d = outer * (int64_t)n * inner;
+    const double *f = fac + (o * n) * inner + c;
+    const T *bl = b + (o * n_u) * inner + c;
+    T *x = u + (o * n_u) * inner + c;
+    T y[2] = {Num<T>::zero(), Num<T>::zero()};
+    for (int i = 0; i < n; ++i) {
+        const int par = i & 1;
+        T v = bl[(int64_t)i * inner];
+        if (i >= 2) v = Num<T>::fnma(f[3 * fs_d + (int64_t)(i - 2) * inner], y[par], v);
+        x[(int64_t)i * inner] = v;
+        y[par] = v;
+    }
+    T un[2] = {Num<T>::zero(), Num<T>::zero()};     // u_{i+2} per parity
+    T sum[2] = {Num<T>::zero(), Num<T>::zero()};    // sum_{q>=2} u_{i+2q} per parity
+    for (int i = n - 1; i >= 0; --i) {
+        const int par = i & 1;
+        T v = x[(int64_t)i * inner];
+        v = Num<T>::fnma(f[1 * fs_d + (int64_t)i * inner], un[par], v);
+        v = Num<T>::fnma(f[2 * fs_d + (int64_t)i * inner], sum[par], v);
+        v = Num<T>::div(v, f[0 * fs_d + (int64_t)i * inner]);
+        x[(int64_t)i * inner] = v;
+        sum[par] = Num<T>::add(sum[par], un[par]);
+        un[par] = v;
+    }
+}
+
+static inline unsigned bd_blocks(int64_t nlines) { return (unsigned)((nlines + BD_THREADS - 1) / BD_THREADS); }
+
+template <int KL, int KU>
+static int launch_factor(const BandedDesc &d, cudaStream_t st) {
+    banded_factor_kernel<KL, KU><<<bd_blocks(d.outer * d.inner), BD_THREADS, 0, st>>>(d);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+template <int KL, int KU>
+static int launch_solve(void *u, const double *fac, int64_t outer, int64_t inner, int n, int n_u, int step,
+                        int fac_shared, int is_complex, cudaStream_t st) {
+    if (is_complex)
+        banded_solve_kernel<KL, KU, cplx><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (cplx *)u, fac, outer, inner, n, n_u, step, fac_shared);
+    else
+        banded_solve_kernel<KL, KU, double><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (double *)u, fac, outer, inner, n, n_u, step, fac_shared);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+#define SHB_BAND_DISPATCH(KLv, KUv, CALL)                                   \
+    if (kl == 0 && ku == 0) { constexpr int KL = 0, KU = 0; CALL; }         \
+    else if (kl == 0 && ku == 1) { constexpr int KL = 0, KU = 1; CALL; }    \
+    else if (kl == 0 && ku == 2) { constexpr int KL = 0, KU = 2; CALL; }    \
+    else if (kl == 1 && ku == 1) { constexpr int KL = 1, KU = 1; CALL; }    \
+    else if (kl == 1 && ku == 2) { constexpr int KL = 1, KU = 2; CALL; }    \
+    else if (kl == 2 && ku == 2) { constexpr int KL = 2, KU = 2; CALL; }    \
+    else if (kl == 2 && ku == 4) { constexpr int KL = 2, KU = 4; CALL; }    \
+    else if (kl == 1 && ku == 0) { constexpr int KL = 1, KU = 0; CALL; }    \
+    else if (kl == 2 && ku == 0) { constexpr int KL = 2, KU = 0; CALL; }    \
+    else if (kl == 2 && ku == 1) { constexpr int KL = 2, KU = 1; CALL; }    \
+    else { set_error("banded: unsupported bandwidth kl=%d ku=%d", kl, ku); return SHB_ERR_UNSUPPORTED; }
+
+}  // namespace shb
+
+using namespace shb;
+
+extern "C" {
+
+int shb_banded_factor(int kl, int ku, int step, int nmat, const double *const *d_mats,
+                      const double *const *d_scales, double *d_fac, int64_t outer, int64_t inner, int n,
+                      int64_t pin_line, void *stream) {
+    SHB_REQUIRE(nmat >= 1 && nmat <= BD_MAXMAT && d_mats && d_fac && n >= 1 && (step == 1 || step == 2),
+                "bad arguments");
+    if (outer * inner == 0) return SHB_OK;
+    BandedDesc d;
+    d.outer = outer; d.inner = inner; d.n = n; d.n_u = n; d.step = step; d.nmat = nmat;
+    for (int m = 0; m < BD_MAXMAT; ++m) {
+        d.mats[m] = m < nmat ? d_mats[m] : nullptr;
+        d.scales[m] = (m < nmat && d_scales) ? d_scales[m] : nullptr;
+    }
+    d.fac = d_fac; d.fac_shared = 0; d.pin_line = pin_line;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SHB_BAND_DISPATCH(kl, ku, return (launch_factor<KL, KU>(d, st)));
+}
+
+int shb_banded_solve(int kl, int ku, int step, void *d_u, const double *d_fac, int64_t outer, int64_t inner,
+                     int n, int n_u, int fac_shared, int is_complex, void *stream) {
+    SHB_REQUIRE(d_u && d_fac && n >= 1 && n_u >= n && (step == 1 || step == 2), "bad arguments");
+    if (outer * inner == 0) return SHB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SHB_BAND_DISPATCH(kl, ku, return (launch_solve<KL, KU>(d_u, d_fac, outer, inner, n, n_u, step, fac_shared,
+                                                           is_complex, st)));
+}
+
+int shb_banded_matvec(const void *d_u, void *d_out, int nmat, int ndiag, const int *offsets,
+                      const double *const *d_mats, const double *const *d_scales, int64_t outer, int64_t inner,
+                      int n_rows, int n_cols, int n_u, int n_out, int accumulate, int is_complex, void *stream) {
+    SHB_REQUIRE(d_u && d_out && nmat >= 1 && nmat <= BD_MAXMAT && ndiag >= 1 && ndiag <= 16 && offsets && d_mats,
+                "bad arguments");
+    MatvecDesc d;
+    d.outer = outer; d.inner = inner; d.n_rows = n_rows; d.n_cols = n_cols; d.n_u = n_u; d.n_out = n_out;
+    d.nmat = nmat; d.ndiag = ndiag; d.accumulate = accumulate;
+    for (int k = 0; k < ndiag; ++k) d.offs[k] = offsets[k];
+    for (int m = 0; m < BD_MAXMAT; ++m) {
+        d.mats[m] = m < nmat ? d_mats[m] : nullptr;
+        d.scales[m] = (m < nmat && d_scales) ? d_scales[m] : nullptr;
+    }
+    const int64_t tot = outer * (int64_t)n_out * inner;
+    if (tot == 0) return SHB_OK;
+    int64_t blocks = (tot + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (is_complex) banded_matvec_kernel<cplx><<<(unsigned)blocks, 256, 0, st>>>((const cplx *)d_u, (cplx *)d_out, d);
+    else banded_matvec_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double *)d_u, (double *)d_out, d);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_helmholtz_factor(const double *d_A0, const double *d_A2, const double *d_A4, const double *d_Bm2,
+                         const double *d_B0, const double *d_B2, const double *d_alfa, const double *d_beta,
+                         double *d_fac, int64_t outer, int64_t inner, int n, void *stream) {
+    SHB_REQUIRE(d_A0 && d_A2 && d_A4 && d_Bm2 && d_B0 && d_B2 && d_alfa && d_beta && d_fac && n >= 1, "bad arguments");
+    if (outer * inner == 0) return SHB_OK;
+    helmholtz_factor_kernel<<<bd_blocks(outer * inner), BD_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        d_A0, d_A2, d_A4, d_Bm2, d_B0, d_B2, d_alfa, d_beta, d_fac, outer, inner, n);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_helmholtz_solve(const void *d_b, void *d_u, const double *d_fac, int64_t outer, int64_t inner, int n,
+                        int n_u, int is_complex, void *stream) {
+    SHB_REQUIRE(d_b && d_u && d_fac && n >= 1 && n_u >= n, "bad arguments");
+    if (outer * inner == 0) return SHB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (is_complex)
+        helmholtz_solve_kernel<cplx><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (const cplx *)d_b, (cplx *)d_u, d_fac, outer, inner, n, n_u);
+    else
+        helmholtz_solve_kernel<double><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (const double *)d_b, (double *)d_u, d_fac, outer, inner, n, n_u);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+}  // extern "C"

@@ -10,8 +10,12 @@ enum FftMode {
     FFT_R2C = 2,        // even n_fft: half-length complex FFT + split
     FFT_C2R = 3,
     FFT_R2C_FULL = 4,   // odd n_fft: full complex FFT of the real line
-    FFT_C2R_FULL = 5
+    FFT_C2R_FULL = 5,
+    FFT_DCT2 = 6,       // Chebyshev scalar product: DCT-II * scale, then stencil K
+    FFT_DCT3 = 7        // Chebyshev evaluation: stencil K^T, then 0.5*DCT-III + c0/2
 };
+
+constexpr int DCT_MAX_STENCIL = 6;
 
 constexpr int FFT_MAX_STAGES = 24;
 
@@ -32,7 +36,27 @@ struct FftDesc {
     double scale;
     const cplx *tw;   // exp(-2 pi i k / M)
     const cplx *tw2;  // exp(-2 pi i k / (2M)), k = 0..M
+    // --- DCT / Shen-stencil modes ---
+    const cplx *tw3;  // exp(-i pi k / (2M)), k = 0..M
+    int is_real;      // data arrays are real (double) instead of complex
+    int dim;          // degrees of freedom along the axis (rows that carry the stencil)
+    int nsten;        // stencil diagonals: phi_k = sum_i sten[i][k] T_{k+soff[i]}
+    int soff[DCT_MAX_STENCIL];
+    const double *sten[DCT_MAX_STENCIL];   // NULL = all ones
+    int nbc;                               // boundary dofs stored in rows dim..dim+nbc-1
+    const double *bc_lift;                 // [nbc][4]: ortho coefficients T_0..T_3 of each boundary function
 };
+
+struct DctArgs {
+    int is_real, dim, nsten;
+    int soff[DCT_MAX_STENCIL];
+    const double *sten[DCT_MAX_STENCIL];
+    int nbc;
+    const double *bc_lift;
+};
+
+int dct_generic_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner, int n_phys,
+                       int n_spec, double scale, const DctArgs &a, cudaStream_t st);
 
 int fft_generic_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner,
                        int n_fft, int N, double scale, int flags, cudaStream_t st);

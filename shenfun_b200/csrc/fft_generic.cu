@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
     cplx *buf1 = buf0 + (size_t)d.M * d.PT;
 
     constexpr bool INV = (MODE == FFT_C2C_BWD || MODE == FFT_C2R || MODE == FFT_C2R_FULL);
+    constexpr bool DCT = (MODE == FFT_DCT2 || MODE == FFT_DCT3);
     const int T = d.T, PT = d.PT, M = d.M;
     const int P = blockDim.x / T;
     const int64_t line0 = (int64_t)blockIdx.x * T;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
     // -------- prologue: global -> buf0 (rows 0..M-1) -----------------------------
     // iteration space: (row, line) with the fast index chosen for coalescing
     const int rows_load = M;
-    for (int idx = threadIdx.x; idx < rows_load * T; idx += blockDim.x) {
+    for (int idx = threadIdx.x; !DCT && idx < rows_load * T; idx += blockDim.x) {
         int r, l;
         if (contig) { r = idx % rows_load; l = idx / rows_load; }
         else        { l = idx % T;         r = idx / T; }
@@ -188,12 +189,137 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const __grid_constant_
         }
         buf0[(size_t)r * PT + l] = val;
     }
+    if (DCT) {
+        // generic element fetch of the (real or complex) input line
+        auto fetch = [&](int64_t base, int r) -> cplx {
+            if (d.is_real) return make_double2(reinterpret_cast<const double *>(d.in)[base + (int64_t)r * d.inner], 0.0);
+            return reinterpret_cast<const cplx *>(d.in)[base + (int64_t)r * d.inner];
+        };
+        if (MODE == FFT_DCT2) {
+            // even-odd permutation: v[n] = x[2n], v[M-1-n] = x[2n+1]
+            for (int idx = threadIdx.x; idx < M * T; idx += blockDim.x) {
+                int r, l;
+                if (contig) { r = idx % M; l = idx / M; } else { l = idx % T; r = idx / T; }
+                cplx val = make_double2(0.0, 0.0);
+                if (l < nl) {
+                    const int64_t line = line0 + l;
+                    const int64_t o = line / d.inner, cc = line % d.inner;
+                    val = fetch(o * (int64_t)n_in * d.inner + cc, r);
+                }
+                const int pos = (r & 1) ? (M - 1 - (r >> 1)) : (r >> 1);
+                buf0[(size_t)pos * PT + l] = val;
+            }
+        } else {
+            // DCT3: stored coefficients -> buf0; stencil transpose (to_ortho) c_j -> buf1;
+            // U_0 = c_0, U_k = 0.5 w_k (c_k + i c_{M-k}) -> buf0
+            for (int idx = threadIdx.x; idx < M * T; idx += blockDim.x) {
+                int r, l;
+                if (contig) { r = idx % M; l = idx / M; } else { l = idx % T; r = idx / T; }
+                cplx val = make_double2(0.0, 0.0);
+                if (l < nl && r < d.dim + d.nbc && r < n_in) {
+                    const int64_t line = line0 + l;
+                    const int64_t o = line / d.inner, cc = line % d.inner;
+                    val = fetch(o * (int64_t)n_in * d.inner + cc, r);
+                }
+                buf0[(size_t)r * PT + l] = val;
+            }
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < M * T; idx += blockDim.x) {
+                const int l = idx % T, jr = idx / T;
+                cplx acc = make_double2(0.0, 0.0);
+                for (int i = 0; i < d.nsten; ++i) {
+                    const int k = jr - d.soff[i];
+                    if (k >= 0 && k < d.dim) {
+                        const double a = d.sten[i] ? __ldg(&d.sten[i][k]) : 1.0;
+                        const cplx x = buf0[(size_t)k * PT + l];
+                        acc.x = fma(a, x.x, acc.x);
+                        acc.y = fma(a, x.y, acc.y);
+                    }
+                }
+                if (d.nbc > 0 && jr < 4) {
+                    for (int b = 0; b < d.nbc; ++b) {
+                        if (d.dim + b >= M) break;
+                        const double a = __ldg(&d.bc_lift[b * 4 + jr]);
+                        const cplx x = buf0[(size_t)(d.dim + b) * PT + l];
+                        acc.x = fma(a, x.x, acc.x);
+                        acc.y = fma(a, x.y, acc.y);
+                    }
+                }
+                buf1[(size_t)jr * PT + l] = acc;
+            }
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < M * T; idx += blockDim.x) {
+                const int l = idx % T, k = idx / T;
+                cplx u;
+                if (k == 0) u = buf1[l];
+                else {
+                    const cplx ck = buf1[(size_t)k * PT + l], cm = buf1[(size_t)(M - k) * PT + l];
+                    const cplx w = __ldg(&d.tw3[k]);
+                    const cplx sum = make_double2(ck.x - cm.y, ck.y + cm.x);     // c_k + i c_{M-k}
+                    u = cscale(cmul(w, sum), 0.5);
+                }
+                buf0[(size_t)k * PT + l] = u;
+            }
+        }
+    }
     __syncthreads();
 
     // -------- FFT -------------------------------------------------------------------
     const int c = threadIdx.x % T;
     const int t = threadIdx.x / T;
     cplx *res = fft_core_smem<INV>(buf0, buf1, d, c, t, P, true);
+
+    if (DCT) {
+        cplx *oth = (res == buf0) ? buf1 : buf0;
+        if (MODE == FFT_DCT2) {
+            // S_k = scale * (w_k V_k + conj(w_k) V_{M-k})  -> oth ; then out_k = sum_i sten_i[k] S_{k+soff_i}
+            for (int idx = threadIdx.x; idx < M * T; idx += blockDim.x) {
+                const int l = idx % T, k = idx / T;
+                const cplx vk = res[(size_t)k * PT + l], vm = res[(size_t)((M - k) % M) * PT + l];
+                const cplx w = __ldg(&d.tw3[k]);
+                cplx sres = cadd(cmul(w, vk), cmulc(vm, w));
+                oth[(size_t)k * PT + l] = cscale(sres, d.scale);
+            }
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < n_out * T; idx += blockDim.x) {
+                int r, l;
+                if (contig) { r = idx % n_out; l = idx / n_out; } else { l = idx % T; r = idx / T; }
+                if (l >= nl) continue;
+                cplx acc = make_double2(0.0, 0.0);
+                if (r < d.dim) {
+                    for (int i = 0; i < d.nsten; ++i) {
+                        const int jj = r + d.soff[i];
+                        if (jj >= 0 && jj < M) {
+                            const double a = d.sten[i] ? __ldg(&d.sten[i][r]) : 1.0;
+                            const cplx x = oth[(size_t)jj * PT + l];
+                            acc.x = fma(a, x.x, acc.x);
+                            acc.y = fma(a, x.y, acc.y);
+                        }
+                    }
+                }
+                const int64_t line = line0 + l;
+                const int64_t o = line / d.inner, cc = line % d.inner;
+                const int64_t oidx = o * (int64_t)n_out * d.inner + cc + (int64_t)r * d.inner;
+                if (d.is_real) reinterpret_cast<double *>(d.out)[oidx] = acc.x;
+                else reinterpret_cast<cplx *>(d.out)[oidx] = acc;
+            }
+        } else {
+            // un-permute: out[2n] = y[n], out[2n+1] = y[M-1-n]
+            for (int idx = threadIdx.x; idx < M * T; idx += blockDim.x) {
+                int r, l;
+                if (contig) { r = idx % M; l = idx / M; } else { l = idx % T; r = idx / T; }
+                if (l >= nl) continue;
+                const int pos = (r & 1) ? (M - 1 - (r >> 1)) : (r >> 1);
+                const cplx y = cscale(res[(size_t)pos * PT + l], d.scale);
+                const int64_t line = line0 + l;
+                const int64_t o = line / d.inner, cc = line % d.inner;
+                const int64_t oidx = o * (int64_t)n_out * d.inner + cc + (int64_t)r * d.inner;
+                if (d.is_real) reinterpret_cast<double *>(d.out)[oidx] = y.x;
+                else reinterpret_cast<cplx *>(d.out)[oidx] = y;
+            }
+        }
+        return;
+    }
 
     // -------- epilogue: result -> global ----------------------------------------------
     const double scale = d.scale;
@@ -322,6 +448,38 @@ int fft_generic_launch(int mode, const void *in, void *out, int64_t outer, int64
     case FFT_C2R_FULL: return launch_mode<FFT_C2R_FULL>(d, threads, smem, ntiles, st);
     }
     return SHB_ERR_ARG;
+}
+
+int dct_generic_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner, int n_phys,
+                       int n_spec, double scale, const DctArgs &a, cudaStream_t st) {
+    FftDesc d;
+    d.in = in; d.out = out; d.outer = outer; d.inner = inner;
+    d.n_fft = n_phys; d.N = n_spec; d.scale = scale; d.flags = 0;
+    d.M = n_phys;
+    if (mode == FFT_DCT2) { d.n_in = n_phys; d.n_out = n_spec; }
+    else if (mode == FFT_DCT3) { d.n_in = n_spec; d.n_out = n_phys; }
+    else { set_error("dct: bad mode %d", mode); return SHB_ERR_ARG; }
+    if (outer * inner == 0) return SHB_OK;
+    d.is_real = a.is_real; d.dim = a.dim; d.nsten = a.nsten; d.nbc = a.nbc; d.bc_lift = a.bc_lift;
+    for (int i = 0; i < DCT_MAX_STENCIL; ++i) { d.soff[i] = a.soff[i]; d.sten[i] = a.sten[i]; }
+    d.nstages = factorize(d.M, d.radix);
+    if (d.nstages < 0) { set_error("dct: too many factors in n=%d", d.M); return SHB_ERR_UNSUPPORTED; }
+    if (d.M == 1) d.nstages = 0;
+    d.tw = twiddle_table(0, d.M);
+    d.tw2 = nullptr;
+    d.tw3 = twiddle_table(2, d.M);
+    if (!d.tw || !d.tw3) { set_error("dct: twiddle table allocation failed"); return SHB_ERR_NOMEM; }
+    const size_t smem_max = 200 * 1024;
+    int T = 16;
+    while (T > 1 && 2 * (size_t)d.M * (T | 1) * sizeof(cplx) > smem_max) T >>= 1;
+    const int64_t nlines = outer * inner;
+    while (T > 1 && (int64_t)T / 2 >= nlines) T >>= 1;
+    d.T = T; d.PT = (T | 1);
+    const size_t smem = 2 * (size_t)d.M * d.PT * sizeof(cplx);
+    if (smem > 227 * 1024) { set_error("dct: n=%d too long for the shared-memory path", n_phys); return SHB_ERR_UNSUPPORTED; }
+    const int64_t ntiles = (nlines + T - 1) / T;
+    if (mode == FFT_DCT2) return launch_mode<FFT_DCT2>(d, 256, smem, ntiles, st);
+    return launch_mode<FFT_DCT3>(d, 256, smem, ntiles, st);
 }
 
 }  // namespace shb

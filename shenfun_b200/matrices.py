@@ -191,3 +191,8 @@ def get_simplified_tpmatrices(mats):
             groups.setdefault(m.global_index, []).append(m)
         return [DiagonalTPMatrix(g) for g in groups.values()]
     return list(mats)
+
+
+def mass_solve(T, rhs, out):
+    from .la import mass_solve as _ms
+    return _ms(T, rhs, out)

@@ -108,3 +108,75 @@ def apply_mask(u_hat, mask):
     _call('shb_apply_mask', _req(u_hat, C128, 'u_hat'), _req(mask, F64, 'mask'), n, u_hat.numel()//n,
           _lib.stream_ptr())
     return u_hat
+
+
+def _ptr_array(tensors):
+    """Host array of device pointers (None -> NULL) for the C ABI."""
+    import ctypes
+    arr = (ctypes.c_void_p*len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else _req(t, F64, 'table')
+    return arr
+
+
+def banded_factor(kl, ku, step, mats, scales, fac, outer, inner, n, pin_line=-1):
+    pm = _ptr_array(mats)
+    ps = _ptr_array(scales)
+    _call('shb_banded_factor', kl, ku, step, len(mats), pm, ps, _req(fac, F64, 'fac'), outer, inner, n,
+          pin_line, _lib.stream_ptr())
+
+
+def banded_solve(kl, ku, step, u, fac, outer, inner, n, n_u, fac_shared):
+    _call('shb_banded_solve', kl, ku, step, _req(u, u.dtype, 'u'), _req(fac, F64, 'fac'), outer, inner, n, n_u,
+          int(fac_shared), int(u.dtype.is_complex), _lib.stream_ptr())
+
+
+def banded_matvec(u, out, offsets, mats, scales, outer, inner, n_rows, n_cols, n_u, n_out, accumulate):
+    import ctypes
+    offs = (ctypes.c_int*len(offsets))(*[int(o) for o in offsets])
+    pm = _ptr_array(mats)
+    ps = _ptr_array(scales)
+    assert u.dtype == out.dtype
+    _call('shb_banded_matvec', _req(u, u.dtype, 'u'), _req(out, out.dtype, 'out'), len(mats), len(offsets), offs,
+          pm, ps, outer, inner, n_rows, n_cols, n_u, n_out, int(accumulate), int(u.dtype.is_complex),
+          _lib.stream_ptr())
+
+
+def helmholtz_factor(A0, A2, A4, Bm2, B0, B2, alfa, beta, fac, outer, inner, n):
+    _call('shb_helmholtz_factor', *[_req(t, F64, 'table') for t in (A0, A2, A4, Bm2, B0, B2, alfa, beta)],
+          _req(fac, F64, 'fac'), outer, inner, n, _lib.stream_ptr())
+
+
+def helmholtz_solve(b, u, fac, outer, inner, n, n_u):
+    assert b.dtype == u.dtype
+    _call('shb_helmholtz_solve', _req(b, b.dtype, 'b'), _req(u, u.dtype, 'u'), _req(fac, F64, 'fac'), outer, inner,
+          n, n_u, int(u.dtype.is_complex), _lib.stream_ptr())
+
+
+def _stencil_args(soff, sten):
+    import ctypes
+    offs = (ctypes.c_int*len(soff))(*[int(o) for o in soff])
+    return offs, _ptr_array(sten)
+
+
+def cheb_scalar_product(u, out, outer, inner, n_phys, n_spec, scale, dim, soff, sten):
+    assert u.dtype == out.dtype
+    offs, ps = _stencil_args(soff, sten)
+    _call('shb_cheb_scalar_product', _req(u, u.dtype, 'in'), _req(out, out.dtype, 'out'), outer, inner, n_phys,
+          n_spec, float(scale), int(not u.dtype.is_complex), dim, len(soff), offs, ps, _lib.stream_ptr())
+
+
+def cheb_backward(uh, out, outer, inner, n_phys, n_spec, dim, soff, sten, nbc=0, bc_lift=None):
+    assert uh.dtype == out.dtype
+    offs, ps = _stencil_args(soff, sten)
+    _call('shb_cheb_backward', _req(uh, uh.dtype, 'in'), _req(out, out.dtype, 'out'), outer, inner, n_phys,
+          n_spec, int(not uh.dtype.is_complex), dim, len(soff), offs, ps, nbc,
+          None if bc_lift is None else _req(bc_lift, F64, 'bc_lift'), _lib.stream_ptr())
+
+
+def gemm_axis(A, u, out, outer, inner):
+    """out[o][i][c] = sum_j A[i][j] u[o][j][c] (A real (M, K) device matrix)."""
+    assert u.dtype == out.dtype
+    M, K = A.shape
+    _call('shb_gemm_axis', _req(A, F64, 'A'), _req(u, u.dtype, 'u'), _req(out, out.dtype, 'out'), M, K, outer, inner,
+          int(u.dtype.is_complex), _lib.stream_ptr())

@@ -31,3 +31,24 @@ def rel_l2(a, b):
 def lib():
     from shenfun_b200 import _lib
     return _lib.load()
+
+
+BCS = {
+    'ortho': None,
+    'dirichlet': (0, 0),
+    'neumann': {'left': {'N': 0}, 'right': {'N': 0}},
+    'biharmonic': (0, 0, 0, 0),
+    'dn': {'left': {'D': 0}, 'right': {'N': 0}},
+    'inhom': {'left': {'D': 1.5}, 'right': {'D': -0.5}},
+}
+
+
+def oracle_spec(base):
+    """What oracle/polybases.py needs, taken from the host-side basis object (whose stencil and
+    mass matrix are themselves pinned against the reference in test_oracle_poly.py)."""
+    spec = dict(family='C' if base.family() == 'chebyshev' else 'L', N=base.N, n_phys=base.physical_len(),
+                dim=base.dim(), stencil=base.stencil(), df=float(base.domain_factor()),
+                mass=base.mass_matrix().diags())
+    if spec['family'] == 'L':
+        spec['x'], spec['w'] = base.points_and_weights(base.physical_len())
+    return spec

@@ -5,8 +5,9 @@ Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py
 
 The reference imports on top of oracle/refshim (serial stand-ins for the absent
-mpi4py / mpi4py-fft, restated on scipy.fft) with
-config['optimization']['mode'] = 'numba' (the reference's own numba kernels).
+mpi4py / mpi4py-fft, restated on scipy.fft; the reference's own fastgl.cpp compiled
+into oracle/_ref by oracle/build_ref.sh) with config['optimization']['mode'] = 'numba'
+(the reference's own numba kernels).
 Outputs: tests/golden/*.npz (inputs + reference outputs, fp64), small enough to
 commit.  The GPU box never reads /root/reference; tests compare the device
 path and the numpy oracle against these files.
@@ -16,14 +17,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, os.path.join(ROOT, 'oracle', 'refshim'))
-sys.path.insert(0, '/root/reference')
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 os.chdir(HERE)
 
 import numpy as np  # noqa: E402
-import shenfun as sf  # noqa: E402
+import refshim  # noqa: E402
 
-sf.config['optimization']['mode'] = 'numba'
+sf = refshim.activate()       # reference's shenfun on the serial shims, numba kernels
 rng = np.random.default_rng(20261017)
 
 
@@ -132,6 +132,162 @@ def navier_stokes():
     assert round(k-0.124953117517, 7) == 0, k
     out['k32_t01'] = k
     save('ns_16', **out)
+
+
+BCS = {
+    'ortho': None,
+    'dirichlet': (0, 0),
+    'neumann': {'left': {'N': 0}, 'right': {'N': 0}},
+    'biharmonic': (0, 0, 0, 0),
+    'dn': {'left': {'D': 0}, 'right': {'N': 0}},
+    'inhom': {'left': {'D': 1.5}, 'right': {'D': -0.5}},
+}
+
+
+def poly_1d():
+    """1-D Chebyshev / Legendre bases: matrices, scalar product, forward, backward (plain, padded)."""
+    for fam in ('C', 'L'):
+        out = {}
+        for name, bc in BCS.items():
+            for N in (16, 15):
+                S = sf.FunctionSpace(N, fam, bc=bc) if bc is not None else sf.FunctionSpace(N, fam)
+                tag = f'{name}_{N}'
+                u = rng.standard_normal(N)
+                out[f'u_{tag}'] = u
+                out[f'sp_{tag}'] = np.array(S.scalar_product(u.copy()))
+                uh = np.array(S.forward(u.copy()))
+                out[f'fw_{tag}'] = uh
+                vh = np.zeros(N)
+                vh[:S.dim()] = rng.standard_normal(S.dim())
+                if name == 'inhom':
+                    vh[S.dim():] = uh[S.dim():]
+                out[f'vh_{tag}'] = vh
+                out[f'bw_{tag}'] = np.array(S.backward(vh.copy()))
+                Sp = S.get_dealiased(1.5)
+                out[f'bwpad_{tag}'] = np.array(Sp.backward(vh.copy()))
+                w = rng.standard_normal(Sp.shape(False))
+                out[f'w_{tag}'] = w
+                out[f'fwpad_{tag}'] = np.array(Sp.forward(w.copy()))
+                if N == 16:
+                    K = S.stencil_matrix() if bc is not None else None
+                    if K is not None:
+                        out[f'K_{tag}'] = K.diags().toarray()
+                    for (a, b) in ((0, 0), (0, 1), (0, 2), (1, 1), (0, 4), (2, 2)):
+                        try:
+                            M = sf.SpectralMatrix((S, a), (S, b))
+                            out[f'M{a}{b}_{tag}'] = M.diags().toarray()
+                        except Exception as e:  # noqa: BLE001
+                            print('skip matrix', fam, name, a, b, repr(e)[:80])
+        save('poly1d_'+fam, **out)
+
+
+def poly_3d():
+    """Chebyshev/Legendre x Fourier^2 tensor spaces, two axis orders, plain and 3/2-padded."""
+    out = {}
+    for fam in ('C', 'L'):
+        for name in ('dirichlet', 'biharmonic', 'neumann'):
+            bc = BCS[name]
+            for layout in ('first', 'middle'):
+                SD = sf.FunctionSpace(14, fam, bc=bc)
+                K1 = sf.FunctionSpace(12, 'F', dtype='D')
+                K2 = sf.FunctionSpace(10, 'F', dtype='d')
+                if layout == 'first':
+                    T = sf.TensorProductSpace(sf.comm, (SD, K1, K2))
+                else:
+                    T = sf.TensorProductSpace(sf.comm, (K1, SD, K2), axes=(1, 0, 2))
+                tag = f'{fam}_{name}_{layout}'
+                u = rng.standard_normal(T.shape(False))
+                ua = sf.Array(T)
+                ua[:] = u
+                out[f'u_{tag}'] = u
+                out[f'fw_{tag}'] = np.array(T.forward(ua, sf.Function(T)))
+                out[f'sp_{tag}'] = np.array(T.scalar_product(ua, sf.Function(T)))
+                vh = sf.Function(T)
+                vh[:] = rng.standard_normal(T.shape(True))+1j*rng.standard_normal(T.shape(True))
+                sl = [slice(None)]*3
+                ax = 0 if layout == 'first' else 1
+                sl[ax] = slice(SD.dim(), None)
+                vh[tuple(sl)] = 0
+                out[f'vh_{tag}'] = np.array(vh)
+                out[f'bw_{tag}'] = np.array(T.backward(vh, sf.Array(T)))
+                Tp = T.get_dealiased((1.5, 1.5, 1.5))
+                out[f'bwpad_{tag}'] = np.array(Tp.backward(vh, sf.Array(Tp)))
+                w = rng.standard_normal(Tp.shape(False))
+                wa = sf.Array(Tp)
+                wa[:] = w
+                out[f'w_{tag}'] = w
+                out[f'fwpad_{tag}'] = np.array(Tp.forward(wa, sf.Function(Tp)))
+    save('poly3d', **out)
+
+
+def solvers():
+    """la.TDMA/PDMA/... along axes; SolverGeneric1ND Poisson / biharmonic; Chebyshev Helmholtz."""
+    from shenfun import la, inner, div, grad, TestFunction, TrialFunction, Dx
+    from shenfun.chebyshev.la import Helmholtz
+    out = {}
+    # --- named banded solvers on 1-D matrices along the axes of a 3-D array (tests/test_la.py:20-49)
+    N = 16
+    cases = {
+        'TDMA': (sf.FunctionSpace(N, 'C', bc=(0, 0)), (0, 0), la.TDMA),
+        'PDMA': (sf.FunctionSpace(N, 'C', bc=(0, 0, 0, 0)), (0, 0), la.PDMA),
+        'TDMA_L': (sf.FunctionSpace(N, 'L', bc=(0, 0)), (0, 0), la.TDMA),
+        'PDMA_L': (sf.FunctionSpace(N, 'L', bc=(0, 0, 0, 0)), (0, 0), la.PDMA),
+    }
+    for name, (S, (a, b), cls) in cases.items():
+        M = sf.SpectralMatrix((S, a), (S, b))
+        out[f'mat_{name}'] = M.diags().toarray()
+        for axis in (0, 1, 2):
+            shape = [5, 6, 7]
+            shape[axis] = N
+            f = rng.standard_normal(shape)+1j*rng.standard_normal(shape)
+            sol = cls(M) if cls is not None else la.Solver(M)
+            u = np.array(sol(f.copy(), axis=axis))
+            out[f'f_{name}_{axis}'] = f
+            out[f'u_{name}_{axis}'] = u
+    # --- Poisson with SolverGeneric1ND, Legendre Dirichlet x F x F (demo/poisson3D.py structure)
+    for fam, tag in (('L', 'leg'), ('C', 'cheb')):
+        SD = sf.FunctionSpace(14, fam, bc=(0, 0))
+        K1 = sf.FunctionSpace(12, 'F', dtype='D')
+        K2 = sf.FunctionSpace(10, 'F', dtype='d')
+        T = sf.TensorProductSpace(sf.comm, (SD, K1, K2))
+        u = TrialFunction(T)
+        v = TestFunction(T)
+        f_hat = sf.Function(T)
+        f_hat[:] = rng.standard_normal(T.shape(True))+1j*rng.standard_normal(T.shape(True))
+        f_hat[SD.dim():] = 0
+        out[f'poisson_{tag}_f'] = np.array(f_hat)
+        if fam == 'L':
+            mats = inner(v, div(grad(u)))
+            H = la.SolverGeneric1ND(mats)
+            u_hat = H(f_hat.copy(), sf.Function(T), constraints=((0, 0),))
+            out[f'poisson_{tag}_u'] = np.array(u_hat)
+            # Helmholtz-like without gauge: (v, div grad u) - 2.5 (v, u)
+            mats2 = inner(v, div(grad(u))-2.5*u)
+            H2 = la.SolverGeneric1ND(mats2)
+            out[f'helm_{tag}_u'] = np.array(H2(f_hat.copy(), sf.Function(T)))
+        else:
+            mats = inner(v, div(grad(u))-2.5*u)
+            H = Helmholtz(*mats)
+            u_hat = H(f_hat.copy(), sf.Function(T))
+            out[f'helm_{tag}_u'] = np.array(u_hat)
+            c = sf.Function(T)
+            out[f'helm_{tag}_matvec'] = np.array(H.matvec(u_hat, c))
+    # --- biharmonic, Legendre x F x F (demo/biharmonic3D.py structure)
+    SB = sf.FunctionSpace(16, 'L', bc=(0, 0, 0, 0))
+    K1 = sf.FunctionSpace(12, 'F', dtype='D')
+    K2 = sf.FunctionSpace(10, 'F', dtype='d')
+    T = sf.TensorProductSpace(sf.comm, (K1, K2.get_unplanned() if False else sf.FunctionSpace(10, 'F', dtype='D'), SB)) if False else \
+        sf.TensorProductSpace(sf.comm, (SB, K1, K2))
+    u = TrialFunction(T)
+    v = TestFunction(T)
+    f_hat = sf.Function(T)
+    f_hat[:] = rng.standard_normal(T.shape(True))+1j*rng.standard_normal(T.shape(True))
+    f_hat[SB.dim():] = 0
+    mats = inner(v, div(grad(div(grad(u)))))
+    H = la.SolverGeneric1ND(mats)
+    out['biharm_f'] = np.array(f_hat)
+    out['biharm_u'] = np.array(H(f_hat.copy(), sf.Function(T)))
+    save('solvers', **out)
 
 
 if __name__ == '__main__':

@@ -1,0 +1,165 @@
+"""Device parity for the Chebyshev / Legendre bases, the banded line solvers, SolverGeneric1ND and
+the Chebyshev Helmholtz solver against golden vectors produced by the reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, BCS, oracle_spec
+import shenfun_b200 as sf
+from shenfun_b200 import la
+from oracle import polybases as opb
+from oracle import la as ola
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+NAMES = ['ortho', 'dirichlet', 'neumann', 'biharmonic', 'dn']
+
+
+@pytest.mark.parametrize('fam', ['C', 'L'])
+@pytest.mark.parametrize('name', NAMES)
+@pytest.mark.parametrize('N', [16, 15])
+def test_1d_transforms_golden(fam, name, N):
+    g = load_golden('poly1d_'+fam)
+    S = sf.FunctionSpace(N, fam, bc=BCS[name])
+    tag = f'{name}_{N}'
+    d = S.dim()
+    sp = S.scalar_product(g[f'u_{tag}']).cpu().numpy()
+    assert rel_l2(sp[:d], g[f'sp_{tag}'][:d]) < TOL
+    assert np.all(sp[d:] == 0)
+    assert rel_l2(S.forward(g[f'u_{tag}']).cpu().numpy(), g[f'fw_{tag}']) < TOL
+    assert rel_l2(S.backward(g[f'vh_{tag}']).cpu().numpy(), g[f'bw_{tag}']) < TOL
+    Sp = S.get_dealiased(1.5)
+    assert rel_l2(Sp.backward(g[f'vh_{tag}']).cpu().numpy(), g[f'bwpad_{tag}']) < TOL
+    assert rel_l2(Sp.forward(g[f'w_{tag}']).cpu().numpy(), g[f'fwpad_{tag}']) < TOL
+
+
+@pytest.mark.parametrize('fam', ['C', 'L'])
+@pytest.mark.parametrize('N', [16, 15])
+def test_1d_inhomogeneous_dirichlet(fam, N):
+    g = load_golden('poly1d_'+fam)
+    S = sf.FunctionSpace(N, fam, bc=BCS['inhom'])
+    tag = f'inhom_{N}'
+    assert rel_l2(S.forward(g[f'u_{tag}']).cpu().numpy(), g[f'fw_{tag}']) < TOL
+    assert rel_l2(S.backward(g[f'vh_{tag}']).cpu().numpy(), g[f'bw_{tag}']) < TOL
+
+
+def _space(fam, name, layout, pf=1.0):
+    SD = sf.FunctionSpace(14, fam, bc=BCS[name], padding_factor=pf)
+    K1 = sf.FunctionSpace(12, 'F', dtype='D', padding_factor=pf)
+    K2 = sf.FunctionSpace(10, 'F', dtype='d', padding_factor=pf)
+    if layout == 'first':
+        return sf.TensorProductSpace(sf.comm, (SD, K1, K2)), 0
+    return sf.TensorProductSpace(sf.comm, (K1, SD, K2), axes=(1, 0, 2)), 1
+
+
+@pytest.mark.parametrize('fam', ['C', 'L'])
+@pytest.mark.parametrize('name', ['dirichlet', 'biharmonic', 'neumann'])
+@pytest.mark.parametrize('layout', ['first', 'middle'])
+def test_3d_spaces_golden(fam, name, layout):
+    g = load_golden('poly3d')
+    tag = f'{fam}_{name}_{layout}'
+    T, ax = _space(fam, name, layout)
+    d = T.bases[ax].dim()
+    sl = [slice(None)]*3
+    sl[ax] = slice(0, d)
+    sl = tuple(sl)
+    assert rel_l2(T.forward(g[f'u_{tag}']).get(), g[f'fw_{tag}']) < TOL
+    assert rel_l2(T.scalar_product(g[f'u_{tag}']).get()[sl], g[f'sp_{tag}'][sl]) < TOL
+    vh = sf.Function(T, buffer=g[f'vh_{tag}'])
+    assert rel_l2(T.backward(vh).get(), g[f'bw_{tag}']) < TOL
+    Tp = T.get_dealiased((1.5, 1.5, 1.5))
+    assert rel_l2(Tp.backward(vh).get(), g[f'bwpad_{tag}']) < TOL
+    assert rel_l2(Tp.forward(g[f'w_{tag}']).get(), g[f'fwpad_{tag}']) < TOL
+
+
+@pytest.mark.parametrize('fam,N', [('C', 64), ('C', 96), ('C', 81), ('L', 64), ('L', 50)])
+@pytest.mark.parametrize('name', ['dirichlet', 'biharmonic'])
+def test_larger_transforms_against_oracle(fam, N, name):
+    rng = np.random.default_rng(N)
+    S = sf.FunctionSpace(N, fam, bc=BCS[name])
+    T = sf.TensorProductSpace(sf.comm, (S, sf.FunctionSpace(12, 'F', dtype='D'), sf.FunctionSpace(8, 'F', dtype='d')))
+    spec = oracle_spec(T.bases[0])
+    u = rng.standard_normal((N, 12, 5))+1j*rng.standard_normal((N, 12, 5))
+    ud = torch.from_numpy(u).cuda()
+    out = torch.empty_like(ud)
+    T.bases[0]._forward_axis(ud, out, 1, 60)
+    assert rel_l2(out.cpu().numpy(), opb.forward_axis(u, 0, spec)) < TOL
+    vh = np.array(u)
+    vh[S.dim():] = 0
+    T.bases[0]._backward_axis(torch.from_numpy(vh).cuda(), out, 1, 60)
+    assert rel_l2(out.cpu().numpy(), opb.backward_axis(vh, 0, spec)) < TOL
+
+
+@pytest.mark.parametrize('name,fam,bc', [('TDMA', 'C', (0, 0)), ('PDMA', 'C', (0, 0, 0, 0)),
+                                         ('TDMA_L', 'L', (0, 0)), ('PDMA_L', 'L', (0, 0, 0, 0))])
+@pytest.mark.parametrize('axis', [0, 1, 2])
+def test_named_banded_solvers_golden(name, fam, bc, axis):
+    g = load_golden('solvers')
+    S = sf.FunctionSpace(16, fam, bc=bc)
+    M = S.mass_matrix()
+    cls = la.TDMA if 'TDMA' in name else la.PDMA
+    f = torch.from_numpy(g[f'f_{name}_{axis}']).cuda()
+    u = cls(M)(f, axis=axis)
+    assert rel_l2(u.cpu().numpy(), g[f'u_{name}_{axis}']) < TOL
+
+
+def _poisson_space(fam, n=14):
+    SD = sf.FunctionSpace(n, fam, bc=(0, 0))
+    K1 = sf.FunctionSpace(12, 'F', dtype='D')
+    K2 = sf.FunctionSpace(10, 'F', dtype='d')
+    return sf.TensorProductSpace(sf.comm, (SD, K1, K2))
+
+
+def test_solver_generic_1nd_poisson_and_helmholtz_legendre():
+    g = load_golden('solvers')
+    T = _poisson_space('L')
+    u, v = sf.TrialFunction(T), sf.TestFunction(T)
+    f_hat = sf.Function(T, buffer=g['poisson_leg_f'])
+    H = la.SolverGeneric1ND(sf.inner(v, sf.div(sf.grad(u))))
+    u_hat = H(f_hat, sf.Function(T), constraints=((0, 0),))
+    assert rel_l2(u_hat.get(), g['poisson_leg_u']) < TOL
+    H2 = la.SolverGeneric1ND(sf.inner(v, sf.div(sf.grad(u))-2.5*u))
+    u2 = H2(f_hat, sf.Function(T))
+    assert rel_l2(u2.get(), g['helm_leg_u']) < TOL
+    # solve o matvec round trip (tests/test_matrices.py:559-591)
+    c = H2.matvec(u2, sf.Function(T))
+    d = T.bases[0].dim()
+    assert rel_l2(c.get()[:d], g['poisson_leg_f'][:d]) < TOL
+
+
+def test_chebyshev_helmholtz_golden():
+    g = load_golden('solvers')
+    T = _poisson_space('C')
+    u, v = sf.TrialFunction(T), sf.TestFunction(T)
+    f_hat = sf.Function(T, buffer=g['poisson_cheb_f'])
+    H = la.Helmholtz(sf.inner(v, sf.div(sf.grad(u))-2.5*u))
+    u_hat = H(f_hat, sf.Function(T))
+    assert rel_l2(u_hat.get(), g['helm_cheb_u']) < TOL
+    c = H.matvec(u_hat, sf.Function(T))
+    assert rel_l2(c.get(), g['helm_cheb_matvec']) < 1e-11
+    d = T.bases[0].dim()
+    assert rel_l2(c.get()[:d], g['poisson_cheb_f'][:d]) < 1e-11
+
+
+def test_biharmonic_legendre_golden():
+    g = load_golden('solvers')
+    SB = sf.FunctionSpace(16, 'L', bc=(0, 0, 0, 0))
+    T = sf.TensorProductSpace(sf.comm, (SB, sf.FunctionSpace(12, 'F', dtype='D'), sf.FunctionSpace(10, 'F', dtype='d')))
+    u, v = sf.TrialFunction(T), sf.TestFunction(T)
+    H = la.SolverGeneric1ND(sf.inner(v, sf.div(sf.grad(sf.div(sf.grad(u))))))
+    u_hat = H(sf.Function(T, buffer=g['biharm_f']), sf.Function(T))
+    assert rel_l2(u_hat.get(), g['biharm_u']) < 1e-11
+
+
+def test_gemm_axis_shapes():
+    rng = np.random.default_rng(2)
+    for (M, K, outer, inner, cplx) in [(37, 29, 3, 11, True), (64, 64, 1, 130, False), (70, 50, 9, 1, False),
+                                        (33, 65, 5, 1, True), (128, 96, 2, 257, True)]:
+        A = rng.standard_normal((M, K))
+        u = rng.standard_normal((outer, K, inner))
+        if cplx:
+            u = u+1j*rng.standard_normal(u.shape)
+        out = torch.empty((outer, M, inner), dtype=torch.complex128 if cplx else torch.float64, device='cuda')
+        sf.ops.gemm_axis(torch.from_numpy(A).cuda(), torch.from_numpy(u).cuda(), out, outer, inner)
+        ref = np.einsum('ij,ojc->oic', A, u)
+        assert rel_l2(out.cpu().numpy(), ref) < 1e-14
