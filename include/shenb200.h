@@ -148,6 +148,12 @@ SHB_API int shb_helmholtz_factor(const double *d_A0, const double *d_A2, const d
                                  int64_t inner, int n, void *stream);
 SHB_API int shb_helmholtz_solve(const void *d_b, void *d_u, const double *d_fac, int64_t outer, int64_t inner,
                                 int n, int n_u, int is_complex, void *stream);
+/* c = (alfa*A + beta*B) v with running sums over the constant rows of A; replaces
+ * Helmholtz_matvec (optimization/cython/Matvec.pyx:656-712).                    */
+SHB_API int shb_helmholtz_matvec(const void *d_v, void *d_c, const double *d_A0, const double *d_A2,
+                                 const double *d_A4, const double *d_Bm2, const double *d_B0,
+                                 const double *d_B2, const double *d_alfa, const double *d_beta, int64_t outer,
+                                 int64_t inner, int n, int n_u, int is_complex, void *stream);
 
 /* ------------------------------------------------------------------ */
 /* Chebyshev (Gauss-Chebyshev points) axis transforms on [outer][n][inner],

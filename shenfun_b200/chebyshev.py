@@ -61,6 +61,16 @@ class Orthogonal(PolyBase):
             D = D1 @ D
         return D
 
+    def ortho_gram(self, N, d_test, d_trial):
+        """(T_j^(b), T_k^(a))_w = (pi/2) * c_k-weighted integer matrix: pi/2 is pulled out."""
+        ld = np.longdouble
+        c = np.ones(N, dtype=ld)
+        c[0] = 2
+        G = c[:, None]*self._deriv_ld(N, d_trial)
+        if d_test > 0:
+            G = self._deriv_ld(N, d_test).T @ G
+        return G, ld(np.pi)/2 if False else np.longdouble('1.5707963267948966192313216916397514')
+
     def boundary_values(self, n, order, side):
         n = np.asarray(n, dtype=float)
         sgn = 1.0 if side == 'right' else -1.0

@@ -306,6 +306,37 @@ __global__ void __launch_bounds__(BD_THREADS) helmholtz_solve_kernel(
     }
 }
 
+
+// c = (alfa*A + beta*B) v with the same structure (Matvec.pyx:656-712 `Helmholtz_matvec`):
+// (A v)_k = A0[k] v_k + A2[k] v_{k+2} + A4[k] sum_{q>=2} v_{k+2q}
+template <class T>
+__global__ void __launch_bounds__(BD_THREADS) helmholtz_matvec_kernel(
+    const T *__restrict__ v, T *__restrict__ c, const double *__restrict__ A0, const double *__restrict__ A2,
+    const double *__restrict__ A4, const double *__restrict__ Bm2, const double *__restrict__ B0,
+    const double *__restrict__ B2, const double *__restrict__ alfa, const double *__restrict__ beta,
+    int64_t outer, int64_t inner, int n, int n_u) {
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= outer * inner) return;
+    const int64_t o = line / inner, cc = line % inner;
+    const double al = alfa[line], be = beta[line];
+    const T *x = v + (o * n_u) * inner + cc;
+    T *y = c + (o * n_u) * inner + cc;
+    T un[2] = {Num<T>::zero(), Num<T>::zero()};
+    T sum[2] = {Num<T>::zero(), Num<T>::zero()};
+    for (int i = n_u - 1; i >= n; --i) y[(int64_t)i * inner] = Num<T>::zero();
+    for (int i = n - 1; i >= 0; --i) {
+        const int par = i & 1;
+        const T xi = x[(int64_t)i * inner];
+        T acc = Num<T>::mul(al * __ldg(&A0[i]) + be * __ldg(&B0[i]), xi);
+        if (i < n - 2) acc = Num<T>::fnma(-(al * __ldg(&A2[i]) + be * __ldg(&B2[i])), un[par], acc);
+        if (i < n - 4) acc = Num<T>::fnma(-(al * __ldg(&A4[i])), sum[par], acc);
+        if (i >= 2) acc = Num<T>::fnma(-(be * __ldg(&Bm2[i - 2])), x[(int64_t)(i - 2) * inner], acc);
+        y[(int64_t)i * inner] = acc;
+        sum[par] = Num<T>::add(sum[par], un[par]);
+        un[par] = xi;
+    }
+}
+
 static inline unsigned bd_blocks(int64_t nlines) { return (unsigned)((nlines + BD_THREADS - 1) / BD_THREADS); }
 
 template <int KL, int KU>
@@ -420,6 +451,24 @@ int shb_helmholtz_solve(const void *d_b, void *d_u, const double *d_fac, int64_t
     else
         helmholtz_solve_kernel<double><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
             (const double *)d_b, (double *)d_u, d_fac, outer, inner, n, n_u);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_helmholtz_matvec(const void *d_v, void *d_c, const double *d_A0, const double *d_A2, const double *d_A4,
+                         const double *d_Bm2, const double *d_B0, const double *d_B2, const double *d_alfa,
+                         const double *d_beta, int64_t outer, int64_t inner, int n, int n_u, int is_complex,
+                         void *stream) {
+    SHB_REQUIRE(d_v && d_c && d_v != d_c && d_A0 && d_A2 && d_A4 && d_Bm2 && d_B0 && d_B2 && d_alfa && d_beta &&
+                n >= 1 && n_u >= n, "bad arguments");
+    if (outer * inner == 0) return SHB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (is_complex)
+        helmholtz_matvec_kernel<cplx><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (const cplx *)d_v, (cplx *)d_c, d_A0, d_A2, d_A4, d_Bm2, d_B0, d_B2, d_alfa, d_beta, outer, inner, n, n_u);
+    else
+        helmholtz_matvec_kernel<double><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (const double *)d_v, (double *)d_c, d_A0, d_A2, d_A4, d_Bm2, d_B0, d_B2, d_alfa, d_beta, outer, inner, n, n_u);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }

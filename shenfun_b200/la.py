@@ -339,7 +339,8 @@ class SolverGeneric1ND:
         return self._fac[pinned]
 
     def matvec(self, u, c):
-        return self.op.matvec(ops.plain(u), ops.plain(c), accumulate=False)
+        self.op.matvec(ops.plain(u), ops.plain(c), accumulate=False)
+        return c
 
     def __call__(self, b, u=None, constraints=()):
         op = self.op
@@ -402,7 +403,10 @@ class Helmholtz:
         ops.helmholtz_factor(*self._tabs, self.alfa, self.beta, self.fac, op.outer, op.inner, n)
 
     def matvec(self, v, c):
-        return self.op.matvec(ops.plain(v), ops.plain(c), accumulate=False)
+        op = self.op
+        ops.helmholtz_matvec(ops.plain(v), ops.plain(c), self._tabs, self.alfa, self.beta, op.outer, op.inner,
+                             op.n_rows, op.n_u)
+        return c
 
     def __call__(self, b, u=None, constraints=()):
         op = self.op

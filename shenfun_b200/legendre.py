@@ -92,20 +92,22 @@ class Orthogonal(PolyBase):
         return D
 
     def ortho_gram(self, N, d_test, d_trial):
-        """(L_j^(b), L_i) in closed integer form where available (exact in fp64)."""
-        i = np.arange(N)[:, None].astype(float)
-        j = np.arange(N)[None, :].astype(float)
+        """(L_j^(b), L_i) in closed integer form where available (exact), extended precision."""
+        ld = np.longdouble
+        i = np.arange(N, dtype=ld)[:, None]
+        j = np.arange(N, dtype=ld)[None, :]
+        par = (np.arange(N)[:, None]+np.arange(N)[None, :]) % 2
         if d_trial == 0:
-            G = np.diag(self.ortho_norm_sq(N))
+            G = np.diag(ld(2)/(2*np.arange(N, dtype=ld)+1))
         elif d_trial == 1:
-            G = np.where((j > i) & ((i+j) % 2 == 1), 2.0, 0.0)
+            G = np.where((j > i) & (par == 1), ld(2), ld(0))
         elif d_trial == 2:
-            G = np.where((j > i) & ((i+j) % 2 == 0), j*(j+1)-i*(i+1), 0.0)
+            G = np.where((j > i) & (par == 0), j*(j+1)-i*(i+1), ld(0))
         else:
-            G = self.ortho_norm_sq(N)[:, None]*self.ortho_deriv_matrix(N, d_trial)
+            G = (ld(2)/(2*np.arange(N, dtype=ld)+1))[:, None]*self._deriv_ld(N, d_trial)
         if d_test > 0:
-            G = self.ortho_deriv_matrix(N, d_test).T @ G
-        return G
+            G = self._deriv_ld(N, d_test).T @ G
+        return G, ld(1)
 
     def boundary_values(self, n, order, side):
         n = np.asarray(n, dtype=float)

@@ -180,3 +180,10 @@ def gemm_axis(A, u, out, outer, inner):
     M, K = A.shape
     _call('shb_gemm_axis', _req(A, F64, 'A'), _req(u, u.dtype, 'u'), _req(out, out.dtype, 'out'), M, K, outer, inner,
           int(u.dtype.is_complex), _lib.stream_ptr())
+
+
+def helmholtz_matvec(v, c, tabs, alfa, beta, outer, inner, n, n_u):
+    assert v.dtype == c.dtype
+    _call('shb_helmholtz_matvec', _req(v, v.dtype, 'v'), _req(c, c.dtype, 'c'), *[_req(t, F64, 'table') for t in tabs],
+          _req(alfa, F64, 'alfa'), _req(beta, F64, 'beta'), outer, inner, n, n_u, int(v.dtype.is_complex),
+          _lib.stream_ptr())

@@ -213,13 +213,17 @@ class PolyBase(SpectralBase):
         nbc = len(conds)
         if nbc == 0:
             return np.zeros((0, 4))
-        n = np.arange(nbc)
+        # polynomials of the lowest degrees that can carry the conditions (pure Neumann
+        # data cannot be lifted by a constant)
+        m0 = min(order for (_, order, _) in conds)
+        n = m0+np.arange(nbc)
+        assert n.max() < 4, 'boundary lifting uses polynomials up to degree 3'
         A = np.zeros((nbc, nbc))
         for c, (side, order, _) in enumerate(conds):
             A[c] = self.boundary_values(n, order, side)
         C = np.linalg.solve(A, np.eye(nbc)).T       # row b: coefficients of function b
         out = np.zeros((nbc, 4))
-        out[:, :nbc] = C
+        out[:, n] = C
         # derivatives scale with the domain: value of d^o u/dx^o = df^o d^o u/dX^o
         df = self.domain_factor()
         for b, (_, order, _) in enumerate(conds):
@@ -232,23 +236,48 @@ class PolyBase(SpectralBase):
 
     # ---- matrices ------------------------------------------------------------------------------------
     def ortho_gram(self, N, d_test, d_trial):
-        """G[k, j] = (P_j^(d_trial), P_k^(d_test))_w on the reference domain (N x N, dense)."""
-        h = self.ortho_norm_sq(N)
-        G = h[:, None]*self.ortho_deriv_matrix(N, d_trial)
+        """(G, factor): factor*G[k, j] = (P_j^(d_trial), P_k^(d_test))_w on the reference domain.
+        G is held in extended precision with any irrational constant pulled out into `factor`, so
+        that the stencil recombination below (which cancels O(N^3) entries down to O(N)) loses
+        nothing: for integer stencils the result is exact."""
+        ld = np.longdouble
+        h = self.ortho_norm_sq(N).astype(ld)
+        G = h[:, None]*self._deriv_ld(N, d_trial)
         if d_test > 0:
-            G = self.ortho_deriv_matrix(N, d_test).T @ G
-        return G
+            G = self._deriv_ld(N, d_test).T @ G
+        return G, ld(1)
+
+    def _deriv_ld(self, N, k):
+        """k-th derivative matrix in extended precision (entries are integers / half-integers;
+        float64 products are exact up to k = 2, beyond that the magnitudes exceed 2^53)."""
+        ld = np.longdouble
+        if k <= 2:
+            return self.ortho_deriv_matrix(N, k).astype(ld)
+        D1 = self.ortho_deriv_matrix(N, 1).astype(ld)
+        D = self.ortho_deriv_matrix(N, 2).astype(ld)
+        for _ in range(k-2):
+            D = D1 @ D
+        return D
 
     def spectral_matrix(self, d_test, d_trial, trial=None, tol=1e-9):
         """(phi_j^(d_trial), psi_k^(d_test))_w as a banded SparseMatrix (dim_test x dim_trial);
         domain scaling as in matrixbase.py:690-691."""
         trial = self if trial is None else trial
         assert trial.N == self.N and trial.family() == self.family()
+        key = ('mat', d_test, d_trial, hash(trial))
+        if key in self._tables:
+            return self._tables[key]
+        ld = np.longdouble
         N = self.N
-        G = self.ortho_gram(N, d_test, d_trial)
-        Kt = self.stencil_matrix().diags()        # (dim_test, N)
-        Ku = trial.stencil_matrix().diags()       # (dim_trial, N)
-        A = Kt @ G @ Ku.T
+        G, fac = self.ortho_gram(N, d_test, d_trial)
+        dim_t, dim_u = self.dim(), trial.dim()
+        X = np.zeros((dim_t, N), dtype=ld)
+        for off, v in self.stencil().items():
+            X += np.asarray(v, dtype=ld)[:, None]*G[off:off+dim_t, :]
+        A = np.zeros((dim_t, dim_u), dtype=ld)
+        for off, v in trial.stencil().items():
+            A += X[:, off:off+dim_u]*np.asarray(v, dtype=ld)[None, :]
+        A = np.asarray(A*fac, dtype=float)
         scale = 1.0
         df = float(self.domain_factor())
         if df != 1:
@@ -262,7 +291,8 @@ class PolyBase(SpectralBase):
                 d[off] = v.copy()
         if not d:
             d = {0: np.zeros(min(M, Nn))}
-        return SparseMatrix(d, A.shape, scale)
+        self._tables[key] = SparseMatrix(d, A.shape, scale)
+        return self._tables[key]
 
     def mass_matrix(self):
         if 'mass' not in self._tables:
@@ -274,7 +304,8 @@ class PolyBase(SpectralBase):
         transform to move the lifting to the right hand side (tensorproductspace.py:2091-2106)."""
         if 'bc_mass' not in self._tables:
             N = self.N
-            G = self.ortho_gram(N, 0, 0)
+            G, fac = self.ortho_gram(N, 0, 0)
+            G = np.asarray(G*fac, dtype=float)
             Kt = self.stencil_matrix().diags()
             L = np.zeros((self.bcs.num_bcs(), N))
             L[:, :4] = self.bc_basis()[:, :min(4, N)]

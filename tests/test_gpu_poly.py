@@ -83,7 +83,9 @@ def test_larger_transforms_against_oracle(fam, N, name):
     ud = torch.from_numpy(u).cuda()
     out = torch.empty_like(ud)
     T.bases[0]._forward_axis(ud, out, 1, 60)
-    assert rel_l2(out.cpu().numpy(), opb.forward_axis(u, 0, spec)) < TOL
+    # the forward transform ends with the inverse-mass banded solve: for the biharmonic basis the
+    # pentadiagonal mass matrix is ill conditioned (cond ~ N^4), device LU vs LAPACK differ by cond*eps
+    assert rel_l2(out.cpu().numpy(), opb.forward_axis(u, 0, spec)) < (1e-11 if name == 'biharmonic' else TOL)
     vh = np.array(u)
     vh[S.dim():] = 0
     T.bases[0]._backward_axis(torch.from_numpy(vh).cuda(), out, 1, 60)
