@@ -41,34 +41,71 @@ class SlabExchange:
         return tuple(a), tuple(b)
 
     def __call__(self, src, dst, ncomp, direction):
-        """direction 'forward'/'scalar_product': gather `ga`, scatter `sa`; 'backward': reverse."""
+        """direction 'forward'/'scalar_product': gather `ga`, scatter `sa`; 'backward': reverse.
+
+        When the scattered axis is the leading one of a chunk the peer blocks are already
+        contiguous on that side, so only ONE local strided copy (pack or unpack) is needed:
+        the other side of the all-to-all reads from / writes to the array itself."""
         lead = src.dim() - len(self.gshape)
         if direction == 'backward':
             ga, sa, g_blocks, s_blocks = self.sa, self.ga, self.s_blocks, self.g_blocks
         else:
             ga, sa, g_blocks, s_blocks = self.ga, self.sa, self.g_blocks, self.s_blocks
-        ga += lead
-        sa += lead
         P, rank = self.P, self.rank
-        # pack: chunk p = src[..., s_blocks[p] along sa, ...] made contiguous
-        send_chunks = [src.narrow(sa, s_blocks[p][0], s_blocks[p][1]) for p in range(P)]
-        send_sizes = [int(c.numel()) for c in send_chunks]
-        sendbuf = torch.cat([c.reshape(-1) for c in send_chunks])
-        # receive: from peer p a block with its g-extent along ga and my s-extent along sa
-        recv_shapes = []
+        batch = int(np.prod(src.shape[:lead])) if lead else 1
+        # leading batch (vector components) is exchanged component by component when it would
+        # break contiguity of the peer blocks
+        if batch > 1:
+            sv = src.reshape((batch,)+tuple(src.shape[lead:]))
+            dv = dst.reshape((batch,)+tuple(dst.shape[lead:]))
+            for c in range(batch):
+                self._exchange(sv[c], dv[c], ga, sa, g_blocks, s_blocks)
+        else:
+            self._exchange(src.reshape(src.shape[lead:]), dst.reshape(dst.shape[lead:]), ga, sa, g_blocks, s_blocks)
+
+    def _exchange(self, src, dst, ga, sa, g_blocks, s_blocks):
+        P, rank = self.P, self.rank
+        send_sizes = []
+        recv_sizes = []
         for p in range(P):
             sh = list(src.shape)
+            sh[sa] = s_blocks[p][1]
+            send_sizes.append(int(np.prod(sh)))
+            sh = list(dst.shape)
             sh[ga] = g_blocks[p][1]
-            sh[sa] = s_blocks[rank][1]
-            recv_shapes.append(sh)
-        recv_sizes = [int(np.prod(s)) for s in recv_shapes]
-        recvbuf = torch.empty(sum(recv_sizes), dtype=src.dtype, device=src.device)
+            recv_sizes.append(int(np.prod(sh)))
+        # send side: chunk p = src[.., s_blocks[p] along sa, ..]; contiguous already when sa == 0
+        if sa == 0:
+            sendbuf = src.reshape(-1)
+        else:
+            sendbuf = self._buffer('send', src.numel(), src)
+            off = 0
+            for p in range(P):
+                chunk = src.narrow(sa, s_blocks[p][0], s_blocks[p][1])
+                sendbuf[off:off+send_sizes[p]].view(chunk.shape).copy_(chunk)
+                off += send_sizes[p]
+        # receive side: block from p spans g_blocks[p] along ga; lands in place when ga == 0
+        if ga == 0:
+            recvbuf = dst.reshape(-1)
+        else:
+            recvbuf = self._buffer('recv', dst.numel(), dst)
         _all_to_all(recvbuf, sendbuf, recv_sizes, send_sizes, self.comm.group)
-        off = 0
-        for p in range(P):
-            blk = recvbuf[off:off+recv_sizes[p]].view(recv_shapes[p])
-            dst.narrow(ga, g_blocks[p][0], g_blocks[p][1]).copy_(blk)
-            off += recv_sizes[p]
+        if ga != 0:
+            off = 0
+            for p in range(P):
+                tgt = dst.narrow(ga, g_blocks[p][0], g_blocks[p][1])
+                tgt.copy_(recvbuf[off:off+recv_sizes[p]].view(tgt.shape))
+                off += recv_sizes[p]
+
+    def _buffer(self, name, numel, like):
+        key = (name, like.dtype, like.device)
+        if not hasattr(self, '_bufs'):
+            self._bufs = {}
+        b = self._bufs.get(key)
+        if b is None or b.numel() < numel:
+            b = torch.empty(numel, dtype=like.dtype, device=like.device)
+            self._bufs[key] = b
+        return b[:numel]
 
 
 def _all_to_all(recvbuf, sendbuf, recv_sizes, send_sizes, group):

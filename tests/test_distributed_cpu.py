@@ -1,0 +1,75 @@
+"""Host-side multi-rank logic on CPU: two gloo processes check the slab bookkeeping of
+TensorProductSpace (local shapes / slices as mpi4py-fft's slab decomposition) and the
+SlabExchange redistribution against a numpy model of the global array."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import shenfun_b200 as sf
+        from shenfun_b200.transfer import SlabExchange
+        comm = sf.Comm()
+        assert comm.Get_size() == world and comm.Get_rank() == rank
+        # --- bookkeeping of a slab-distributed Fourier space (uneven split on purpose)
+        N = (10, 9, 8)
+        T = sf.TensorProductSpace(comm, [sf.FunctionSpace(N[0], 'F', dtype='D'), sf.FunctionSpace(N[1], 'F', dtype='D'),
+                                         sf.FunctionSpace(N[2], 'F', dtype='d')])
+        assert T.global_shape(False) == (10, 9, 8) and T.global_shape(True) == (10, 9, 5)
+        n0 = [5, 5][rank]
+        n1 = [5, 4][rank]
+        assert T.shape(False) == (n0, 9, 8), T.shape(False)
+        assert T.shape(True) == (10, n1, 5), T.shape(True)
+        assert T.local_slice(False)[0] == slice(rank*5, rank*5+5)
+        assert T.local_slice(True)[1] == (slice(0, 5) if rank == 0 else slice(5, 9))
+        Tp = T.get_dealiased((1.5, 1.5, 1.5))
+        assert Tp.shape(True) == T.shape(True)
+        assert Tp.global_shape(False) == (15, 13, 12)
+        # --- exchange against a numpy model of the global array
+        rng = np.random.default_rng(5)
+        G = rng.standard_normal((10, 9, 5))+1j*rng.standard_normal((10, 9, 5))
+        ex = SlabExchange(comm, (10, 9, 5), gather_axis=0, scatter_axis=1)
+        src = torch.from_numpy(np.ascontiguousarray(G[T.local_slice(False)[0]]))
+        dst = torch.empty((10, n1, 5), dtype=torch.complex128)
+        ex(src, dst, 1, 'forward')
+        assert np.array_equal(dst.numpy(), G[:, T.local_slice(True)[1]])
+        back = torch.empty_like(src)
+        ex(dst, back, 1, 'backward')
+        assert np.array_equal(back.numpy(), src.numpy())
+        # vector valued (leading component axis)
+        GV = rng.standard_normal((3, 10, 9, 5))
+        srcv = torch.from_numpy(np.ascontiguousarray(GV[:, T.local_slice(False)[0]]))
+        dstv = torch.empty((3, 10, n1, 5), dtype=torch.float64)
+        ex(srcv, dstv, 3, 'forward')
+        assert np.array_equal(dstv.numpy(), GV[:, :, T.local_slice(True)[1]])
+        # reductions through the communicator facade
+        assert comm.allreduce(float(rank+1)) == 3.0
+        assert comm.bcast({'a': rank}, root=0) == {'a': 0}
+        results[rank] = 'ok'
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        results[rank] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_slab_logic_gloo():
+    world = 2
+    port = 29600+os.getpid() % 300
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+    for r in range(world):
+        assert results.get(r) == 'ok', results.get(r)
