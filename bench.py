@@ -326,10 +326,16 @@ def secondary_workloads(T, uh, args, peak):
     try:
         from shenfun_b200.demos import navier_stokes
         out['ns'] = navier_stokes.bench(512, steps=max(2, min(args.steps, 5)), warmup=1)
-    except ImportError:
-        pass
     except Exception as e:  # noqa: BLE001
         out['ns'] = {'error': repr(e)}
+    torch.cuda.empty_cache()
+    try:
+        from shenfun_b200.demos import poisson3d, biharmonic3d
+        out['poisson3d_chebyshev_512'] = poisson3d.bench(512, 'C')
+        torch.cuda.empty_cache()
+        out['biharmonic3d_legendre_256'] = biharmonic3d.bench(256, 'L')
+    except Exception as e:  # noqa: BLE001
+        out['poisson_biharmonic'] = {'error': repr(e)}
     return out
 
 
