@@ -65,6 +65,18 @@ SHB_API int shb_fft_c2c_forward(const void *d_in, void *d_out, int64_t outer, in
 SHB_API int shb_fft_c2c_backward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
                          int n_fft, int N, double scale, int flags, void *stream);
 
+/* C2C transform fused with the local half of the slab all-to-all (replaces the pack /
+ * unpack that mpi4py_fft.pencil.Transfer expresses as MPI sub-array datatypes; call sites
+ * shenfun/tensorproductspace.py:89,183,252).  With chunk_rows = cr != 0 the rows of the
+ * transform axis are addressed peer by peer: row r of outer index o is at
+ *   (r / cr) * (outer*cr*inner) + (o*cr + r % cr) * inner + c
+ * i.e. the send buffer (out_chunk_rows) / receive buffer (in_chunk_rows) of an all-to-all
+ * with equal blocks.  Returns SHB_ERR_UNSUPPORTED when no register-resident kernel covers
+ * the size (callers then pack / unpack separately).                                   */
+SHB_API int shb_fft_c2c_chunked(int backward, const void *d_in, void *d_out, int64_t outer, int64_t inner,
+                                int n_fft, int N, double scale, int flags, int in_chunk_rows,
+                                int out_chunk_rows, void *stream);
+
 /* Real-to-complex forward DFT of length n_fft, truncation to N//2+1 modes
  * (Nyquist -> 2*Re when N even and N < n_fft), scaling.
  * in : real [outer][n_fft][inner];  out : complex [outer][N/2+1][inner].  */

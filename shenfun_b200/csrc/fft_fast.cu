@@ -131,6 +131,10 @@ struct FastDesc {
     int n_fft, N, n_in, n_out, flags;
     double scale;
     const cplx *tw, *tw2;
+    // peer-chunked addressing along the transform axis (fused all-to-all pack / unpack):
+    // row r of outer index o lives at (r / cr) * cs + ((o * cr + r % cr) * inner + c); cr == 0: off
+    int in_cr, out_cr;
+    int64_t in_cs, out_cs;
 };
 
 // zero-padding rule of the C2C backward transform as a branch-free gather:
@@ -154,8 +158,9 @@ struct PadMap {
 };
 
 // ---- kernel A ---------------------------------------------------------------------
-template <class SC, int MODE, int T>
-__global__ void __launch_bounds__(SC::P *T) fft_strided_kernel(const __grid_constant__ FastDesc d) {
+template <class SC, int MODE, int T, bool CH>
+__global__ void __launch_bounds__(SC::P *T, (SC::P * T <= 512 && SC::EMAX <= 8 ? 2 : 1))
+fft_strided_kernel(const __grid_constant__ FastDesc d) {
     constexpr bool INV = (MODE == FFT_C2C_BWD);
     constexpr int M = SC::M, P = SC::P;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -165,9 +170,22 @@ __global__ void __launch_bounds__(SC::P *T) fft_strided_kernel(const __grid_cons
     const int64_t line = (int64_t)blockIdx.x * T + c;
     const bool valid = line < d.nlines;
     const int64_t o = valid ? line / d.inner : 0, cc = valid ? line % d.inner : 0;
-    const int64_t stride = d.inner;
-    const cplx *__restrict__ in = reinterpret_cast<const cplx *>(d.in) + (o * d.n_in * d.inner + cc);
-    cplx *__restrict__ out = reinterpret_cast<cplx *>(d.out) + (o * d.n_out * d.inner + cc);
+    const cplx *__restrict__ inb = reinterpret_cast<const cplx *>(d.in);
+    cplx *__restrict__ outb = reinterpret_cast<cplx *>(d.out);
+    auto in_at = [&](int r) -> const cplx & {
+        if (CH && d.in_cr) {
+            const int p = r / d.in_cr;
+            return inb[p * d.in_cs + ((o * d.in_cr + (r - p * d.in_cr)) * d.inner + cc)];
+        }
+        return inb[(o * d.n_in + r) * d.inner + cc];
+    };
+    auto out_at = [&](int r) -> cplx & {
+        if (CH && d.out_cr) {
+            const int p = r / d.out_cr;
+            return outb[p * d.out_cs + ((o * d.out_cr + (r - p * d.out_cr)) * d.inner + cc)];
+        }
+        return outb[(o * d.n_out + r) * d.inner + cc];
+    };
     const int N = d.N;
     const bool padded = (N < M);
     const bool evenN = (N % 2 == 0);
@@ -187,7 +205,7 @@ __global__ void __launch_bounds__(SC::P *T) fft_strided_kernel(const __grid_cons
                 double f = 1.0;
                 if (MODE == FFT_C2C_BWD) ok = pm.map(r, src, f) && valid;
                 cplx x = make_double2(0.0, 0.0);
-                if (ok) x = in[(int64_t)src * stride];
+                if (ok) x = in_at(src);
                 v[q * SC::R0 + m] = (MODE == FFT_C2C_BWD) ? make_double2(x.x * f, x.y * f) : x;
             }
         }
@@ -216,14 +234,14 @@ __global__ void __launch_bounds__(SC::P *T) fft_strided_kernel(const __grid_cons
                 const int r = (j + q * P) + m * SC::NBL;
                 const cplx x0 = v[q * SC::RL + m];
                 if (MODE == FFT_C2C_BWD || !padded) {
-                    out[(int64_t)r * stride] = cscale(x0, scale);
+                    out_at(r) = cscale(x0, scale);
                 } else {
                     if (r <= h) {
                         cplx x = x0;
                         if (evenN && r == h) x = cadd(x, sm[c]);
-                        out[(int64_t)r * stride] = cscale(x, scale);
+                        out_at(r) = cscale(x, scale);
                     } else if (r > M - h || (!evenN && r == M - h)) {
-                        out[(int64_t)(r - M + N) * stride] = cscale(x0, scale);
+                        out_at(r - M + N) = cscale(x0, scale);
                     }
                 }
             }
@@ -414,19 +432,25 @@ __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_cons
 }
 
 // ---- host-side dispatch ---------------------------------------------------------------
-template <class SC, int MODE, int T>
-static int launch_strided(const FastDesc &d, cudaStream_t st) {
+template <class SC, int MODE, int T, bool CH>
+static int launch_strided_ch(const FastDesc &d, cudaStream_t st) {
     constexpr size_t smem = (size_t)SC::M * T * sizeof(cplx);
     static bool attr_set = false;
     if (!attr_set) {
-        SHB_CUDA(cudaFuncSetAttribute(fft_strided_kernel<SC, MODE, T>,
+        SHB_CUDA(cudaFuncSetAttribute(fft_strided_kernel<SC, MODE, T, CH>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int64_t ntiles = (d.nlines + T - 1) / T;
-    fft_strided_kernel<SC, MODE, T><<<(unsigned)ntiles, SC::P * T, smem, st>>>(d);
+    fft_strided_kernel<SC, MODE, T, CH><<<(unsigned)ntiles, SC::P * T, smem, st>>>(d);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
+}
+
+template <class SC, int MODE, int T>
+static int launch_strided(const FastDesc &d, cudaStream_t st) {
+    if (d.in_cr || d.out_cr) return launch_strided_ch<SC, MODE, T, true>(d, st);
+    return launch_strided_ch<SC, MODE, T, false>(d, st);
 }
 
 template <class SC, int MODE, int TL>
@@ -491,8 +515,10 @@ static int contig_r2c(int M, const FastDesc &d, cudaStream_t st) { SHB_CONTIG_CA
 static int contig_c2r(int M, const FastDesc &d, cudaStream_t st) { SHB_CONTIG_CASES(FFT_C2R) }
 
 int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner,
-                    int n_fft, int N, double scale, int flags, cudaStream_t st) {
+                    int n_fft, int N, double scale, int flags, cudaStream_t st, int in_cr, int out_cr) {
     FastDesc d;
+    d.in_cr = in_cr; d.out_cr = out_cr;
+    d.in_cs = (int64_t)outer * in_cr * inner; d.out_cs = (int64_t)outer * out_cr * inner;
     d.in = in; d.out = out; d.outer = outer; d.inner = inner; d.nlines = outer * inner;
     d.n_fft = n_fft; d.N = N; d.flags = flags; d.scale = scale;
     if (d.nlines == 0) return SHB_OK;
@@ -517,6 +543,7 @@ int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t 
     };
     const bool strided = inner > 1;
     if (!supported(M, strided)) return SHB_ERR_UNSUPPORTED;
+    if ((in_cr || out_cr) && !strided) return SHB_ERR_UNSUPPORTED;
     d.tw = twiddle_table(0, M);
     d.tw2 = (mode == FFT_R2C || mode == FFT_C2R) ? twiddle_table(1, M) : nullptr;
     if (!d.tw || ((mode == FFT_R2C || mode == FFT_C2R) && !d.tw2)) {

@@ -150,10 +150,19 @@ class C2C(FourierBase):
     def inplace_ok(self):
         return not self.is_padded
 
-    def _forward_axis(self, u, out, outer, inner, scalar_product=False):
-        n = self.physical_len()
-        ops.fft_c2c_forward(u, out, outer, inner, n, self.N, 1./n)
+    supports_chunked = True    # axis kernels can address the all-to-all send / receive layout
 
-    def _backward_axis(self, uh, out, outer, inner):
-        ops.fft_c2c_backward(uh, out, outer, inner, self.physical_len(), self.N, 1.0,
-                             self.dealias_direct)
+    def _forward_axis(self, u, out, outer, inner, scalar_product=False, in_chunk=0, out_chunk=0):
+        n = self.physical_len()
+        if in_chunk or out_chunk:
+            ops.fft_c2c_chunked(False, u, out, outer, inner, n, self.N, 1./n, False, in_chunk, out_chunk)
+        else:
+            ops.fft_c2c_forward(u, out, outer, inner, n, self.N, 1./n)
+
+    def _backward_axis(self, uh, out, outer, inner, in_chunk=0, out_chunk=0):
+        if in_chunk or out_chunk:
+            ops.fft_c2c_chunked(True, uh, out, outer, inner, self.physical_len(), self.N, 1.0,
+                                self.dealias_direct, in_chunk, out_chunk)
+        else:
+            ops.fft_c2c_backward(uh, out, outer, inner, self.physical_len(), self.N, 1.0,
+                                 self.dealias_direct)

@@ -57,6 +57,12 @@ def fft_c2c_backward(uh, out, outer, inner, n_fft, N, scale=1.0, dealias_direct=
           outer, inner, n_fft, N, scale, int(dealias_direct), _lib.stream_ptr())
 
 
+def fft_c2c_chunked(backward, u, out, outer, inner, n_fft, N, scale, dealias_direct=False, in_chunk=0, out_chunk=0):
+    """C2C transform reading from / writing to the peer-chunked layout of the slab all-to-all."""
+    _call('shb_fft_c2c_chunked', int(backward), _req(u, C128, 'in'), _req(out, C128, 'out'), outer, inner, n_fft, N,
+          scale, int(dealias_direct), int(in_chunk), int(out_chunk), _lib.stream_ptr())
+
+
 def fft_r2c_forward(u, out, outer, inner, n_fft, N, scale):
     _call('shb_fft_r2c_forward', _req(u, F64, 'in'), _req(out, C128, 'out'),
           outer, inner, n_fft, N, scale, _lib.stream_ptr())

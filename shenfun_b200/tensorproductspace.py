@@ -39,7 +39,7 @@ def _block(N, P, i):
 class _Step:
     """One stage of a plan: an axis transform or a global exchange."""
     __slots__ = ('kind', 'axis', 'base', 'in_shape', 'out_shape', 'in_dtype', 'out_dtype',
-                 'inplace_ok', 'exchange')
+                 'inplace_ok', 'exchange', 'fuse')
 
     def __init__(self, kind, axis, base, in_shape, out_shape, in_dtype, out_dtype,
                  inplace_ok=False, exchange=None):
@@ -52,6 +52,7 @@ class _Step:
         self.out_dtype = out_dtype
         self.inplace_ok = inplace_ok
         self.exchange = exchange
+        self.fuse = None      # exchange steps: [producer_fused, consumer_fused]
 
 
 class _WorkPool:
@@ -87,6 +88,22 @@ class _Transform:
         return self.steps[-1].out_shape
 
     def _run(self, u, out, ncomp):
+        from ._lib import ShenB200Error
+        try:
+            return self._run_impl(u, out, ncomp)
+        except ShenB200Error as e:
+            fused = [s for s in self.steps if s.kind == 'exchange' and s.fuse and any(s.fuse)]
+            if 'fft_c2c_chunked' not in str(e) or not fused:
+                raise
+            # no register-resident kernel for this size: pack / unpack around the all-to-all instead
+            sp = self.space
+            for tr in (sp.forward, sp.backward, sp.scalar_product):
+                for s in tr.steps:
+                    if s.kind == 'exchange':
+                        s.fuse = None
+            return self._run_impl(u, out, ncomp)
+
+    def _run_impl(self, u, out, ncomp):
         """u, out: plain contiguous tensors with a leading component batch folded in."""
         steps = self.steps
         n = len(steps)
@@ -101,11 +118,23 @@ class _Transform:
         cur = u
         cur_is_user_input = True
         which = 0
+        bwd = self.direction == 'backward'
+        cur_packed = False
         for i, s in enumerate(steps):
             full_out_shape = lead + s.out_shape
+            # fused all-to-all: the axis kernel before an exchange writes the send layout, the one
+            # after it reads the receive layout (see transfer.SlabExchange / shb_fft_c2c_chunked)
+            out_chunk = in_chunk = 0
+            nxt = steps[i+1] if i+1 < n else None
+            prv = steps[i-1] if i > 0 else None
+            if s.kind == 'axis' and nxt is not None and nxt.kind == 'exchange' and nxt.fuse and nxt.fuse[0]:
+                out_chunk = nxt.exchange.chunk_rows(self.direction, 'send')
+            if s.kind == 'axis' and prv is not None and prv.kind == 'exchange' and prv.fuse and prv.fuse[1]:
+                in_chunk = prv.exchange.chunk_rows(self.direction, 'recv')
+            fused_io = bool(out_chunk or in_chunk)
             can_inplace = (s.inplace_ok and s.in_shape == s.out_shape and s.in_dtype == s.out_dtype
-                           and not cur_is_user_input)
-            if dest_is_out[i]:
+                           and not cur_is_user_input and not fused_io and s.kind == 'axis')
+            if dest_is_out[i] and not out_chunk and not (s.kind == 'exchange' and s.fuse and s.fuse[1]):
                 if can_inplace and cur.data_ptr() == out.data_ptr():
                     dst = cur
                 else:
@@ -119,16 +148,22 @@ class _Transform:
                     dst = self._pool.get(which, full_out_shape, s.out_dtype, u.device)
                 which ^= 1
             if s.kind == 'exchange':
-                s.exchange(cur, dst, ncomp, self.direction)
+                s.exchange(cur, dst, ncomp, self.direction, src_packed=cur_packed,
+                           dst_packed=bool(s.fuse and s.fuse[1]))
+                cur_packed = False
             else:
                 ax = s.axis
                 outer = ncomp*int(np.prod(s.in_shape[:ax], dtype=np.int64))
                 inner = int(np.prod(s.in_shape[ax+1:], dtype=np.int64))
-                if self.direction == 'backward':
-                    s.base._backward_axis(cur, dst, outer, inner)
+                kw = {}
+                if fused_io:
+                    kw = dict(in_chunk=in_chunk, out_chunk=out_chunk)
+                if bwd:
+                    s.base._backward_axis(cur, dst, outer, inner, **kw)
                 else:
                     s.base._forward_axis(cur, dst, outer, inner,
-                                         scalar_product=(self.direction == 'scalar_product'))
+                                         scalar_product=(self.direction == 'scalar_product'), **kw)
+                cur_packed = bool(out_chunk)
             cur = dst
             cur_is_user_input = False
         if cur.data_ptr() != out.data_ptr():
@@ -192,6 +227,7 @@ class TensorProductSpace:
         self._padded_space = {}
         self._pool = _WorkPool()
         self.coors = None
+        self._fuse_exchange = bool(kw.pop('fuse_exchange', True))
 
         first = self.bases[self.axes[-1]]
         # tensorproductspace.py:365-385: real input needs an R2C (or a real
@@ -250,7 +286,16 @@ class TensorProductSpace:
                 in_shape, _ = self._local(gshape, dist)
                 out_shape, _ = self._local(gshape, new_dist)
                 ex = SlabExchange(self.comm, tuple(gshape), gather_axis=dist, scatter_axis=new_dist)
-                fsteps.append(_Step('exchange', None, None, in_shape, out_shape, dt, dt, exchange=ex))
+                st = _Step('exchange', None, None, in_shape, out_shape, dt, dt, exchange=ex)
+                # fuse the pack into the kernel of the axis transformed just before (new_dist) and the
+                # unpack into the kernel of the axis transformed next (ax), when both can address
+                # the peer-chunked layout and the blocks are equal
+                prod = fsteps[-1].base if fsteps and fsteps[-1].kind == 'axis' else None
+                can = ex.uniform() and dt == torch.complex128 and self._fuse_exchange
+                st.fuse = [bool(can and prod is not None and getattr(prod, 'supports_chunked', False)
+                                and fsteps[-1].axis == new_dist),
+                           bool(can and getattr(b, 'supports_chunked', False))]
+                fsteps.append(st)
                 dist = new_dist
             in_shape, _ = self._local(gshape, dist)
             gshape[ax] = b.spectral_len()
@@ -263,8 +308,11 @@ class TensorProductSpace:
         # backward = mirror image
         bsteps = []
         for s in reversed(fsteps):
-            bsteps.append(_Step(s.kind, s.axis, s.base, s.out_shape, s.in_shape, s.out_dtype, s.in_dtype,
-                                inplace_ok=s.inplace_ok, exchange=s.exchange))
+            b_ = _Step(s.kind, s.axis, s.base, s.out_shape, s.in_shape, s.out_dtype, s.in_dtype,
+                       inplace_ok=s.inplace_ok, exchange=s.exchange)
+            if s.fuse:
+                b_.fuse = [s.fuse[1], s.fuse[0]]      # producer / consumer swap roles
+            bsteps.append(b_)
         self.forward = _Transform(self, fsteps, 'forward')
         self.backward = _Transform(self, bsteps, 'backward')
         self.scalar_product = _Transform(self, fsteps, 'scalar_product')

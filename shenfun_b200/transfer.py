@@ -40,60 +40,76 @@ class SlabExchange:
         b[self.sa] = self.s_blocks[self.rank][1]
         return tuple(a), tuple(b)
 
-    def __call__(self, src, dst, ncomp, direction):
-        """direction 'forward'/'scalar_product': gather `ga`, scatter `sa`; 'backward': reverse.
+    def chunk_rows(self, direction, side):
+        """Rows per peer chunk along the axis of the kernel on the send / receive side."""
+        if direction == 'backward':
+            ga, sa = self.sa, self.ga
+        else:
+            ga, sa = self.ga, self.sa
+        ax = sa if side == 'send' else ga
+        return self.gshape[ax]//self.P
 
-        When the scattered axis is the leading one of a chunk the peer blocks are already
-        contiguous on that side, so only ONE local strided copy (pack or unpack) is needed:
-        the other side of the all-to-all reads from / writes to the array itself."""
-        lead = src.dim() - len(self.gshape)
+    def uniform(self):
+        """Equal blocks on both axes (needed by the fused, kernel-side pack / unpack)."""
+        return self.gshape[self.ga] % self.P == 0 and self.gshape[self.sa] % self.P == 0
+
+    def __call__(self, src, dst, ncomp, direction, src_packed=False, dst_packed=False):
+        """Redistribute.  direction 'forward'/'scalar_product': un-distribute `ga`, distribute
+        `sa`; 'backward': the reverse.
+
+        Peer-chunked ("packed") layout: chunk p holds the block exchanged with rank p in the
+        array's own index order.  `src_packed`: the producing kernel already wrote that layout
+        (src is the flat send buffer); `dst_packed`: the consuming kernel will read it (dst is
+        the flat receive buffer).  Otherwise one strided copy packs / unpacks -- or none at all
+        when the blocks are contiguous in the array (leading axis, single component)."""
+        nd = len(self.gshape)
         if direction == 'backward':
             ga, sa, g_blocks, s_blocks = self.sa, self.ga, self.s_blocks, self.g_blocks
         else:
             ga, sa, g_blocks, s_blocks = self.ga, self.sa, self.g_blocks, self.s_blocks
         P, rank = self.P, self.rank
-        batch = int(np.prod(src.shape[:lead])) if lead else 1
-        # leading batch (vector components) is exchanged component by component when it would
-        # break contiguity of the peer blocks
-        if batch > 1:
-            sv = src.reshape((batch,)+tuple(src.shape[lead:]))
-            dv = dst.reshape((batch,)+tuple(dst.shape[lead:]))
-            for c in range(batch):
-                self._exchange(sv[c], dv[c], ga, sa, g_blocks, s_blocks)
-        else:
-            self._exchange(src.reshape(src.shape[lead:]), dst.reshape(dst.shape[lead:]), ga, sa, g_blocks, s_blocks)
-
-    def _exchange(self, src, dst, ga, sa, g_blocks, s_blocks):
-        P, rank = self.P, self.rank
-        send_sizes = []
-        recv_sizes = []
+        # local shapes before / after (with the leading component batch)
+        sh_a = list(self.gshape)
+        sh_a[ga] = g_blocks[rank][1]
+        sh_b = list(self.gshape)
+        sh_b[sa] = s_blocks[rank][1]
+        lead = (ncomp,) if ncomp > 1 else ()
+        L = len(lead)
+        send_sizes, recv_sizes, send_shapes, recv_shapes = [], [], [], []
         for p in range(P):
-            sh = list(src.shape)
-            sh[sa] = s_blocks[p][1]
-            send_sizes.append(int(np.prod(sh)))
-            sh = list(dst.shape)
-            sh[ga] = g_blocks[p][1]
-            recv_sizes.append(int(np.prod(sh)))
-        # send side: chunk p = src[.., s_blocks[p] along sa, ..]; contiguous already when sa == 0
-        if sa == 0:
+            s = list(sh_a)
+            s[sa] = s_blocks[p][1]
+            send_shapes.append(lead+tuple(s))
+            send_sizes.append(int(np.prod(send_shapes[-1])))
+            r = list(sh_b)
+            r[ga] = g_blocks[p][1]
+            recv_shapes.append(lead+tuple(r))
+            recv_sizes.append(int(np.prod(recv_shapes[-1])))
+        # ---- send side
+        if src_packed:
             sendbuf = src.reshape(-1)
+        elif sa == 0 and ncomp == 1:
+            sendbuf = src.reshape(-1)                        # blocks already contiguous
         else:
-            sendbuf = self._buffer('send', src.numel(), src)
+            srcv = src.reshape(lead+tuple(sh_a))
+            sendbuf = self._buffer('send', srcv.numel(), src)
             off = 0
             for p in range(P):
-                chunk = src.narrow(sa, s_blocks[p][0], s_blocks[p][1])
+                chunk = srcv.narrow(sa+L, s_blocks[p][0], s_blocks[p][1])
                 sendbuf[off:off+send_sizes[p]].view(chunk.shape).copy_(chunk)
                 off += send_sizes[p]
-        # receive side: block from p spans g_blocks[p] along ga; lands in place when ga == 0
-        if ga == 0:
+        # ---- receive side
+        direct = (ga == 0 and ncomp == 1)
+        if dst_packed or direct:
             recvbuf = dst.reshape(-1)
         else:
-            recvbuf = self._buffer('recv', dst.numel(), dst)
+            recvbuf = self._buffer('recv', sum(recv_sizes), dst)
         _all_to_all(recvbuf, sendbuf, recv_sizes, send_sizes, self.comm.group)
-        if ga != 0:
+        if not (dst_packed or direct):
+            dstv = dst.reshape(lead+tuple(sh_b))
             off = 0
             for p in range(P):
-                tgt = dst.narrow(ga, g_blocks[p][0], g_blocks[p][1])
+                tgt = dstv.narrow(ga+L, g_blocks[p][0], g_blocks[p][1])
                 tgt.copy_(recvbuf[off:off+recv_sizes[p]].view(tgt.shape))
                 off += recv_sizes[p]
 
