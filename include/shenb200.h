@@ -77,6 +77,15 @@ SHB_API int shb_fft_c2c_chunked(int backward, const void *d_in, void *d_out, int
                                 int n_fft, int N, double scale, int flags, int in_chunk_rows,
                                 int out_chunk_rows, void *stream);
 
+/* Same, with the all-to-all done by the kernel itself: block p of the output is stored
+ * straight into d_peer_out[p] -- the receive buffer of rank p (peer-mapped memory over
+ * NVLink / NVSwitch), already offset to this rank's slot -- so the transfer overlaps the
+ * transform tile by tile and no separate collective runs.  The caller synchronises the
+ * ranks (barrier) before the consumers read.  d_peer_out is a HOST array of nranks pointers. */
+SHB_API int shb_fft_c2c_peer(int backward, const void *d_in, void *const *d_peer_out, int nranks,
+                             int64_t outer, int64_t inner, int n_fft, int N, double scale, int flags,
+                             int in_chunk_rows, int out_chunk_rows, void *stream);
+
 /* Real-to-complex forward DFT of length n_fft, truncation to N//2+1 modes
  * (Nyquist -> 2*Re when N even and N < n_fft), scaling.
  * in : real [outer][n_fft][inner];  out : complex [outer][N/2+1][inner].  */

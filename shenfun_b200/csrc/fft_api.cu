@@ -27,6 +27,26 @@ static int dispatch(int mode, const void *in, void *out, int64_t outer, int64_t 
 
 extern "C" {
 
+int shb_fft_c2c_peer(int backward, const void *d_in, void *const *d_peer_out, int nranks, int64_t outer,
+                     int64_t inner, int n_fft, int N, double scale, int flags, int in_chunk_rows,
+                     int out_chunk_rows, void *stream) {
+    if (!d_in || !d_peer_out || nranks < 1 || nranks > 8 || outer < 0 || inner < 0 || n_fft < 1 || N < 1 ||
+        N > n_fft || in_chunk_rows < 0 || out_chunk_rows <= 0) {
+        set_error("fft_c2c_peer: bad arguments");
+        return SHB_ERR_ARG;
+    }
+    const int n_in = backward ? N : n_fft, n_out = backward ? n_fft : N;
+    if ((in_chunk_rows && n_in % in_chunk_rows) || n_out % out_chunk_rows || n_out / out_chunk_rows != nranks) {
+        set_error("fft_c2c_peer: chunk rows must split the axis into one block per rank");
+        return SHB_ERR_ARG;
+    }
+    int rc = fft_fast_launch(backward ? FFT_C2C_BWD : FFT_C2C_FWD, d_in, d_peer_out[0], outer, inner, n_fft, N, scale,
+                             flags, reinterpret_cast<cudaStream_t>(stream), in_chunk_rows, out_chunk_rows,
+                             d_peer_out, nranks);
+    if (rc == SHB_ERR_UNSUPPORTED) set_error("fft_c2c_chunked: no fused kernel for n_fft=%d inner=%lld", n_fft, (long long)inner);
+    return rc;
+}
+
 int shb_fft_c2c_chunked(int backward, const void *d_in, void *d_out, int64_t outer, int64_t inner, int n_fft,
                         int N, double scale, int flags, int in_chunk_rows, int out_chunk_rows, void *stream) {
     if (!d_in || !d_out || d_in == d_out || outer < 0 || inner < 0 || n_fft < 1 || N < 1 || N > n_fft ||

@@ -63,6 +63,7 @@ int fft_generic_launch(int mode, const void *in, void *out, int64_t outer, int64
 
 // returns SHB_ERR_UNSUPPORTED when no specialised kernel covers the case
 int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner,
-                    int n_fft, int N, double scale, int flags, cudaStream_t st, int in_cr = 0, int out_cr = 0);
+                    int n_fft, int N, double scale, int flags, cudaStream_t st, int in_cr = 0, int out_cr = 0,
+                    void *const *peer_out = nullptr, int npeer = 0);
 
 }  // namespace shb

@@ -135,6 +135,10 @@ struct FastDesc {
     // row r of outer index o lives at (r / cr) * cs + ((o * cr + r % cr) * inner + c); cr == 0: off
     int in_cr, out_cr;
     int64_t in_cs, out_cs;
+    // direct peer stores over NVLink: chunk p of the output goes to out_peer[p] (the receive
+    // buffer of rank p, already offset to the slot of this rank) instead of out + p*out_cs
+    cplx *out_peer[8];
+    int use_peer;
 };
 
 // zero-padding rule of the C2C backward transform as a branch-free gather:
@@ -182,7 +186,9 @@ fft_strided_kernel(const __grid_constant__ FastDesc d) {
     auto out_at = [&](int r) -> cplx & {
         if (CH && d.out_cr) {
             const int p = r / d.out_cr;
-            return outb[p * d.out_cs + ((o * d.out_cr + (r - p * d.out_cr)) * d.inner + cc)];
+            const int64_t off = (o * d.out_cr + (r - p * d.out_cr)) * d.inner + cc;
+            if (d.use_peer) return d.out_peer[p][off];
+            return outb[p * d.out_cs + off];
         }
         return outb[(o * d.n_out + r) * d.inner + cc];
     };
@@ -515,9 +521,12 @@ static int contig_r2c(int M, const FastDesc &d, cudaStream_t st) { SHB_CONTIG_CA
 static int contig_c2r(int M, const FastDesc &d, cudaStream_t st) { SHB_CONTIG_CASES(FFT_C2R) }
 
 int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner,
-                    int n_fft, int N, double scale, int flags, cudaStream_t st, int in_cr, int out_cr) {
+                    int n_fft, int N, double scale, int flags, cudaStream_t st, int in_cr, int out_cr,
+                    void *const *peer_out, int npeer) {
     FastDesc d;
     d.in_cr = in_cr; d.out_cr = out_cr;
+    d.use_peer = (peer_out != nullptr && npeer > 0);
+    for (int p = 0; p < 8; ++p) d.out_peer[p] = (d.use_peer && p < npeer) ? reinterpret_cast<cplx *>(peer_out[p]) : nullptr;
     d.in_cs = (int64_t)outer * in_cr * inner; d.out_cs = (int64_t)outer * out_cr * inner;
     d.in = in; d.out = out; d.outer = outer; d.inner = inner; d.nlines = outer * inner;
     d.n_fft = n_fft; d.N = N; d.flags = flags; d.scale = scale;

@@ -152,15 +152,20 @@ class C2C(FourierBase):
 
     supports_chunked = True    # axis kernels can address the all-to-all send / receive layout
 
-    def _forward_axis(self, u, out, outer, inner, scalar_product=False, in_chunk=0, out_chunk=0):
+    def _forward_axis(self, u, out, outer, inner, scalar_product=False, in_chunk=0, out_chunk=0, peers=None):
         n = self.physical_len()
-        if in_chunk or out_chunk:
+        if peers is not None:
+            ops.fft_c2c_peer(False, u, peers, outer, inner, n, self.N, 1./n, False, in_chunk, out_chunk)
+        elif in_chunk or out_chunk:
             ops.fft_c2c_chunked(False, u, out, outer, inner, n, self.N, 1./n, False, in_chunk, out_chunk)
         else:
             ops.fft_c2c_forward(u, out, outer, inner, n, self.N, 1./n)
 
-    def _backward_axis(self, uh, out, outer, inner, in_chunk=0, out_chunk=0):
-        if in_chunk or out_chunk:
+    def _backward_axis(self, uh, out, outer, inner, in_chunk=0, out_chunk=0, peers=None):
+        if peers is not None:
+            ops.fft_c2c_peer(True, uh, peers, outer, inner, self.physical_len(), self.N, 1.0,
+                             self.dealias_direct, in_chunk, out_chunk)
+        elif in_chunk or out_chunk:
             ops.fft_c2c_chunked(True, uh, out, outer, inner, self.physical_len(), self.N, 1.0,
                                 self.dealias_direct, in_chunk, out_chunk)
         else:

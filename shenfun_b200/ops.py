@@ -63,6 +63,15 @@ def fft_c2c_chunked(backward, u, out, outer, inner, n_fft, N, scale, dealias_dir
           scale, int(dealias_direct), int(in_chunk), int(out_chunk), _lib.stream_ptr())
 
 
+def fft_c2c_peer(backward, u, peer_ptrs, outer, inner, n_fft, N, scale, dealias_direct=False, in_chunk=0,
+                 out_chunk=0):
+    """C2C transform whose output blocks are stored directly into the peers' receive buffers."""
+    import ctypes
+    arr = (ctypes.c_void_p*len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    _call('shb_fft_c2c_peer', int(backward), _req(u, C128, 'in'), arr, len(peer_ptrs), outer, inner, n_fft, N,
+          scale, int(dealias_direct), int(in_chunk), int(out_chunk), _lib.stream_ptr())
+
+
 def fft_r2c_forward(u, out, outer, inner, n_fft, N, scale):
     _call('shb_fft_r2c_forward', _req(u, F64, 'in'), _req(out, C128, 'out'),
           outer, inner, n_fft, N, scale, _lib.stream_ptr())

@@ -120,6 +120,7 @@ class _Transform:
         which = 0
         bwd = self.direction == 'backward'
         cur_packed = False
+        peer_done = None
         for i, s in enumerate(steps):
             full_out_shape = lead + s.out_shape
             # fused all-to-all: the axis kernel before an exchange writes the send layout, the one
@@ -148,8 +149,15 @@ class _Transform:
                     dst = self._pool.get(which, full_out_shape, s.out_dtype, u.device)
                 which ^= 1
             if s.kind == 'exchange':
-                s.exchange(cur, dst, ncomp, self.direction, src_packed=cur_packed,
-                           dst_packed=bool(s.fuse and s.fuse[1]))
+                if peer_done is not None:
+                    # the producer already stored every block into the peers' receive buffers
+                    rbuf, hdl = peer_done
+                    hdl.barrier()
+                    dst = rbuf[:int(np.prod(full_out_shape))].view(full_out_shape)
+                    peer_done = None
+                else:
+                    s.exchange(cur, dst, ncomp, self.direction, src_packed=cur_packed,
+                               dst_packed=bool(s.fuse and s.fuse[1]))
                 cur_packed = False
             else:
                 ax = s.axis
@@ -158,6 +166,18 @@ class _Transform:
                 kw = {}
                 if fused_io:
                     kw = dict(in_chunk=in_chunk, out_chunk=out_chunk)
+                if out_chunk and nxt.fuse[1] and nxt.exchange.peer_available():
+                    try:
+                        numel = int(np.prod(full_out_shape))
+                        rbuf, hdl = nxt.exchange.peer_buffers(numel, u.device)
+                        P_, r_ = nxt.exchange.P, nxt.exchange.rank
+                        slot = (numel//P_)*16*r_
+                        kw['peers'] = [int(p)+slot for p in hdl.buffer_ptrs]
+                        peer_done = (rbuf, hdl)
+                    except Exception:  # noqa: BLE001  (no P2P / symmetric memory on this box)
+                        nxt.exchange._peer_broken = True
+                        kw.pop('peers', None)
+                        peer_done = None
                 if bwd:
                     s.base._backward_axis(cur, dst, outer, inner, **kw)
                 else:

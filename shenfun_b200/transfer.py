@@ -49,6 +49,33 @@ class SlabExchange:
         ax = sa if side == 'send' else ga
         return self.gshape[ax]//self.P
 
+    # ---- direct peer stores (symmetric memory over NVLink) -----------------------------------
+    def peer_available(self):
+        """NCCL backend, equal blocks, <= 8 ranks and torch symmetric memory usable."""
+        import os
+        if os.environ.get('SHB_PEER_EXCHANGE', '1') == '0' or getattr(self, '_peer_broken', False):
+            return False
+        if not (dist.is_initialized() and dist.get_backend(self.comm.group) == 'nccl'):
+            return False
+        return self.uniform() and self.P <= 8
+
+    def peer_buffers(self, numel, device):
+        """Two alternating symmetric receive buffers of `numel` complex128 each: (local tensor,
+        rendezvous handle).  Alternation + one barrier per exchange keeps a rank from overwriting
+        a buffer a peer is still reading."""
+        import torch.distributed._symmetric_memory as symm
+        st = getattr(self, '_peer', None)
+        if st is None or st['numel'] < numel:
+            bufs = []
+            for _ in range(2):
+                t = symm.empty(numel, dtype=torch.complex128, device=device)
+                hdl = symm.rendezvous(t, self.comm.group if self.comm.group is not None else dist.group.WORLD)
+                bufs.append((t, hdl))
+            st = {'numel': numel, 'bufs': bufs, 'turn': 0}
+            self._peer = st
+        st['turn'] ^= 1
+        return st['bufs'][st['turn']]
+
     def uniform(self):
         """Equal blocks on both axes (needed by the fused, kernel-side pack / unpack)."""
         return self.gshape[self.ga] % self.P == 0 and self.gshape[self.sa] % self.P == 0
