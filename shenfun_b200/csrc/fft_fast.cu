@@ -48,7 +48,14 @@ struct Sched {
 // (line butterfly b = j + q*P) has operand m at v[q*R0+m] = x[b + m*NB0].  On
 // return v[q*RL+m] = X[b + m*NBL].  `S` maps a line position to shared memory
 // for this thread's line, `Y` synchronises the threads that share the line.
-template <class SC, bool INV, class S, class Y>
+// w[m] = w1^m for m = 1..R-1 with multiplication depth <= log2(R) (each entry stays within a few ulp)
+template <int R> __device__ __forceinline__ void twiddle_powers(cplx w1, cplx *w) {
+    w[1] = w1;
+#pragma unroll
+    for (int m = 2; m < R; ++m) w[m] = cmul(w[m / 2], w[m - m / 2]);
+}
+
+template <class SC, bool INV, bool CHAIN, class S, class Y>
 __device__ __forceinline__ void fft_stages(cplx *v, const int j, S s, Y sync, const cplx *__restrict__ tw) {
     constexpr int R0 = SC::R0, R1 = SC::R1, R2 = SC::R2, P = SC::P;
     if (j < SC::NB0) {
@@ -70,10 +77,18 @@ __device__ __forceinline__ void fft_stages(cplx *v, const int j, S s, Y sync, co
 #pragma unroll
         for (int q = 0; q < SC::B1; ++q) {
             const int k = (j + q * P) % R0;
+            if constexpr (CHAIN && R1 > 2) {
+                cplx w[R1];
+                twiddle_powers<R1>(__ldg(&tw[k * R2]), w);
 #pragma unroll
-            for (int m = 1; m < R1; ++m) {
-                const cplx w = __ldg(&tw[k * m * R2]);
-                v[q * R1 + m] = INV ? cmulc(v[q * R1 + m], w) : cmul(v[q * R1 + m], w);
+                for (int m = 1; m < R1; ++m)
+                    v[q * R1 + m] = INV ? cmulc(v[q * R1 + m], w[m]) : cmul(v[q * R1 + m], w[m]);
+            } else {
+#pragma unroll
+                for (int m = 1; m < R1; ++m) {
+                    const cplx w = __ldg(&tw[k * m * R2]);
+                    v[q * R1 + m] = INV ? cmulc(v[q * R1 + m], w) : cmul(v[q * R1 + m], w);
+                }
             }
             Bfly<R1, INV>::run(v + q * R1);
         }
@@ -101,14 +116,40 @@ __device__ __forceinline__ void fft_stages(cplx *v, const int j, S s, Y sync, co
 #pragma unroll
             for (int q = 0; q < SC::B2; ++q) {
                 const int b = j + q * P;
+                if constexpr (CHAIN && R2 > 2) {
+                    cplx w[R2];
+                    twiddle_powers<R2>(__ldg(&tw[b]), w);
 #pragma unroll
-                for (int m = 1; m < R2; ++m) {
-                    const cplx w = __ldg(&tw[b * m]);
-                    v[q * R2 + m] = INV ? cmulc(v[q * R2 + m], w) : cmul(v[q * R2 + m], w);
+                    for (int m = 1; m < R2; ++m)
+                        v[q * R2 + m] = INV ? cmulc(v[q * R2 + m], w[m]) : cmul(v[q * R2 + m], w[m]);
+                } else {
+#pragma unroll
+                    for (int m = 1; m < R2; ++m) {
+                        const cplx w = __ldg(&tw[b * m]);
+                        v[q * R2 + m] = INV ? cmulc(v[q * R2 + m], w) : cmul(v[q * R2 + m], w);
+                    }
                 }
                 Bfly<R2, INV>::run(v + q * R2);
             }
         }
+    }
+}
+
+// a * exp(-2 pi i STEP*m/48) for the unrolled loop index m (resolved at compile time after unrolling)
+template <int STEP> __device__ __forceinline__ cplx root48_rt(cplx a, int m) {
+    switch (m) {
+    case 0: return a;
+    case 1: return mul_root48<STEP * 1, false>(a);
+    case 2: return mul_root48<STEP * 2, false>(a);
+    case 3: return mul_root48<STEP * 3, false>(a);
+    case 4: return mul_root48<STEP * 4, false>(a);
+    case 5: return mul_root48<STEP * 5, false>(a);
+    case 6: return mul_root48<STEP * 6, false>(a);
+    case 7: return mul_root48<STEP * 7, false>(a);
+    case 8: return mul_root48<STEP * 8, false>(a);
+    case 9: return mul_root48<STEP * 9, false>(a);
+    case 10: return mul_root48<STEP * 10, false>(a);
+    default: return mul_root48<STEP * 11, false>(a);
     }
 }
 
@@ -217,7 +258,7 @@ fft_strided_kernel(const __grid_constant__ FastDesc d) {
         }
     }
     auto s = [&](int pos) -> cplx & { return sm[pos * T + c]; };
-    fft_stages<SC, INV>(v, j, s, CtaSync(), d.tw);
+    fft_stages<SC, INV, true>(v, j, s, CtaSync(), d.tw);
 
     const double scale = d.scale;
     if (MODE == FFT_C2C_FWD && padded && evenN) {
@@ -252,6 +293,143 @@ fft_strided_kernel(const __grid_constant__ FastDesc d) {
                 }
             }
         }
+    }
+}
+
+// ---- kernel A, software-pipelined variant ------------------------------------------------
+// For the long lines (768 ... 1536) one CTA fills an SM (>= 768 threads, ~100 KB of exchange
+// buffer), so CTAs cannot overlap each other's load / compute / store phases.  This persistent
+// variant overlaps them itself: the stage-0 operands of the NEXT tile are fetched with cp.async
+// (16 B per copy, zero-fill for the padded rows) into a per-thread staging area in shared memory
+// while the current tile is transformed and stored.  Each thread only ever reads the slots it
+// filled, so cp.async.wait_group is the only synchronisation the staging area needs.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool pred) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+
+template <class SC, int MODE, int T, bool CH>
+__global__ void __launch_bounds__(SC::P *T, (SC::P * T <= 512 ? 2 : 1)) fft_strided_pipe_kernel(const __grid_constant__ FastDesc d,
+                                                                       const int64_t ntiles) {
+    constexpr bool INV = (MODE == FFT_C2C_BWD);
+    constexpr int M = SC::M, P = SC::P, E0 = SC::B0 * SC::R0;
+    constexpr int NT = (SC::NB0 < SC::P ? SC::NB0 : SC::P) * T;   // threads that own stage-0 operands
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *sm = reinterpret_cast<cplx *>(smem_raw);          // exchange buffer [M][T]
+    cplx *stg = sm + (size_t)M * T;                         // staging [E0][NT] (= M*T slots)
+    const int c = threadIdx.x % T;
+    const int j = threadIdx.x / T;
+    const cplx *__restrict__ inb = reinterpret_cast<const cplx *>(d.in);
+    cplx *__restrict__ outb = reinterpret_cast<cplx *>(d.out);
+    const int N = d.N;
+    const bool padded = (N < M);
+    const bool evenN = (N % 2 == 0);
+    const int h = N / 2;
+    const PadMap pm(N, M, d.flags);
+    const double scale = d.scale;
+
+    auto issue = [&](int64_t tile) {
+        const int64_t line = tile * T + c;
+        const bool valid = line < d.nlines;
+        const int64_t o = valid ? line / d.inner : 0, cc = valid ? line % d.inner : 0;
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q) {
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int r = (j + q * P) + m * SC::NB0;
+                    bool ok = valid;
+                    int src = r;
+                    double f = 1.0;
+                    if (MODE == FFT_C2C_BWD) ok = pm.map(r, src, f) && valid;
+                    const cplx *g = inb;
+                    if (ok) {
+                        if (CH && d.in_cr) {
+                            const int p = src / d.in_cr;
+                            g = inb + (p * d.in_cs + ((o * d.in_cr + (src - p * d.in_cr)) * d.inner + cc));
+                        } else {
+                            g = inb + ((o * d.n_in + src) * d.inner + cc);
+                        }
+                    }
+                    cp_async16(&stg[(size_t)(q * SC::R0 + m) * NT + threadIdx.x], g, ok);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int64_t tile = blockIdx.x;
+    if (tile < ntiles) issue(tile);
+    while (tile < ntiles) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        cplx v[SC::EMAX];
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q) {
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    cplx x = stg[(size_t)(q * SC::R0 + m) * NT + threadIdx.x];
+                    if (MODE == FFT_C2C_BWD && padded && evenN) {
+                        const int r = (j + q * P) + m * SC::NB0;
+                        if (r == h || r == M - h) x = cscale(x, 0.5);
+                    }
+                    v[q * SC::R0 + m] = x;
+                }
+            }
+        }
+        const int64_t next = tile + gridDim.x;
+        if (next < ntiles) issue(next);
+
+        const int64_t line = tile * T + c;
+        const bool valid = line < d.nlines;
+        const int64_t o = valid ? line / d.inner : 0, cc = valid ? line % d.inner : 0;
+        auto out_at = [&](int r) -> cplx & {
+            if (CH && d.out_cr) {
+                const int p = r / d.out_cr;
+                const int64_t off = (o * d.out_cr + (r - p * d.out_cr)) * d.inner + cc;
+                if (d.use_peer) return d.out_peer[p][off];
+                return outb[p * d.out_cs + off];
+            }
+            return outb[(o * d.n_out + r) * d.inner + cc];
+        };
+        auto s = [&](int pos) -> cplx & { return sm[pos * T + c]; };
+        fft_stages<SC, INV, true>(v, j, s, CtaSync(), d.tw);
+
+        if (MODE == FFT_C2C_FWD && padded && evenN) {
+            __syncthreads();
+            if (j < SC::NBL) {
+#pragma unroll
+                for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                    for (int m = 0; m < SC::RL; ++m)
+                        if ((j + q * P) + m * SC::NBL == M - h) sm[c] = v[q * SC::RL + m];
+            }
+            __syncthreads();
+        }
+        if (j < SC::NBL && valid) {
+#pragma unroll
+            for (int q = 0; q < SC::BL; ++q) {
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m) {
+                    const int r = (j + q * P) + m * SC::NBL;
+                    const cplx x0 = v[q * SC::RL + m];
+                    if (MODE == FFT_C2C_BWD || !padded) {
+                        out_at(r) = cscale(x0, scale);
+                    } else {
+                        if (r <= h) {
+                            cplx x = x0;
+                            if (evenN && r == h) x = cadd(x, sm[c]);
+                            out_at(r) = cscale(x, scale);
+                        } else if (r > M - h || (!evenN && r == M - h)) {
+                            out_at(r - M + N) = cscale(x0, scale);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();     // exchange buffer is reused by the next tile
+        tile = next;
     }
 }
 
@@ -319,35 +497,53 @@ __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_cons
         if (j < SC::NB0) {
 #pragma unroll
             for (int q = 0; q < SC::B0; ++q) {
-                cplx xa[SC::R0], xb[SC::R0];
+                cplx wq = make_double2(1.0, 0.0);
+                // operands are fetched in two batches to bound the live registers (2 x R0/2 pairs)
+                constexpr int HB = (SC::R0 + 1) / 2;
 #pragma unroll
-                for (int m = 0; m < SC::R0; ++m) {
-                    const int n = (j + q * P) + m * SC::NB0;
-                    const int nm = M - n;
-                    xa[m] = (valid && n < ns) ? in[n] : make_double2(0.0, 0.0);
-                    xb[m] = (valid && nm < ns) ? in[nm] : make_double2(0.0, 0.0);
-                }
+                for (int half = 0; half < 2; ++half) {
+                    cplx xa[HB], xb[HB];
 #pragma unroll
-                for (int m = 0; m < SC::R0; ++m) {
-                    const int n = (j + q * P) + m * SC::NB0;
-                    const int nm = M - n;
-                    cplx xk = xa[m], xc = xb[m];
-                    if (dd && n >= N / 3) xk = make_double2(0.0, 0.0);
-                    if (dd && nm >= N / 3) xc = make_double2(0.0, 0.0);
-                    if (padded && evenN && n == ns - 1) xk = make_double2(0.5 * xk.x, 0.0);
-                    if (padded && evenN && nm == ns - 1) xc = make_double2(0.5 * xc.x, 0.0);
-                    if (n == 0) { xk.y = 0.0; xc.y = 0.0; }      // DC and Nyquist (X[M]) are real
-                    xc.y = -xc.y;
-                    const cplx sum = cadd(xk, xc), df = csub(xk, xc);
-                    const cplx w = __ldg(&d.tw2[n]);               // e^{-i pi n / M}
-                    const cplx iw = make_double2(w.y, w.x);        // i * conj(w)
-                    v[q * SC::R0 + m] = cadd(sum, cmul(iw, df));
+                    for (int mm = 0; mm < HB; ++mm) {
+                        const int m = half * HB + mm;
+                        if (m < SC::R0) {
+                            const int n = (j + q * P) + m * SC::NB0;
+                            const int nm = M - n;
+                            xa[mm] = (valid && n < ns) ? in[n] : make_double2(0.0, 0.0);
+                            xb[mm] = (valid && nm < ns) ? in[nm] : make_double2(0.0, 0.0);
+                        }
+                    }
+#pragma unroll
+                    for (int mm = 0; mm < HB; ++mm) {
+                        const int m = half * HB + mm;
+                        if (m < SC::R0) {
+                            const int n = (j + q * P) + m * SC::NB0;
+                            const int nm = M - n;
+                            cplx xk = xa[mm], xc = xb[mm];
+                            if (dd && n >= N / 3) xk = make_double2(0.0, 0.0);
+                            if (dd && nm >= N / 3) xc = make_double2(0.0, 0.0);
+                            if (padded && evenN && n == ns - 1) xk = make_double2(0.5 * xk.x, 0.0);
+                            if (padded && evenN && nm == ns - 1) xc = make_double2(0.5 * xc.x, 0.0);
+                            if (n == 0) { xk.y = 0.0; xc.y = 0.0; }      // DC and Nyquist (X[M]) are real
+                            xc.y = -xc.y;
+                            const cplx sum = cadd(xk, xc), df = csub(xk, xc);
+                            cplx w;                                          // e^{-i pi n / M}
+                            if constexpr (48 % (2 * SC::R0) == 0) {
+                                if (m == 0) wq = __ldg(&d.tw2[j + q * P]);
+                                w = root48_rt<48 / (2 * SC::R0)>(wq, m);
+                            } else {
+                                w = __ldg(&d.tw2[n]);
+                            }
+                            const cplx iw = make_double2(w.y, w.x);        // i * conj(w)
+                            v[q * SC::R0 + m] = cadd(sum, cmul(iw, df));
+                        }
+                    }
                 }
             }
         }
     }
 
-    fft_stages<SC, INV>(v, j, s, sync, d.tw);
+    fft_stages<SC, INV, true>(v, j, s, sync, d.tw);
 
     if (MODE == FFT_C2C_BWD || (MODE == FFT_C2C_FWD && !padded)) {
         cplx *__restrict__ out = reinterpret_cast<cplx *>(d.out) + line * d.n_out;
@@ -403,6 +599,7 @@ __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_cons
             const int ns = h + 1;
 #pragma unroll
             for (int q = 0; q < SC::BL; ++q) {
+                cplx wq = make_double2(1.0, 0.0);
 #pragma unroll
                 for (int m = 0; m < SC::RL; ++m) {
                     const int k = (j + q * P) + m * SC::NBL;
@@ -412,7 +609,13 @@ __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_cons
                         const cplx e = cscale(cadd(zk, zc), 0.5);
                         const cplx df = cscale(csub(zk, zc), 0.5);
                         const cplx o_ = make_double2(df.y, -df.x);
-                        const cplx w = __ldg(&d.tw2[k]);
+                        cplx w;
+                        if constexpr (48 % (2 * SC::RL) == 0) {
+                            if (m == 0) wq = __ldg(&d.tw2[j + q * P]);
+                            w = root48_rt<48 / (2 * SC::RL)>(wq, m);
+                        } else {
+                            w = __ldg(&d.tw2[k]);
+                        }
                         cplx x = cadd(e, cmul(w, o_));
                         if (padded && evenN && k == h) x = make_double2(2.0 * x.x, 0.0);
                         out[k] = cscale(x, scale);
@@ -453,8 +656,38 @@ static int launch_strided_ch(const FastDesc &d, cudaStream_t st) {
     return SHB_OK;
 }
 
+template <class SC, int MODE, int T, bool CH>
+static int launch_strided_pipe(const FastDesc &d, cudaStream_t st) {
+    constexpr size_t smem = 2 * (size_t)SC::M * T * sizeof(cplx);
+    static_assert(smem <= 227 * 1024, "pipelined kernel does not fit in shared memory");
+    static bool attr_set = false;
+    if (!attr_set) {
+        SHB_CUDA(cudaFuncSetAttribute(fft_strided_pipe_kernel<SC, MODE, T, CH>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int64_t ntiles = (d.nlines + T - 1) / T;
+    const int per_sm = (smem <= 110 * 1024 && SC::P * T <= 512) ? 2 : 1;
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    const int64_t grid = ntiles < cap ? ntiles : cap;
+    fft_strided_pipe_kernel<SC, MODE, T, CH><<<(unsigned)grid, SC::P * T, smem, st>>>(d, ntiles);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+static const bool g_no_pipe = getenv("SHB_FFT_NO_PIPE") != nullptr;
+static const bool g_t4 = getenv("SHB_T4") != nullptr;
+
 template <class SC, int MODE, int T>
 static int launch_strided(const FastDesc &d, cudaStream_t st) {
+    // one CTA per SM anyway (>= 768 threads): use the persistent cp.async-pipelined variant
+    constexpr bool big = (SC::P * T > 512) && (2 * (size_t)SC::M * T * sizeof(cplx) <= 227 * 1024);
+    if constexpr (big) {
+        if (!g_no_pipe) {
+            if (d.in_cr || d.out_cr) return launch_strided_pipe<SC, MODE, T, true>(d, st);
+            return launch_strided_pipe<SC, MODE, T, false>(d, st);
+        }
+    }
     if (d.in_cr || d.out_cr) return launch_strided_ch<SC, MODE, T, true>(d, st);
     return launch_strided_ch<SC, MODE, T, false>(d, st);
 }
@@ -489,7 +722,9 @@ static int launch_contig(const FastDesc &d, cudaStream_t st) {
                                 : launch_strided<Sched<192, 4, 8, 6, 48>, MODE, 8>(d, st);          \
     case 384:  return FIRSTWIDE ? launch_strided<Sched<384, 6, 8, 8, 64>, MODE, 8>(d, st)           \
                                 : launch_strided<Sched<384, 8, 8, 6, 64>, MODE, 8>(d, st);          \
-    case 768:  return FIRSTWIDE ? launch_strided<Sched<768, 12, 8, 8, 96>, MODE, 8>(d, st)          \
+    case 768:  if (g_t4) return FIRSTWIDE ? launch_strided_pipe<Sched<768, 12, 8, 8, 96>, MODE, 4, false>(d, st) \
+                                : launch_strided_pipe<Sched<768, 8, 8, 12, 96>, MODE, 4, false>(d, st);         \
+               return FIRSTWIDE ? launch_strided<Sched<768, 12, 8, 8, 96>, MODE, 8>(d, st)          \
                                 : launch_strided<Sched<768, 8, 8, 12, 96>, MODE, 8>(d, st);         \
     case 1536: return FIRSTWIDE ? launch_strided<Sched<1536, 12, 16, 8, 192>, MODE, 4>(d, st)       \
                                 : launch_strided<Sched<1536, 8, 16, 12, 192>, MODE, 4>(d, st);      \
@@ -507,7 +742,7 @@ static int launch_contig(const FastDesc &d, cudaStream_t st) {
     case 1024: return launch_contig<Sched<1024, 16, 8, 8, 128>, MODE, 2>(d, st);                    \
     case 96:   return launch_contig<Sched<96, 12, 8, 1, 32>, MODE, 8>(d, st);                       \
     case 192:  return launch_contig<Sched<192, 6, 8, 4, 64>, MODE, 4>(d, st);                       \
-    case 384:  return launch_contig<Sched<384, 6, 8, 8, 64>, MODE, 4>(d, st);                       \
+    case 384:  return launch_contig<Sched<384, 8, 8, 6, 64>, MODE, 4>(d, st);                       \
     case 768:  return launch_contig<Sched<768, 12, 8, 8, 96>, MODE, 4>(d, st);                      \
     case 576:  return launch_contig<Sched<576, 6, 12, 8, 96>, MODE, 4>(d, st);                      \
     default: return SHB_ERR_UNSUPPORTED;                                                            \
