@@ -1,8 +1,19 @@
 // dct_api.cu -- C ABI for the Chebyshev axis transforms (DCT-II / DCT-III built on
 // the complex FFT core, with scaling and the Shen stencil fused).
 #include "fft_common.cuh"
+#include <stdlib.h>
 
 using namespace shb;
+
+static int dct_dispatch(int mode, const void *in, void *out, int64_t outer, int64_t inner, int n_phys, int n_spec,
+                        double scale, const DctArgs &a, cudaStream_t st) {
+    static const bool force_generic = getenv("SHB_FFT_FORCE_GENERIC") != nullptr;
+    if (!force_generic && in != out) {
+        int rc = dct_fast_launch(mode, in, out, outer, inner, n_phys, n_spec, scale, a, st);
+        if (rc != SHB_ERR_UNSUPPORTED) return rc;
+    }
+    return dct_generic_launch(mode, in, out, outer, inner, n_phys, n_spec, scale, a, st);
+}
 
 static int fill(DctArgs &a, int is_real, int dim, int nsten, const int *soff, const double *const *d_sten,
                 int nbc, const double *d_bc_lift) {
@@ -26,7 +37,7 @@ int shb_cheb_scalar_product(const void *d_in, void *d_out, int64_t outer, int64_
     DctArgs a;
     int rc = fill(a, is_real, dim, nsten, soff, d_sten, 0, nullptr);
     if (rc) return rc;
-    return dct_generic_launch(FFT_DCT2, d_in, d_out, outer, inner, n_phys, n_spec, scale, a,
+    return dct_dispatch(FFT_DCT2, d_in, d_out, outer, inner, n_phys, n_spec, scale, a,
                               reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -39,7 +50,7 @@ int shb_cheb_backward(const void *d_in, void *d_out, int64_t outer, int64_t inne
     DctArgs a;
     int rc = fill(a, is_real, dim, nsten, soff, d_sten, nbc, d_bc_lift);
     if (rc) return rc;
-    return dct_generic_launch(FFT_DCT3, d_in, d_out, outer, inner, n_phys, n_spec, 1.0, a,
+    return dct_dispatch(FFT_DCT3, d_in, d_out, outer, inner, n_phys, n_spec, 1.0, a,
                               reinterpret_cast<cudaStream_t>(stream));
 }
 

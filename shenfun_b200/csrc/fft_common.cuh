@@ -55,6 +55,10 @@ struct DctArgs {
     const double *bc_lift;
 };
 
+// register-resident DCT kernels (strided axes, headline sizes); SHB_ERR_UNSUPPORTED otherwise
+int dct_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner, int n_phys, int n_spec,
+                    double scale, const DctArgs &a, cudaStream_t st);
+
 int dct_generic_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner, int n_phys,
                        int n_spec, double scale, const DctArgs &a, cudaStream_t st);
 

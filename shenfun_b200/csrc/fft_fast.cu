@@ -433,6 +433,258 @@ __global__ void __launch_bounds__(SC::P *T, (SC::P * T <= 512 ? 2 : 1)) fft_stri
     }
 }
 
+// ---- kernel A for the Chebyshev transforms ---------------------------------------------
+// DCT-II / DCT-III of length M on the complex FFT core (one pass for complex data), with the
+// quadrature scaling, the Shen stencil and zero-padding fused:
+//   DCT2 (scalar product):  v[p] = x[2p] | x[2(M-1-p)+1];  V = FFT(v);
+//        S_k = scale (w_k V_k + conj(w_k) V_{M-k}),  w_k = exp(-i pi k / 2M);
+//        out_k = sum_i sten_i[k] S_{k+soff_i}   (k < dim),  0 for dim <= k < n_spec
+//   DCT3 (evaluation):      c_j = sum_i sten_i[j-soff_i] u_{j-soff_i} (+ boundary lift);
+//        U_0 = c_0, U_k = 0.5 w_k (c_k + i c_{M-k});  y = FFT(U);  x[2p] = y[p], x[2p+1] = y[M-1-p]
+// Reference semantics: chebyshev/bases.py:315-353, spectralbase.py:1462-1474, 1616-1634.
+struct DctFastDesc {
+    const void *in;
+    void *out;
+    int64_t outer, inner, nlines;
+    int n_spec, dim, is_real, nsten, nbc;
+    int soff[DCT_MAX_STENCIL];
+    const double *sten[DCT_MAX_STENCIL];
+    const double *bc_lift;
+    double scale;
+    const cplx *tw, *tw3;
+};
+
+template <class SC, int MODE, int T>
+__global__ void __launch_bounds__(SC::P *T, (SC::P * T <= 512 && SC::EMAX <= 8 ? 2 : 1))
+dct_strided_kernel(const __grid_constant__ DctFastDesc d) {
+    constexpr int M = SC::M, P = SC::P;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *sm = reinterpret_cast<cplx *>(smem_raw);
+    const int c = threadIdx.x % T;
+    const int j = threadIdx.x / T;
+    const int64_t line = (int64_t)blockIdx.x * T + c;
+    const bool valid = line < d.nlines;
+    const int64_t o = valid ? line / d.inner : 0, cc = valid ? line % d.inner : 0;
+    const int n_in = (MODE == FFT_DCT2) ? M : d.n_spec;
+    const int n_out = (MODE == FFT_DCT2) ? d.n_spec : M;
+    auto fetch = [&](int r) -> cplx {
+        const int64_t idx = (o * n_in + r) * d.inner + cc;
+        if (d.is_real) return make_double2(reinterpret_cast<const double *>(d.in)[idx], 0.0);
+        return reinterpret_cast<const cplx *>(d.in)[idx];
+    };
+    auto put = [&](int r, cplx x) {
+        const int64_t idx = (o * n_out + r) * d.inner + cc;
+        if (d.is_real) reinterpret_cast<double *>(d.out)[idx] = x.x;
+        else reinterpret_cast<cplx *>(d.out)[idx] = x;
+    };
+    auto s = [&](int pos) -> cplx & { return sm[pos * T + c]; };
+
+    cplx v[SC::EMAX];
+    if (MODE == FFT_DCT2) {
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int pos = (j + q * P) + m * SC::NB0;
+                    const int src = (pos < (M + 1) / 2) ? 2 * pos : 2 * (M - 1 - pos) + 1;
+                    v[q * SC::R0 + m] = valid ? fetch(src) : make_double2(0.0, 0.0);
+                }
+        }
+    } else {
+        // 1. stored coefficients -> shared (rows beyond the dofs / boundary rows are zero)
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int pos = (j + q * P) + m * SC::NB0;
+                    cplx x = make_double2(0.0, 0.0);
+                    if (valid && pos < d.dim + d.nbc && pos < d.n_spec) x = fetch(pos);
+                    s(pos) = x;
+                }
+        }
+        __syncthreads();
+        // 2. c = K^T u (+ boundary lift), kept in registers, then published
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int pos = (j + q * P) + m * SC::NB0;
+                    cplx acc = make_double2(0.0, 0.0);
+                    for (int i = 0; i < d.nsten; ++i) {
+                        const int k = pos - d.soff[i];
+                        if (k >= 0 && k < d.dim) {
+                            const double a = d.sten[i] ? __ldg(&d.sten[i][k]) : 1.0;
+                            const cplx x = s(k);
+                            acc.x = fma(a, x.x, acc.x);
+                            acc.y = fma(a, x.y, acc.y);
+                        }
+                    }
+                    if (d.nbc > 0 && pos < 4) {
+                        for (int b = 0; b < d.nbc; ++b) {
+                            if (d.dim + b >= M) break;
+                            const double a = __ldg(&d.bc_lift[b * 4 + pos]);
+                            const cplx x = s(d.dim + b);
+                            acc.x = fma(a, x.x, acc.x);
+                            acc.y = fma(a, x.y, acc.y);
+                        }
+                    }
+                    v[q * SC::R0 + m] = acc;
+                }
+        }
+        __syncthreads();
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) s((j + q * P) + m * SC::NB0) = v[q * SC::R0 + m];
+        }
+        __syncthreads();
+        // 3. U_0 = c_0, U_k = 0.5 w_k (c_k + i c_{M-k})
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int pos = (j + q * P) + m * SC::NB0;
+                    if (pos > 0) {
+                        const cplx ck = v[q * SC::R0 + m], cm = s(M - pos);
+                        const cplx w = __ldg(&d.tw3[pos]);
+                        const cplx sum = make_double2(ck.x - cm.y, ck.y + cm.x);
+                        v[q * SC::R0 + m] = cscale(cmul(w, sum), 0.5);
+                    }
+                }
+        }
+        __syncthreads();
+    }
+
+    fft_stages<SC, false, true>(v, j, s, CtaSync(), d.tw);
+
+    if (MODE == FFT_DCT3) {
+        if (j < SC::NBL && valid) {
+#pragma unroll
+            for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m) {
+                    const int pos = (j + q * P) + m * SC::NBL;
+                    const int row = (pos < (M + 1) / 2) ? 2 * pos : 2 * (M - 1 - pos) + 1;
+                    put(row, cscale(v[q * SC::RL + m], d.scale));
+                }
+        }
+        return;
+    }
+    // DCT2 epilogue
+    __syncthreads();
+    if (j < SC::NBL) {
+#pragma unroll
+        for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) s((j + q * P) + m * SC::NBL) = v[q * SC::RL + m];
+    }
+    __syncthreads();
+    if (j < SC::NBL) {
+#pragma unroll
+        for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) {
+                const int k = (j + q * P) + m * SC::NBL;
+                const cplx vk = v[q * SC::RL + m], vm = s(k == 0 ? 0 : M - k);
+                const cplx w = __ldg(&d.tw3[k]);
+                v[q * SC::RL + m] = cscale(cadd(cmul(w, vk), cmulc(vm, w)), d.scale);
+            }
+    }
+    const bool plain = (d.nsten == 1 && d.soff[0] == 0 && d.sten[0] == nullptr);
+    if (!plain) {
+        __syncthreads();
+        if (j < SC::NBL) {
+#pragma unroll
+            for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m) s((j + q * P) + m * SC::NBL) = v[q * SC::RL + m];
+        }
+        __syncthreads();
+    }
+    if (j < SC::NBL && valid) {
+#pragma unroll
+        for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) {
+                const int k = (j + q * P) + m * SC::NBL;
+                if (k >= d.n_spec) continue;
+                cplx acc = make_double2(0.0, 0.0);
+                if (k < d.dim) {
+                    if (plain) acc = v[q * SC::RL + m];
+                    else {
+                        for (int i = 0; i < d.nsten; ++i) {
+                            const int jj = k + d.soff[i];
+                            if (jj < M) {
+                                const double a = d.sten[i] ? __ldg(&d.sten[i][k]) : 1.0;
+                                const cplx x = s(jj);
+                                acc.x = fma(a, x.x, acc.x);
+                                acc.y = fma(a, x.y, acc.y);
+                            }
+                        }
+                    }
+                }
+                put(k, acc);
+            }
+    }
+}
+
+template <class SC, int MODE, int T>
+static int launch_dct(const DctFastDesc &d, cudaStream_t st) {
+    constexpr size_t smem = (size_t)SC::M * T * sizeof(cplx);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SHB_CUDA(cudaFuncSetAttribute(dct_strided_kernel<SC, MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        attr_set = true;
+    }
+    const int64_t ntiles = (d.nlines + T - 1) / T;
+    dct_strided_kernel<SC, MODE, T><<<(unsigned)ntiles, SC::P * T, smem, st>>>(d);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+#define SHB_DCT_CASES(MODE)                                                                          \
+    switch (M) {                                                                                     \
+    case 64:   return launch_dct<Sched<64, 8, 8, 1, 8>, MODE, 8>(d, st);                             \
+    case 128:  return launch_dct<Sched<128, 8, 4, 4, 32>, MODE, 8>(d, st);                           \
+    case 256:  return launch_dct<Sched<256, 8, 8, 4, 32>, MODE, 8>(d, st);                           \
+    case 512:  return launch_dct<Sched<512, 8, 8, 8, 64>, MODE, 8>(d, st);                           \
+    case 1024: return launch_dct<Sched<1024, 16, 8, 8, 128>, MODE, 4>(d, st);                        \
+    case 96:   return launch_dct<Sched<96, 8, 12, 1, 12>, MODE, 8>(d, st);                           \
+    case 192:  return launch_dct<Sched<192, 4, 8, 6, 48>, MODE, 8>(d, st);                           \
+    case 384:  return launch_dct<Sched<384, 8, 8, 6, 64>, MODE, 8>(d, st);                           \
+    case 768:  return launch_dct<Sched<768, 8, 8, 12, 96>, MODE, 8>(d, st);                          \
+    case 1536: return launch_dct<Sched<1536, 8, 16, 12, 192>, MODE, 4>(d, st);                       \
+    default: return SHB_ERR_UNSUPPORTED;                                                             \
+    }
+
+static int dct2_fast(int M, const DctFastDesc &d, cudaStream_t st) { SHB_DCT_CASES(FFT_DCT2) }
+static int dct3_fast(int M, const DctFastDesc &d, cudaStream_t st) { SHB_DCT_CASES(FFT_DCT3) }
+
+int dct_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner, int n_phys, int n_spec,
+                    double scale, const DctArgs &a, cudaStream_t st) {
+    if (inner <= 1) return SHB_ERR_UNSUPPORTED;
+    static const int sizes[] = {64, 128, 256, 512, 1024, 96, 192, 384, 768, 1536};
+    bool ok = false;
+    for (int x : sizes) ok = ok || (x == n_phys);
+    if (!ok) return SHB_ERR_UNSUPPORTED;
+    DctFastDesc d;
+    d.in = in; d.out = out; d.outer = outer; d.inner = inner; d.nlines = outer * inner;
+    if (d.nlines == 0) return SHB_OK;
+    d.n_spec = n_spec; d.dim = a.dim; d.is_real = a.is_real; d.nsten = a.nsten; d.nbc = a.nbc;
+    d.bc_lift = a.bc_lift; d.scale = scale;
+    for (int i = 0; i < DCT_MAX_STENCIL; ++i) { d.soff[i] = a.soff[i]; d.sten[i] = a.sten[i]; }
+    d.tw = twiddle_table(0, n_phys);
+    d.tw3 = twiddle_table(2, n_phys);
+    if (!d.tw || !d.tw3) { set_error("dct: twiddle table allocation failed"); return SHB_ERR_NOMEM; }
+    return mode == FFT_DCT2 ? dct2_fast(n_phys, d, st) : dct3_fast(n_phys, d, st);
+}
+
 // ---- kernel B ---------------------------------------------------------------------
 __device__ __forceinline__ int skew(int pos) { return pos + (pos >> 3); }
 

@@ -165,3 +165,40 @@ def test_gemm_axis_shapes():
         sf.ops.gemm_axis(torch.from_numpy(A).cuda(), torch.from_numpy(u).cuda(), out, outer, inner)
         ref = np.einsum('ij,ojc->oic', A, u)
         assert rel_l2(out.cpu().numpy(), ref) < 1e-14
+
+
+@pytest.mark.parametrize('pf', [1.0, 1.5])
+def test_fast_dct_sizes_complex_and_padded(pf):
+    """Sizes served by the register-resident DCT kernels (64..768), plain and 3/2-padded."""
+    rng = np.random.default_rng(8)
+    for N, name in ((64, 'dirichlet'), (128, 'biharmonic'), (256, 'neumann'), (512, 'dirichlet'), (96, 'ortho')):
+        S = sf.FunctionSpace(N, 'C', bc=BCS[name], padding_factor=pf)
+        spec = oracle_spec(S)
+        Np = S.physical_len()
+        u = rng.standard_normal((Np, 3, 7))+1j*rng.standard_normal((Np, 3, 7))
+        out = torch.empty((N, 3, 7), dtype=torch.complex128, device='cuda')
+        S._scalar_product_axis(torch.from_numpy(u).cuda(), out, 1, 21)
+        d = S.dim()
+        assert rel_l2(out.cpu().numpy()[:d], opb.scalar_product_axis(u, 0, spec)[:d]) < TOL, (N, name)
+        assert np.all(out.cpu().numpy()[d:] == 0)
+        vh = rng.standard_normal((N, 3, 7))+1j*rng.standard_normal((N, 3, 7))
+        vh[d:] = 0
+        outp = torch.empty((Np, 3, 7), dtype=torch.complex128, device='cuda')
+        S._backward_axis(torch.from_numpy(vh).cuda(), outp, 1, 21)
+        assert rel_l2(outp.cpu().numpy(), opb.backward_axis(vh, 0, spec)) < TOL, (N, name)
+
+
+def test_all_chebyshev_real_2d():
+    """Real data through the Chebyshev kernels (strided fast path on axis 0, generic on axis 1)."""
+    rng = np.random.default_rng(9)
+    S0 = sf.FunctionSpace(64, 'C', bc=(0, 0))
+    S1 = sf.FunctionSpace(24, 'C', bc=(0, 0, 0, 0))
+    T = sf.TensorProductSpace(sf.comm, (S0, S1))
+    u = rng.standard_normal((64, 24))
+    uh = T.forward(u).get()
+    ref = opb.forward_axis(opb.forward_axis(u, 1, oracle_spec(T.bases[1])), 0, oracle_spec(T.bases[0]))
+    assert uh.dtype == np.float64
+    assert rel_l2(uh, ref) < 1e-11
+    ub = T.backward(sf.Function(T, buffer=ref)).get()
+    refb = opb.backward_axis(opb.backward_axis(ref, 0, oracle_spec(T.bases[0])), 1, oracle_spec(T.bases[1]))
+    assert rel_l2(ub, refb) < TOL
