@@ -55,7 +55,7 @@ class ClockSampler:
              'clocks_event_reasons.sw_power_cap')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -133,7 +133,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
@@ -234,6 +234,14 @@ def main():
     extras = {}
     if world == 1 and not args.no_extras:
         extras = secondary_workloads(T, uh, args, peak)
+    elif not args.no_extras:
+        try:
+            from shenfun_b200.demos import navier_stokes
+            del u, ub
+            torch.cuda.empty_cache()
+            extras['ns'] = navier_stokes.bench(512, steps=max(2, min(args.steps, 5)), warmup=1, comm=comm)
+        except Exception as e:  # noqa: BLE001
+            extras['ns'] = {'error': repr(e)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
