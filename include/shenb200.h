@@ -176,6 +176,21 @@ SHB_API int shb_helmholtz_matvec(const void *d_v, void *d_c, const double *d_A0,
                                  const double *d_B2, const double *d_alfa, const double *d_beta, int64_t outer,
                                  int64_t inner, int n, int n_u, int is_complex, void *stream);
 
+/* Chebyshev-Galerkin biharmonic (a*S + b*A + c*B) on the ShenBiharmonic basis, per-line scales
+ * a, b, c[outer*inner].  d_tab[13][n] holds the diagonals of S (0,+2,+4), the coefficients of its
+ * rank-2 tail, A (-2,0,2) and B (-4..4); d_fac[7][outer][n][inner] receives L1, L2, D, U1, U2 and
+ * the eliminated tail coefficients.  O(n) per line.  Replaces LU_Biharmonic,
+ * Biharmonic_factor_pr, Biharmonic_Solve, Biharmonic_matvec (shenfun/chebyshev/la.py:354-558,
+ * optimization/cython/la.pyx:975-2121, Matvec.pyx:820-922).                                  */
+SHB_API int shb_biharmonic_factor(const double *d_tab, const double *d_a, const double *d_b,
+                                  const double *d_c, double *d_fac, int64_t outer, int64_t inner, int n,
+                                  void *stream);
+SHB_API int shb_biharmonic_solve(const void *d_b, void *d_u, const double *d_fac, int64_t outer,
+                                 int64_t inner, int n, int n_u, int is_complex, void *stream);
+SHB_API int shb_biharmonic_matvec(const void *d_v, void *d_c, const double *d_tab, const double *d_a,
+                                  const double *d_b, const double *d_cs, int64_t outer, int64_t inner,
+                                  int n, int n_u, int is_complex, void *stream);
+
 /* ------------------------------------------------------------------ */
 /* Chebyshev (Gauss-Chebyshev points) axis transforms on [outer][n][inner],
  * real (is_real) or complex data (real and imaginary parts in ONE pass --

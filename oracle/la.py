@@ -136,3 +136,39 @@ def helmholtz_solve(A, B, alfa, beta, b, axis):
     out = np.array(b, dtype=u.dtype)
     out[tuple(sl)] = np.moveaxis(u.reshape(shp), 0, axis)
     return out
+
+
+def biharmonic_solve(S, A, B, a0, alfa, beta, b, axis):
+    """Chebyshev biharmonic (a0 S + alfa A + beta B) u = b.  The reference (la.pyx:975-1308) splits
+    odd/even unknowns, eliminates with two lower diagonals and keeps three upper diagonals plus a
+    rank-2 tail; mathematically this is LU without pivoting of the dense matrix, which is what is
+    restated here per line (dense, O(n^3): small sizes only)."""
+    n = S.shape[0]
+    sl = [slice(None)]*b.ndim
+    sl[axis] = slice(0, n)
+    f = np.moveaxis(b[tuple(sl)], axis, 0)
+    shp = f.shape
+    f = f.reshape(n, -1)
+    line_shape = list(b.shape)
+    line_shape[axis] = 1
+    a = np.broadcast_to(a0, line_shape).reshape(-1).astype(float)
+    al = np.broadcast_to(alfa, line_shape).reshape(-1).astype(float)
+    be = np.broadcast_to(beta, line_shape).reshape(-1).astype(float)
+    out_lines = np.zeros(f.shape, dtype=complex if np.iscomplexobj(f) else float)
+    for l in range(f.shape[1]):
+        H = a[l]*S+al[l]*A+be[l]*B
+        x = f[:, l].astype(out_lines.dtype)
+        # LU without pivoting (Doolittle, natural order)
+        U = H.copy()
+        for i in range(n):
+            for r in range(i+1, min(n, i+5)):
+                if U[r, i] != 0:
+                    m = U[r, i]/U[i, i]
+                    U[r, i:] -= m*U[i, i:]
+                    x[r] -= m*x[i]
+        for i in range(n-1, -1, -1):
+            x[i] = (x[i]-U[i, i+1:] @ x[i+1:])/U[i, i]
+        out_lines[:, l] = x
+    out = np.array(b, dtype=out_lines.dtype)
+    out[tuple(sl)] = np.moveaxis(out_lines.reshape(shp), 0, axis)
+    return out

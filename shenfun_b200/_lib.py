@@ -42,6 +42,9 @@ def _declare(lib):
         'shb_helmholtz_solve': [vp, vp, vp, i64, i64, i32, i32, i32, vp],
         'shb_cheb_scalar_product': [vp, vp, i64, i64, i32, i32, f64, i32, i32, i32, vp, vp, vp],
         'shb_helmholtz_matvec': [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp],
+        'shb_biharmonic_factor': [vp, vp, vp, vp, vp, i64, i64, i32, vp],
+        'shb_biharmonic_solve': [vp, vp, vp, i64, i64, i32, i32, i32, vp],
+        'shb_biharmonic_matvec': [vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp],
         'shb_gemm_axis': [vp, vp, vp, i32, i32, i64, i64, i32, vp],
         'shb_cheb_backward': [vp, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp],
     }

@@ -87,11 +87,11 @@ class Orthogonal(PolyBase):
     def _canonical_stencil(self, st, k):
         kind = self.boundary_condition()
         if kind == 'Dirichlet':
-            return {0: np.ones(len(k)), 2: -np.ones(len(k))}
+            return {0: np.ones(len(k), dtype=k.dtype), 2: -np.ones(len(k), dtype=k.dtype)}
         if kind == 'Neumann':
-            return {0: np.ones(len(k)), 2: -(k/(k+2.0))**2}
+            return {0: np.ones(len(k), dtype=k.dtype), 2: -(k/(k+2.0))**2}
         if kind == 'Biharmonic':
-            return {0: np.ones(len(k)), 2: (-2.0*k-4)/(k+3), 4: (k+1.0)/(k+3)}
+            return {0: np.ones(len(k), dtype=k.dtype), 2: (-2.0*k-4)/(k+3), 4: (k+1.0)/(k+3)}
         return st
 
     # ---- device transforms ---------------------------------------------------------------------

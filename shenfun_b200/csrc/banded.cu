@@ -337,6 +337,155 @@ __global__ void __launch_bounds__(BD_THREADS) helmholtz_matvec_kernel(
     }
 }
 
+// ---- Chebyshev biharmonic ------------------------------------------------------------------
+// H = a*S + b*A + c*B on the Chebyshev ShenBiharmonic basis (chebyshev/la.py:354-558,
+// la.pyx:975-1308): S = (d^4 phi_j / dx^4, phi_k)_w is upper triangular with diagonals 0, +2, +4
+// and a rank-2 tail  S[k, j] = (alpha_k + beta_k (j+2)^2) / (j+3)  for j >= k+6 (same parity);
+// A has offsets -2, 0, 2 and B offsets -4 .. 4.  LU without pivoting keeps that shape: two lower
+// diagonals, three upper diagonals and tail coefficients (FA, FB) that follow the row recurrence,
+// so the factorisation is O(n) per line (the reference eliminates full rows, O(n^2)).
+// Table layout tab[13][n]: S0 S2 S4 alpha beta | A-2 A0 A2 | B-4 B-2 B0 B2 B4  (entry [d][i] = M[i, i+off]).
+// Factor layout fac[7][outer][n][inner]: L1 (vs row i-2), L2 (vs row i-4), D, U1, U2, FA, FB.
+__device__ __forceinline__ double bih_far(double fa, double fb, int j) {
+    const double jp2 = (double)(j + 2);
+    return (fa + fb * jp2 * jp2) / (double)(j + 3);
+}
+
+__global__ void __launch_bounds__(BD_THREADS) biharmonic_factor_kernel(
+    const double *__restrict__ tab, const double *__restrict__ sa, const double *__restrict__ sb,
+    const double *__restrict__ sc, double *__restrict__ fac, int64_t outer, int64_t inner, int n) {
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= outer * inner) return;
+    const int64_t o = line / inner, c = line % inner;
+    const double a = sa[line], b = sb[line], cc = sc[line];
+    const int64_t fs = outer * (int64_t)n * inner;
+    double *f = fac + (o * n) * inner + c;
+    auto T = [&](int d, int i) { return __ldg(&tab[d * n + i]); };
+    for (int par = 0; par < 2; ++par) {
+        // previous two pivot rows of this parity: p1 = row i-2, p2 = row i-4
+        double D1 = 1, U11 = 0, U21 = 0, FA1 = 0, FB1 = 0;
+        double D2 = 1, U12 = 0, U22 = 0, FA2 = 0, FB2 = 0;
+        for (int i = par; i < n; i += 2) {
+            double lo2 = cc * T(8, i);
+            double lo1 = b * T(5, i) + cc * T(9, i);
+            double dg = a * T(0, i) + b * T(6, i) + cc * T(10, i);
+            double up1 = a * T(1, i) + b * T(7, i) + cc * T(11, i);
+            double up2 = a * T(2, i) + cc * T(12, i);
+            double fa = a * T(3, i), fb = a * T(4, i);
+            double l2 = 0.0, l1 = 0.0;
+            if (i - 4 >= 0) {
+                l2 = lo2 / D2;
+                lo1 -= l2 * U12;
+                dg -= l2 * U22;
+                up1 -= l2 * bih_far(FA2, FB2, i + 2);
+                up2 -= l2 * bih_far(FA2, FB2, i + 4);
+                fa -= l2 * FA2;
+                fb -= l2 * FB2;
+            }
+            if (i - 2 >= 0) {
+                l1 = lo1 / D1;
+                dg -= l1 * U11;
+                up1 -= l1 * U21;
+                up2 -= l1 * bih_far(FA1, FB1, i + 4);
+                fa -= l1 * FA1;
+                fb -= l1 * FB1;
+            }
+            const int64_t r = (int64_t)i * inner;
+            f[0 * fs + r] = l1; f[1 * fs + r] = l2; f[2 * fs + r] = dg; f[3 * fs + r] = up1; f[4 * fs + r] = up2;
+            f[5 * fs + r] = fa; f[6 * fs + r] = fb;
+            D2 = D1; U12 = U11; U22 = U21; FA2 = FA1; FB2 = FB1;
+            D1 = dg; U11 = up1; U21 = up2; FA1 = fa; FB1 = fb;
+        }
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(BD_THREADS) biharmonic_solve_kernel(
+    const T *__restrict__ b, T *__restrict__ u, const double *__restrict__ fac, int64_t outer, int64_t inner,
+    int n, int n_u) {
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= outer * inner) return;
+    const int64_t o = line / inner, c = line % inner;
+    const int64_t fs = outer * (int64_t)n * inner;
+    const double *f = fac + (o * n) * inner + c;
+    const T *bl = b + (o * n_u) * inner + c;
+    T *x = u + (o * n_u) * inner + c;
+    for (int par = 0; par < 2; ++par) {
+        T y1 = Num<T>::zero(), y2 = Num<T>::zero();
+        for (int i = par; i < n; i += 2) {
+            const int64_t r = (int64_t)i * inner;
+            T v = bl[r];
+            v = Num<T>::fnma(f[0 * fs + r], y1, v);
+            v = Num<T>::fnma(f[1 * fs + r], y2, v);
+            x[r] = v;
+            y2 = y1; y1 = v;
+        }
+        if (n - 1 - par < 0) continue;
+        const int last = par + ((n - 1 - par) / 2) * 2;
+        T x1 = Num<T>::zero(), x2 = Num<T>::zero(), x3 = Num<T>::zero();   // x_{i+2}, x_{i+4}, x_{i+6}
+        T s1 = Num<T>::zero(), s2 = Num<T>::zero();
+        for (int i = last; i >= par; i -= 2) {
+            const int64_t r = (int64_t)i * inner;
+            // tail sums over j >= i+6: add x_{i+6} (j = i+6)
+            if (i + 6 <= last) {
+                const int j = i + 6;
+                const double w = 1.0 / (double)(j + 3);
+                const double jp2 = (double)(j + 2);
+                s1 = Num<T>::fnma(-w, x3, s1);
+                s2 = Num<T>::fnma(-(w * jp2 * jp2), x3, s2);
+            }
+            T v = x[r];
+            v = Num<T>::fnma(f[3 * fs + r], x1, v);
+            v = Num<T>::fnma(f[4 * fs + r], x2, v);
+            v = Num<T>::fnma(f[5 * fs + r], s1, v);
+            v = Num<T>::fnma(f[6 * fs + r], s2, v);
+            v = Num<T>::div(v, f[2 * fs + r]);
+            x[r] = v;
+            x3 = x2; x2 = x1; x1 = v;
+        }
+    }
+}
+
+// c = (a*S + b*A + c*B) v with the same structure
+template <class T>
+__global__ void __launch_bounds__(BD_THREADS) biharmonic_matvec_kernel(
+    const T *__restrict__ v, T *__restrict__ out, const double *__restrict__ tab, const double *__restrict__ sa,
+    const double *__restrict__ sb, const double *__restrict__ sc, int64_t outer, int64_t inner, int n, int n_u) {
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= outer * inner) return;
+    const int64_t o = line / inner, c = line % inner;
+    const double a = sa[line], b = sb[line], cc = sc[line];
+    const T *x = v + (o * n_u) * inner + c;
+    T *y = out + (o * n_u) * inner + c;
+    auto Tb = [&](int d, int i) { return __ldg(&tab[d * n + i]); };
+    for (int i = n; i < n_u; ++i) y[(int64_t)i * inner] = Num<T>::zero();
+    for (int par = 0; par < 2; ++par) {
+        if (n - 1 - par < 0) continue;
+        const int last = par + ((n - 1 - par) / 2) * 2;
+        T x1 = Num<T>::zero(), x2 = Num<T>::zero(), x3 = Num<T>::zero();
+        T s1 = Num<T>::zero(), s2 = Num<T>::zero();
+        for (int i = last; i >= par; i -= 2) {
+            if (i + 6 <= last) {
+                const int j = i + 6;
+                const double w = 1.0 / (double)(j + 3);
+                const double jp2 = (double)(j + 2);
+                s1 = Num<T>::fnma(-w, x3, s1);
+                s2 = Num<T>::fnma(-(w * jp2 * jp2), x3, s2);
+            }
+            const T xi = x[(int64_t)i * inner];
+            T acc = Num<T>::mul(a * Tb(0, i) + b * Tb(6, i) + cc * Tb(10, i), xi);
+            acc = Num<T>::fnma(-(a * Tb(1, i) + b * Tb(7, i) + cc * Tb(11, i)), x1, acc);
+            acc = Num<T>::fnma(-(a * Tb(2, i) + cc * Tb(12, i)), x2, acc);
+            acc = Num<T>::fnma(-(a * Tb(3, i)), s1, acc);
+            acc = Num<T>::fnma(-(a * Tb(4, i)), s2, acc);
+            if (i - 2 >= 0) acc = Num<T>::fnma(-(b * Tb(5, i) + cc * Tb(9, i)), x[(int64_t)(i - 2) * inner], acc);
+            if (i - 4 >= 0) acc = Num<T>::fnma(-(cc * Tb(8, i)), x[(int64_t)(i - 4) * inner], acc);
+            y[(int64_t)i * inner] = acc;
+            x3 = x2; x2 = x1; x1 = xi;
+        }
+    }
+}
+
 static inline unsigned bd_blocks(int64_t nlines) { return (unsigned)((nlines + BD_THREADS - 1) / BD_THREADS); }
 
 template <int KL, int KU>
@@ -469,6 +618,47 @@ int shb_helmholtz_matvec(const void *d_v, void *d_c, const double *d_A0, const d
     else
         helmholtz_matvec_kernel<double><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
             (const double *)d_v, (double *)d_c, d_A0, d_A2, d_A4, d_Bm2, d_B0, d_B2, d_alfa, d_beta, outer, inner, n, n_u);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_biharmonic_factor(const double *d_tab, const double *d_a, const double *d_b, const double *d_c,
+                          double *d_fac, int64_t outer, int64_t inner, int n, void *stream) {
+    SHB_REQUIRE(d_tab && d_a && d_b && d_c && d_fac && n >= 1, "bad arguments");
+    if (outer * inner == 0) return SHB_OK;
+    biharmonic_factor_kernel<<<bd_blocks(outer * inner), BD_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        d_tab, d_a, d_b, d_c, d_fac, outer, inner, n);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_biharmonic_solve(const void *d_b, void *d_u, const double *d_fac, int64_t outer, int64_t inner, int n,
+                         int n_u, int is_complex, void *stream) {
+    SHB_REQUIRE(d_b && d_u && d_fac && n >= 1 && n_u >= n, "bad arguments");
+    if (outer * inner == 0) return SHB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (is_complex)
+        biharmonic_solve_kernel<cplx><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (const cplx *)d_b, (cplx *)d_u, d_fac, outer, inner, n, n_u);
+    else
+        biharmonic_solve_kernel<double><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (const double *)d_b, (double *)d_u, d_fac, outer, inner, n, n_u);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_biharmonic_matvec(const void *d_v, void *d_c, const double *d_tab, const double *d_a, const double *d_b,
+                          const double *d_cs, int64_t outer, int64_t inner, int n, int n_u, int is_complex,
+                          void *stream) {
+    SHB_REQUIRE(d_v && d_c && d_v != d_c && d_tab && d_a && d_b && d_cs && n >= 1 && n_u >= n, "bad arguments");
+    if (outer * inner == 0) return SHB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (is_complex)
+        biharmonic_matvec_kernel<cplx><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (const cplx *)d_v, (cplx *)d_c, d_tab, d_a, d_b, d_cs, outer, inner, n, n_u);
+    else
+        biharmonic_matvec_kernel<double><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (const double *)d_v, (double *)d_c, d_tab, d_a, d_b, d_cs, outer, inner, n, n_u);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }

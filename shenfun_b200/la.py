@@ -16,7 +16,7 @@ import torch
 from .matrices import SparseMatrix, TPMatrix, get_simplified_tpmatrices
 from . import ops
 
-__all__ = ('BandedFactor', 'TDMA', 'TDMA_O', 'PDMA', 'FDMA', 'TwoDMA', 'ThreeDMA', 'HeptaDMA', 'DiagMA',
+__all__ = ('Biharmonic', 'BandedFactor', 'TDMA', 'TDMA_O', 'PDMA', 'FDMA', 'TwoDMA', 'ThreeDMA', 'HeptaDMA', 'DiagMA',
            'Solve', 'Solver', 'SolverGeneric1ND', 'SolverDiagonal', 'Helmholtz', 'tp_matvec')
 
 
@@ -417,6 +417,80 @@ class Helmholtz:
         ops.helmholtz_solve(bt, ut, self.fac, op.outer, op.inner, op.n_rows, op.n_u)
         if hasattr(u, 'set_boundary_dofs'):
             u.set_boundary_dofs()
+        return u
+
+
+class Biharmonic:
+    """Chebyshev-Galerkin biharmonic solver a0*S + alfa*A + beta*B on the ShenBiharmonic basis
+    (chebyshev/la.py:354-558).  The three 1-D matrices are recognised by their shape: S (fourth
+    derivative) is upper triangular with a rank-2 tail, A has offsets (-2, 0, 2), B (-4 .. 4)."""
+
+    def __init__(self, *args):
+        if len(args) == 1:
+            args = args[0]
+        mats = list(args)
+        assert all(isinstance(m, TPMatrix) for m in mats)
+        op = _LineOperator(mats)
+        assert len(op.mats1d) == 3, 'Biharmonic needs S, A and B'
+        self.op = op
+        self.T = op.space
+        self.tpmats = mats
+        base = self.T.bases[op.axis]
+        assert base.family() == 'chebyshev' and base.boundary_condition() == 'Biharmonic', \
+            'Biharmonic: Chebyshev ShenBiharmonic basis only'
+        order = sorted(range(3), key=lambda i: (max(op.mats1d[i].keys()), -min(op.mats1d[i].keys())))
+        iA, iB, iS = order      # A: max offset 2, B: 4, S: widest
+        S, A, B = op.mats1d[iS], op.mats1d[iA], op.mats1d[iB]
+        assert set(A.keys()) <= {-2, 0, 2} and set(B.keys()) <= {-4, -2, 0, 2, 4} and max(S.keys()) > 4
+        self.a0, self.alfa, self.beta = op.scales[iS], op.scales[iA], op.scales[iB]
+        n = op.n_rows
+        k = np.arange(n, dtype=float)
+        tab = np.zeros((13, n))
+
+        def put(row, m, off):
+            if off in m:
+                d = np.real(m[off])*np.real(m.scale)
+                if off >= 0:
+                    tab[row, :len(d)] = d
+                else:
+                    tab[row, -off:-off+len(d)] = d
+        put(0, S, 0)
+        put(1, S, 2)
+        put(2, S, 4)
+        # rank-2 tail of S (chebyshev/matrices.py SSBSBmat; la.pyx:1218-1236):
+        # S[k, j] = (alpha_k + beta_k (j+2)^2)/(j+3), j >= k+6
+        sS = float(np.real(S.scale))
+        tab[3] = 8*np.pi*k*(k+1)*(k+2)*(k+4)*sS
+        tab[4] = 24*np.pi*(k+1)*(k+2)*sS
+        for off in S.keys():
+            if off >= 6:
+                j = np.arange(len(S[off]))+off
+                ref = (tab[3, :len(j)]+tab[4, :len(j)]*(j+2.0)**2)/(j+3.0)
+                assert np.allclose(S[off]*sS, ref, rtol=1e-10), 'S does not have the expected tail'
+        put(5, A, -2)
+        put(6, A, 0)
+        put(7, A, 2)
+        put(8, B, -4)
+        put(9, B, -2)
+        put(10, B, 0)
+        put(11, B, 2)
+        put(12, B, 4)
+        self._tab = ops.as_device_tensor(tab)
+        self.fac = torch.empty((7, op.outer, n, op.inner), dtype=torch.float64, device=self._tab.device)
+        ops.biharmonic_factor(self._tab, self.a0, self.alfa, self.beta, self.fac, op.outer, op.inner, n)
+
+    def matvec(self, v, c):
+        op = self.op
+        ops.biharmonic_matvec(ops.plain(v), ops.plain(c), self._tab, self.a0, self.alfa, self.beta, op.outer,
+                              op.inner, op.n_rows, op.n_u)
+        return c
+
+    def __call__(self, b, u=None, constraints=()):
+        op = self.op
+        bt = ops.as_device_tensor(b)
+        if u is None:
+            u = b
+        ops.biharmonic_solve(bt, ops.plain(u), self.fac, op.outer, op.inner, op.n_rows, op.n_u)
         return u
 
 

@@ -125,11 +125,11 @@ class Orthogonal(PolyBase):
     def _canonical_stencil(self, st, k):
         kind = self.boundary_condition()
         if kind == 'Dirichlet':
-            return {0: np.ones(len(k)), 2: -np.ones(len(k))}
+            return {0: np.ones(len(k), dtype=k.dtype), 2: -np.ones(len(k), dtype=k.dtype)}
         if kind == 'Neumann':
-            return {0: np.ones(len(k)), 2: -k*(k+1.0)/(k**2+5.0*k+6)}
+            return {0: np.ones(len(k), dtype=k.dtype), 2: -k*(k+1.0)/(k**2+5.0*k+6)}
         if kind == 'Biharmonic':
-            return {0: np.ones(len(k)), 2: (-4.0*k-10)/(2*k+7), 4: (2.0*k+3)/(2*k+7)}
+            return {0: np.ones(len(k), dtype=k.dtype), 2: (-4.0*k-10)/(2*k+7), 4: (2.0*k+3)/(2*k+7)}
         return st
 
     # ---- operator matrices of the two contractions -----------------------------------------------

@@ -202,3 +202,21 @@ def helmholtz_matvec(v, c, tabs, alfa, beta, outer, inner, n, n_u):
     _call('shb_helmholtz_matvec', _req(v, v.dtype, 'v'), _req(c, c.dtype, 'c'), *[_req(t, F64, 'table') for t in tabs],
           _req(alfa, F64, 'alfa'), _req(beta, F64, 'beta'), outer, inner, n, n_u, int(v.dtype.is_complex),
           _lib.stream_ptr())
+
+
+def biharmonic_factor(tab, a, b, c, fac, outer, inner, n):
+    _call('shb_biharmonic_factor', *[_req(t, F64, 'table') for t in (tab, a, b, c)], _req(fac, F64, 'fac'),
+          outer, inner, n, _lib.stream_ptr())
+
+
+def biharmonic_solve(b, u, fac, outer, inner, n, n_u):
+    assert b.dtype == u.dtype
+    _call('shb_biharmonic_solve', _req(b, b.dtype, 'b'), _req(u, u.dtype, 'u'), _req(fac, F64, 'fac'), outer, inner,
+          n, n_u, int(u.dtype.is_complex), _lib.stream_ptr())
+
+
+def biharmonic_matvec(v, c, tab, sa, sb, sc, outer, inner, n, n_u):
+    assert v.dtype == c.dtype
+    _call('shb_biharmonic_matvec', _req(v, v.dtype, 'v'), _req(c, c.dtype, 'c'),
+          *[_req(t, F64, 'table') for t in (tab, sa, sb, sc)], outer, inner, n, n_u, int(v.dtype.is_complex),
+          _lib.stream_ptr())

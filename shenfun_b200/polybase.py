@@ -182,6 +182,22 @@ class PolyBase(SpectralBase):
         last bit, like the reference's sympy expressions)."""
         return st
 
+    def stencil_ld(self):
+        """Stencil in extended precision for matrix assembly: the closed forms evaluated in long
+        double where the family knows them (the recombination K G K^T cancels O(N^7) entries of
+        the 4th-derivative Gram matrix, so 1e-16 errors in K would show up as 1e-11 in the
+        matrix); otherwise the float64 stencil."""
+        ld = np.longdouble
+        st = self.stencil()
+        k = np.arange(self.dim(), dtype=ld)
+        stl = self._canonical_stencil({o: np.asarray(v, dtype=ld) for o, v in st.items()}, k)
+        out = {}
+        for o in st:
+            v = np.asarray(stl.get(o, st[o]), dtype=ld)
+            # keep only closed forms that agree with the float64 stencil (sanity)
+            out[o] = v if np.allclose(np.asarray(v, dtype=float), st[o], rtol=1e-14, atol=1e-15) else np.asarray(st[o], dtype=ld)
+        return out
+
     def _stencil_scaling(self, k):
         return np.ones(len(k))
 
@@ -272,10 +288,10 @@ class PolyBase(SpectralBase):
         G, fac = self.ortho_gram(N, d_test, d_trial)
         dim_t, dim_u = self.dim(), trial.dim()
         X = np.zeros((dim_t, N), dtype=ld)
-        for off, v in self.stencil().items():
+        for off, v in self.stencil_ld().items():
             X += np.asarray(v, dtype=ld)[:, None]*G[off:off+dim_t, :]
         A = np.zeros((dim_t, dim_u), dtype=ld)
-        for off, v in trial.stencil().items():
+        for off, v in trial.stencil_ld().items():
             A += X[:, off:off+dim_u]*np.asarray(v, dtype=ld)[None, :]
         A = np.asarray(A*fac, dtype=float)
         scale = 1.0

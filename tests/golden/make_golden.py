@@ -287,6 +287,23 @@ def solvers():
     H = la.SolverGeneric1ND(mats)
     out['biharm_f'] = np.array(f_hat)
     out['biharm_u'] = np.array(H(f_hat.copy(), sf.Function(T)))
+    # --- Chebyshev biharmonic solver (chebyshev/la.py:354-558, tests/test_matrices.py:625-658)
+    from shenfun.chebyshev.la import Biharmonic
+    SB = sf.FunctionSpace(16, 'C', bc=(0, 0, 0, 0))
+    K1 = sf.FunctionSpace(12, 'F', dtype='D')
+    K2 = sf.FunctionSpace(10, 'F', dtype='d')
+    T = sf.TensorProductSpace(sf.comm, (SB, K1, K2))
+    u = TrialFunction(T)
+    v = TestFunction(T)
+    mats = inner(v, div(grad(div(grad(u)))))
+    H = Biharmonic(*mats)
+    f_hat = sf.Function(T)
+    f_hat[:] = rng.standard_normal(T.shape(True))+1j*rng.standard_normal(T.shape(True))
+    f_hat[SB.dim():] = 0
+    out['cheb_biharm_f'] = np.array(f_hat)
+    u_hat = H(f_hat.copy(), sf.Function(T))
+    out['cheb_biharm_u'] = np.array(u_hat)
+    out['cheb_biharm_matvec'] = np.array(H.matvec(u_hat, sf.Function(T)))
     save('solvers', **out)
 
 

@@ -202,3 +202,35 @@ def test_all_chebyshev_real_2d():
     ub = T.backward(sf.Function(T, buffer=ref)).get()
     refb = opb.backward_axis(opb.backward_axis(ref, 0, oracle_spec(T.bases[0])), 1, oracle_spec(T.bases[1]))
     assert rel_l2(ub, refb) < TOL
+
+
+def test_chebyshev_biharmonic_solver_golden():
+    """chebyshev.la.Biharmonic (a18): device LU with the rank-2 tail vs the reference's solver."""
+    g = load_golden('solvers')
+    SB = sf.FunctionSpace(16, 'C', bc=(0, 0, 0, 0))
+    T = sf.TensorProductSpace(sf.comm, (SB, sf.FunctionSpace(12, 'F', dtype='D'), sf.FunctionSpace(10, 'F', dtype='d')))
+    u, v = sf.TrialFunction(T), sf.TestFunction(T)
+    H = la.Biharmonic(sf.inner(v, sf.div(sf.grad(sf.div(sf.grad(u))))))
+    f_hat = sf.Function(T, buffer=g['cheb_biharm_f'])
+    u_hat = H(f_hat, sf.Function(T))
+    # two LU orders of a system with condition number ~1e10 (fourth-derivative matrix, N=16..):
+    # agreement is bounded by cond*eps, the residual by eps
+    assert rel_l2(u_hat.get(), g['cheb_biharm_u']) < 1e-9
+    c = H.matvec(u_hat, sf.Function(T))
+    d = SB.dim()
+    assert rel_l2(c.get()[:d], g['cheb_biharm_f'][:d]) < 1e-11
+    cref = H.matvec(sf.Function(T, buffer=g['cheb_biharm_u']), sf.Function(T))
+    assert rel_l2(cref.get(), g['cheb_biharm_matvec']) < 1e-11
+
+
+def test_chebyshev_biharmonic_larger_residual():
+    rng = np.random.default_rng(4)
+    SB = sf.FunctionSpace(128, 'C', bc=(0, 0, 0, 0))
+    T = sf.TensorProductSpace(sf.comm, (SB, sf.FunctionSpace(16, 'F', dtype='D'), sf.FunctionSpace(12, 'F', dtype='d')))
+    u, v = sf.TrialFunction(T), sf.TestFunction(T)
+    H = la.Biharmonic(sf.inner(v, sf.div(sf.grad(sf.div(sf.grad(u))))))
+    f = rng.standard_normal(T.shape(True))+1j*rng.standard_normal(T.shape(True))
+    f[SB.dim():] = 0
+    x = H(sf.Function(T, buffer=f), sf.Function(T))
+    c = H.matvec(x, sf.Function(T))
+    assert rel_l2(c.get()[:SB.dim()], f[:SB.dim()]) < 1e-10

@@ -77,3 +77,17 @@ def test_oracle_generic_1nd_and_helmholtz():
     A, B, k1, k2 = _poisson_mats('C')
     u = ola.helmholtz_solve(A, B, np.ones((1, 1, 1)), -(k1**2+k2**2)-2.5, g['poisson_cheb_f'], 0)
     assert rel_l2(u, g['helm_cheb_u']) < 1e-12
+
+
+def test_oracle_chebyshev_biharmonic():
+    g = load_golden('solvers')
+    SB = sf.FunctionSpace(16, 'C', bc=(0, 0, 0, 0))
+    S = SB.spectral_matrix(0, 4).diags()
+    A = SB.spectral_matrix(0, 2).diags()
+    B = SB.mass_matrix().diags()
+    k1 = np.fft.fftfreq(12, 1./12)[None, :, None]
+    k2 = np.fft.rfftfreq(10, 1./10)[None, None, :]
+    kk = k1**2+k2**2
+    u = ola.biharmonic_solve(S, A, B, np.ones((1, 1, 1)), -2*kk, kk**2, g['cheb_biharm_f'], 0)
+    # LU of a matrix with condition number ~1e10 in two elimination orders: compare to cond*eps
+    assert rel_l2(u, g['cheb_biharm_u']) < 1e-9
