@@ -5,9 +5,9 @@
 //
 // The data array is viewed as real with W = inner * (complex ? 2 : 1) contiguous
 // columns, so one kernel serves real and complex fields (A is real).  Each CTA owns a
-// 64 x 64 output tile of one outer index and walks K in chunks of 16 through a
-// double-buffered shared-memory pipeline; 8 warps each hold a 32 x 16 sub-tile as
-// 4 x 2 m8n8k4 DMMA accumulators (mma.sync f64 -- tcgen05 has no fp64 kind).
+// 128 x 64 output tile of one outer index and walks K in chunks of 32 through a two-stage
+// cp.async shared-memory pipeline; 8 warps each hold a 32 x 32 sub-tile as 4 x 4 m8n8k4 DMMA
+// accumulators (mma.sync f64 -- tcgen05 has no fp64 kind).
 //
 // Reference semantics restated: shenfun/spectralbase.py:473-483 (evaluate_expansion_all,
 // 'vandermonde': np.dot(P, u_hat) along the axis) and :539-548 (scalar product).
@@ -15,9 +15,11 @@
 
 namespace shb {
 
-constexpr int GM_BM = 64, GM_BN = 64, GM_BK = 16, GM_THREADS = 256;
-constexpr int GM_APAD = 4;    // A tile stored [BM][BK+4]  (conflict-free fragment reads)
-constexpr int GM_XPAD = 8;    // X tile stored [BK][BN+8]
+constexpr int GM_BM = 128, GM_BN = 64, GM_BK = 32, GM_THREADS = 256;
+constexpr int GM_AS = GM_BK + 4;     // A tile row pitch (doubles): pitch % 16 == 4 -> conflict-free fragments
+constexpr int GM_XS = GM_BN + 8;     // X tile row pitch: pitch % 16 == 8
+constexpr int GM_STAGES = 2;
+constexpr size_t GM_SMEM = GM_STAGES * ((size_t)GM_BM * GM_AS + (size_t)GM_BK * GM_XS) * sizeof(double);
 
 struct GemmDesc {
     const double *A;       // [M][K] row-major
@@ -36,64 +38,85 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(GM_THREADS) gemm_axis_kernel(const __grid_constant__ GemmDesc d) {
-    __shared__ double sA[2][GM_BM][GM_BK + GM_APAD];
-    __shared__ double sX[2][GM_BK][GM_BN + GM_XPAD];
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool pred) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+
+// CTA tile 128 x 64, K chunks of 32 through a two-stage cp.async pipeline; 8 warps (4 x 2), each
+// holding a 32 x 32 sub-tile as 4 x 4 m8n8k4 DMMA accumulators (16 DMMA per 8 fragment loads).
+__global__ void __launch_bounds__(GM_THREADS, 2) gemm_axis_kernel(const __grid_constant__ GemmDesc d) {
+    extern __shared__ __align__(16) unsigned char gm_smem[];
+    double *sA = reinterpret_cast<double *>(gm_smem);                       // [stage][BM][AS]
+    double *sX = sA + (size_t)GM_STAGES * GM_BM * GM_AS;                    // [stage][BK][XS]
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 2;          // 0..1 : 32 rows each
-    const int wn = warp & 3;           // 0..3 : 16 cols each
+    const int wm = warp >> 1;          // 0..3 : 32 rows each
+    const int wn = warp & 1;           // 0..1 : 32 cols each
     const int64_t w0 = (int64_t)blockIdx.x * GM_BN;
     const int m0 = blockIdx.y * GM_BM;
     const int64_t batch = blockIdx.z;
     const double *X = d.X + batch * d.xs_batch;
     double *C = d.C + batch * d.cs_batch;
 
-    double acc[4][2][2];
+    double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const bool w_fast = (d.xs_w == 1);
     auto load_tiles = [&](int buf, int k0) {
-        // A tile: 64 x 16 = 1024 elements, 4 per thread, k fastest (A row-major)
+        double *a = sA + (size_t)buf * GM_BM * GM_AS;
+        double *x = sX + (size_t)buf * GM_BK * GM_XS;
+        // A tile: 128 x 32 doubles, 16 per thread, k fastest (A is row-major)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < (GM_BM * GM_BK) / GM_THREADS; ++r) {
             const int e = tid + r * GM_THREADS;
             const int kk = e % GM_BK, mm = e / GM_BK;
             const int gm = m0 + mm, gk = k0 + kk;
-            sA[buf][mm][kk] = (gm < d.M && gk < d.K) ? __ldg(&d.A[(int64_t)gm * d.K + gk]) : 0.0;
+            const bool ok = (gm < d.M && gk < d.K);
+            cp_async8(&a[mm * GM_AS + kk], ok ? &d.A[(int64_t)gm * d.K + gk] : d.A, ok);
         }
-        // X tile: 16 x 64 elements, 4 per thread; fastest index follows the unit stride
+        // X tile: 32 x 64 doubles, 8 per thread; fastest index follows the unit stride
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < (GM_BK * GM_BN) / GM_THREADS; ++r) {
             const int e = tid + r * GM_THREADS;
             int kk, ww;
             if (w_fast) { ww = e % GM_BN; kk = e / GM_BN; } else { kk = e % GM_BK; ww = e / GM_BK; }
             const int gk = k0 + kk;
             const int64_t gw = w0 + ww;
-            sX[buf][kk][ww] = (gk < d.K && gw < d.W) ? X[(int64_t)gk * d.xs_k + gw * d.xs_w] : 0.0;
+            const bool ok = (gk < d.K && gw < d.W);
+            cp_async8(&x[kk * GM_XS + ww], ok ? &X[(int64_t)gk * d.xs_k + gw * d.xs_w] : X, ok);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     const int nk = (d.K + GM_BK - 1) / GM_BK;
     load_tiles(0, 0);
-    __syncthreads();
     for (int kt = 0; kt < nk; ++kt) {
         const int buf = kt & 1;
-        if (kt + 1 < nk) load_tiles(buf ^ 1, (kt + 1) * GM_BK);
+        if (kt + 1 < nk) {
+            load_tiles(buf ^ 1, (kt + 1) * GM_BK);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double *a = sA + (size_t)buf * GM_BM * GM_AS;
+        const double *x = sX + (size_t)buf * GM_BK * GM_XS;
 #pragma unroll
         for (int ks = 0; ks < GM_BK; ks += 4) {
-            double a[4], b[2];
+            double af[4], bf[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = sA[buf][wm * 32 + i * 8 + (lane >> 2)][ks + (lane & 3)];
+            for (int i = 0; i < 4; ++i) af[i] = a[(wm * 32 + i * 8 + (lane >> 2)) * GM_AS + ks + (lane & 3)];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) b[j] = sX[buf][ks + (lane & 3)][wn * 16 + j * 8 + (lane >> 2)];
+            for (int j = 0; j < 4; ++j) bf[j] = x[(ks + (lane & 3)) * GM_XS + wn * 32 + j * 8 + (lane >> 2)];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
         __syncthreads();
     }
@@ -103,10 +126,15 @@ __global__ void __launch_bounds__(GM_THREADS) gemm_axis_kernel(const __grid_cons
         const int gm = m0 + wm * 32 + i * 8 + (lane >> 2);
         if (gm >= d.M) continue;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int64_t gw = w0 + wn * 16 + j * 8 + (lane & 3) * 2;
-            if (gw < d.W) C[(int64_t)gm * d.cs_m + gw * d.cs_w] = acc[i][j][0];
-            if (gw + 1 < d.W) C[(int64_t)gm * d.cs_m + (gw + 1) * d.cs_w] = acc[i][j][1];
+        for (int j = 0; j < 4; ++j) {
+            const int64_t gw = w0 + wn * 32 + j * 8 + (lane & 3) * 2;
+            if (d.cs_w == 1 && gw + 1 < d.W && ((((int64_t)gm * d.cs_m + gw) & 1) == 0) &&
+                ((reinterpret_cast<uintptr_t>(C) & 15) == 0)) {
+                *reinterpret_cast<double2 *>(&C[(int64_t)gm * d.cs_m + gw]) = make_double2(acc[i][j][0], acc[i][j][1]);
+            } else {
+                if (gw < d.W) C[(int64_t)gm * d.cs_m + gw * d.cs_w] = acc[i][j][0];
+                if (gw + 1 < d.W) C[(int64_t)gm * d.cs_m + (gw + 1) * d.cs_w] = acc[i][j][1];
+            }
         }
     }
 }
@@ -136,8 +164,13 @@ int shb_gemm_axis(const double *d_A, const void *d_u, void *d_out, int M, int K,
         d.cs_batch = 0; d.cs_m = 1; d.cs_w = M;
     }
     if (d.nbatch > 65535) { set_error("gemm_axis: outer extent %lld too large", (long long)d.nbatch); return SHB_ERR_UNSUPPORTED; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SHB_CUDA(cudaFuncSetAttribute(gemm_axis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM));
+        attr_set = true;
+    }
     dim3 grid((unsigned)((d.W + GM_BN - 1) / GM_BN), (unsigned)((M + GM_BM - 1) / GM_BM), (unsigned)d.nbatch);
-    gemm_axis_kernel<<<grid, GM_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d);
+    gemm_axis_kernel<<<grid, GM_THREADS, GM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(d);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }

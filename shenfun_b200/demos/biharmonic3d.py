@@ -74,6 +74,13 @@ def bench(n=256, family='L', reps=5):
     ms_fwd = t(lambda: T.forward(u, f_hat))
     ms_solve = t(lambda: H(f_hat, u_hat))
     ms_chain = t(lambda: T.backward(H(T.scalar_product(u, f_hat), u_hat), u))
+    # denominator for the FP64 tensor-pipe utilisation: a library DGEMM measured on the same device
+    a = torch.randn(4096, 4096, dtype=torch.float64, device='cuda')
+    bm = torch.randn(4096, 4096, dtype=torch.float64, device='cuda')
+    ms_ref = t(lambda: torch.matmul(a, bm))
+    dgemm_peak = 2*4096.0**3/ms_ref/1e9
+    del a, bm
     return {'workload': f'{family} ShenBiharmonic x Fourier^2 {n}^3', 'legendre_stage_ms': ms_gemm,
-            'legendre_stage_tflops': flops/ms_gemm/1e9, 'forward_ms': ms_fwd, 'solve_ms': ms_solve,
+            'legendre_stage_tflops': flops/ms_gemm/1e9, 'cublas_dgemm_4096_tflops': dgemm_peak,
+            'legendre_stage_frac_of_dgemm_peak': flops/ms_gemm/1e9/dgemm_peak, 'forward_ms': ms_fwd, 'solve_ms': ms_solve,
             'scalar_product_solve_backward_ms': ms_chain}
