@@ -115,7 +115,7 @@ SHB_API int shb_curl_hat(const void *d_u, void *d_out, const double *d_k0, const
 /* One Runge-Kutta stage of the triply periodic Navier-Stokes demo, fused:
  * pressure solve + gradient (demo/NavierStokes.py:41-43), viscous term and
  * the RK4 stage update (shenfun/utilities/integrators.py:590-598).
- * d_P may be NULL.                                                          */
+ * d_P may be NULL.  `last` bit 0: final stage (u_hat <- U1); bit 1: do not write dU back. */
 SHB_API int shb_ns_rk_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, void *d_P,
                             const double *d_k0, const double *d_k1, const double *d_k2,
                             int n0, int n1, int n2, double nu, double a_dt, double b_dt, int last,
@@ -154,7 +154,8 @@ SHB_API int shb_banded_solve(int kl, int ku, int step, void *d_u, const double *
                              int64_t inner, int n, int n_u, int fac_shared, int is_complex, void *stream);
 
 /* out (+)= sum_m scale_m[line] * M_m u along the axis; M_m given as mat[ndiag][n_rows]
- * with explicit offsets.  Replaces SparseMatrix.matvec / Matvec.pyx:430-512.    */
+ * with explicit offsets.  `accumulate` bit 0: add to out; bit 1: multiply the result by i
+ * (imaginary Fourier scales, complex data).  Replaces SparseMatrix.matvec / Matvec.pyx:430-512. */
 SHB_API int shb_banded_matvec(const void *d_u, void *d_out, int nmat, int ndiag, const int *offsets,
                               const double *const *d_mats, const double *const *d_scales, int64_t outer,
                               int64_t inner, int n_rows, int n_cols, int n_u, int n_out, int accumulate,

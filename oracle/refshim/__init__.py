@@ -33,6 +33,34 @@ def activate(reference='/root/reference'):
     stub.Leg2Cheb = _Unavailable
     stub.Cheb2Leg = _Unavailable
     sys.modules['shenfun.optimization.cython'] = stub
+    import numpy as np
+    if not hasattr(np, 'asscalar'):
+        # removed in numpy 1.23; the reference's numba 1-D Helmholtz still calls it
+        # (shenfun/optimization/numba/helmholtz.py:16)
+        np.asscalar = lambda a: np.asarray(a).item()
     import shenfun
     shenfun.config['optimization']['mode'] = 'numba'
+    _route_matvecs_away_from_cython(shenfun)
     return shenfun
+
+
+def _route_matvecs_away_from_cython(shenfun):
+    """Several hard-coded matrices default to format='cython' in their `matvec`
+    (e.g. shenfun/chebyshev/matrices.py:966-990), i.e. to the compiled Matvec.pyx that is not
+    built here.  Route the default to the reference's own alternative implementations of the same
+    product: the numpy 'self' branch where the class has one, else the scipy 'csr' base class."""
+    import functools
+    import inspect
+    from shenfun.chebyshev import matrices as cm
+    from shenfun.legendre import matrices as lm
+    for mod in (cm, lm):
+        for name, cls in inspect.getmembers(mod, inspect.isclass):
+            if 'matvec' not in cls.__dict__:
+                continue
+            orig = cls.__dict__['matvec']
+
+            def wrapped(self, v, c, format=None, axis=0, _orig=orig):
+                if format is None or format == 'cython':
+                    format = 'self' if 'self' in getattr(self, '_matvec_methods', []) else 'csr'
+                return _orig(self, v, c, format=format, axis=axis)
+            setattr(cls, 'matvec', functools.wraps(orig)(wrapped))

@@ -39,9 +39,18 @@ class Orthogonal(PolyBase):
             N = self.physical_len()
         points, weights = np.polynomial.chebyshev.chebgauss(N)
         points = points.astype(float)
+        weights = weights.astype(float)
+        if not weighted:
+            # chebyshev/bases.py:235-241: weights of int f dx (no Chebyshev weight) on the GC points,
+            # w = DCT-III(d), d[::2] = (2/N) / (1, 1-k^2), k = 2, 4, ...
+            import scipy.fft as sfft
+            d = np.zeros(N)
+            k = 2*(1+np.arange((N-1)//2))
+            d[::2] = (2.0/N)/np.hstack((1.0, 1.0-k*k))
+            weights = sfft.dct(d, type=3)
         if map_true_domain:
             points = self.map_true_domain(points)
-        return points, weights.astype(float)
+        return points, weights
 
     def ortho_norm_sq(self, N=None):
         N = self.N if N is None else N

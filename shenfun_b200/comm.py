@@ -11,15 +11,16 @@ import torch.distributed as dist
 
 
 class Comm:
-    def __init__(self, group=None):
+    def __init__(self, group=None, self_only=False):
         self._group = group
+        self._self_only = self_only
 
     @property
     def group(self):
         return self._group
 
     def _active(self):
-        return dist.is_available() and dist.is_initialized()
+        return (not self._self_only) and dist.is_available() and dist.is_initialized()
 
     def Get_size(self):
         return dist.get_world_size(self._group) if self._active() else 1
@@ -85,3 +86,4 @@ def init_from_env(backend=None):
 
 
 comm = Comm()
+COMM_SELF = Comm(self_only=True)     # single-rank communicator (e.g. the 1-D (0,0)-mode problems)

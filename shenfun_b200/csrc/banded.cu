@@ -199,6 +199,9 @@ struct MatvecDesc {
     int accumulate;
 };
 
+__device__ __forceinline__ double times_i(double a) { return a; }     // (real data never carries imaginary scales)
+__device__ __forceinline__ cplx times_i(cplx a) { return make_double2(-a.y, a.x); }
+
 template <class T>
 __global__ void __launch_bounds__(256) banded_matvec_kernel(const T *__restrict__ u, T *__restrict__ out,
                                                             const __grid_constant__ MatvecDesc d) {
@@ -226,7 +229,8 @@ __global__ void __launch_bounds__(256) banded_matvec_kernel(const T *__restrict_
                 acc = Num<T>::fnma(-s, part, acc);
             }
         }
-        if (d.accumulate) out[idx] = Num<T>::add(out[idx], acc);
+        if (d.accumulate & 2) acc = times_i(acc);          // scale arrays were the imaginary parts
+        if (d.accumulate & 1) out[idx] = Num<T>::add(out[idx], acc);
         else out[idx] = acc;
     }
 }

@@ -109,12 +109,12 @@ __global__ void __launch_bounds__(PW_THREADS) ns_rk_stage_kernel(
             cplx d = make_double2(w[c].x - kv[c] * p.y, w[c].y + kv[c] * p.x);
             d.x = fma(lin, uh.x, d.x);
             d.y = fma(lin, uh.y, d.y);
-            dU[c * n + i] = d;
+            if (!(last & 2)) dU[c * n + i] = d;      // bit 1 of `last`: the caller does not need dU back
             cplx u1 = U1[c * n + i];
             u1.x = fma(a_dt, d.x, u1.x);
             u1.y = fma(a_dt, d.y, u1.y);
             U1[c * n + i] = u1;
-            if (last) {
+            if (last & 1) {
                 u_hat[c * n + i] = u1;
             } else {
                 const cplx u0 = U0[c * n + i];

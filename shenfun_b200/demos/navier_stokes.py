@@ -80,7 +80,8 @@ def solve_reference_style(N=(32, 32, 32), nu=0.000625, dt=0.01, end_time=0.1, pa
 class FusedNS:
     """Same time stepping with fused spectral kernels and batched padded transforms."""
 
-    def __init__(self, N=(32, 32, 32), nu=0.000625, dt=0.01, padding_factor=1.5, comm=None):
+    def __init__(self, N=(32, 32, 32), nu=0.000625, dt=0.01, padding_factor=1.5, comm=None, pressure=False):
+        self.pressure = pressure     # also return P_hat every stage (the demo keeps it; the update does not need it)
         self.N, self.nu, self.dt = tuple(N), nu, dt
         self.T, self.TV = make_spaces(N, comm)
         pad = abs(padding_factor-1) > 1e-8
@@ -119,8 +120,8 @@ class FusedNS:
             self.TVp.backward(self.U_hat, self.Up)
             ops.cross3d(self.Up.v, self.curl_p.v, self.Up.v)        # W overwrites U (same index)
             self.TVp.forward(self.Up, self.dU)
-            ops.ns_rk_stage(dU, uh, U0, U1, self.P_hat.v, k0, k1, k2, nu, self.a[rk]*dt, self.b[rk]*dt,
-                            rk == 3)
+            ops.ns_rk_stage(dU, uh, U0, U1, self.P_hat.v if self.pressure else None, k0, k1, k2, nu,
+                            self.a[rk]*dt, self.b[rk]*dt, rk == 3, keep_dU=False)
         self.t += dt
         self.tstep += 1
 

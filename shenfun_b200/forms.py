@@ -1,12 +1,13 @@
 """A small Cartesian form language: TestFunction / TrialFunction, Dx / grad / div /
-curl, `inner` and `project`.
+curl, `inner`, `project`, and the cached `Inner` / `Project` objects.
 
 Host-side mirror of the *interface* of shenfun/forms/arguments.py:420-1202
 (`Expr`, `TestFunction`, `TrialFunction`), forms/operators.py (`Dx`, `grad`,
-`div`, `curl`), forms/inner.py:16-511 (`inner`) and forms/project.py:16-170
-(`project`) for the cases the hot path needs: constant-coefficient terms on
+`div`, `curl`), forms/inner.py:16-566 (`inner`, `Inner`) and forms/project.py:16-272
+(`project`, `Project`) for the cases the hot path needs: constant-coefficient terms on
 Cartesian tensor-product spaces.  Bilinear forms give `TPMatrix` objects (1-D
-matrices per axis, see matrices.py); linear forms are evaluated on the device.
+matrices per axis, see matrices.py); linear forms are evaluated on the device as
+banded / structured mat-vecs along the non-periodic axis times diagonal Fourier scales.
 Curvilinear coordinates and sympy-valued coefficients are out of scope
 (SURVEY.md section 2, rows 12 and 18).
 """
@@ -17,32 +18,38 @@ import torch
 from .arrays import Function, Array
 from . import ops
 
-__all__ = ('Expr', 'TestFunction', 'TrialFunction', 'Dx', 'grad', 'div', 'curl', 'inner', 'project')
+__all__ = ('Expr', 'TestFunction', 'TrialFunction', 'Dx', 'grad', 'div', 'curl', 'inner', 'project',
+           'Inner', 'Project')
 
 
 class Expr:
-    """Sum of scaled derivatives of the components of one basis.
+    """Sum of scaled derivatives of basis functions or of known Functions.
 
-    `terms[c]` is the list of `(scale, comp, derivs)` making up output component
-    `c`: `scale * d^{derivs}/dx^{derivs} basis[comp]`.  `basis` is a
-    TestFunction / TrialFunction, or a `Function` holding expansion coefficients.
+    `terms[c]` is the list of `(scale, comp, derivs, ref)` making up output component `c`:
+    `scale * d^{derivs}/dx^{derivs} ref[comp]`, where `ref` is a TestFunction / TrialFunction
+    or a `Function` holding expansion coefficients (a term may reference its own Function,
+    so sums like `Dx(H[1], 0, 1) - Dx(H[0], 1, 2)` are fine).
     """
 
-    def __init__(self, basis, terms, rank):
+    def __init__(self, basis, terms=None, rank=None):
+        if terms is None:                       # Expr(Function): arguments.py:452-470
+            e = as_expr(basis)
+            basis, terms, rank = e.basis, e.terms, e.rank
         self.basis = basis
         self.terms = terms
-        self.rank = rank           # 0: scalar expression, 1: vector
+        self.rank = rank           # 0: scalar expression, 1: vector, 2: tensor
 
     @property
     def argument(self):
-        b = self.basis
-        if isinstance(b, BasisFunction):
-            return b.argument
-        return 2               # a Function: known coefficients
+        args = {(t[3].argument if isinstance(t[3], BasisFunction) else 2) for comp in self.terms for t in comp}
+        assert len(args) == 1, 'an expression cannot mix test, trial and known functions'
+        return args.pop()
 
     def function_space(self):
-        b = self.basis
-        return b.function_space() if isinstance(b, (BasisFunction, Function)) else b.space
+        return self.basis.function_space()
+
+    def base(self):
+        return self.basis
 
     @property
     def dimensions(self):
@@ -52,7 +59,7 @@ class Expr:
         return len(self.terms)
 
     def _scaled(self, a):
-        return Expr(self.basis, [[(s*a, c, d) for (s, c, d) in t] for t in self.terms], self.rank)
+        return Expr(self.basis, [[(s*a, c, d, r) for (s, c, d, r) in t] for t in self.terms], self.rank)
 
     def __mul__(self, a):
         assert isinstance(a, numbers.Number), 'only constant coefficients are on the device path'
@@ -68,7 +75,7 @@ class Expr:
 
     def __add__(self, other):
         other = as_expr(other)
-        assert other.basis is self.basis and other.rank == self.rank
+        assert other.rank == self.rank and len(other.terms) == len(self.terms)
         return Expr(self.basis, [a+b for a, b in zip(self.terms, other.terms)], self.rank)
 
     def __sub__(self, other):
@@ -78,6 +85,11 @@ class Expr:
         assert self.rank == 1
         return Expr(self.basis, [self.terms[i]], 0)
 
+    def with_basis(self, new):
+        """Same expression with every reference replaced by `new` (arguments.py: `ul._basis = ...`,
+        used by the IMEX integrators to turn u into a TrialFunction)."""
+        return Expr(new, [[(s, c, d, new) for (s, c, d, r) in t] for t in self.terms], self.rank)
+
 
 class BasisFunction(Expr):
     argument = 0
@@ -86,7 +98,7 @@ class BasisFunction(Expr):
         self.space = space
         nd = space.dimensions
         ncomp = space.num_components() if space.is_composite_space else 1
-        terms = [[(1.0, c, (0,)*nd)] for c in range(ncomp)]
+        terms = [[(1.0, c, (0,)*nd, self)] for c in range(ncomp)]
         Expr.__init__(self, self, terms, 1 if space.is_composite_space else 0)
 
     def function_space(self):
@@ -111,7 +123,7 @@ def as_expr(u):
         space = u.function_space()
         nd = space.dimensions
         ncomp = space.num_components() if space.is_composite_space else 1
-        return Expr(u, [[(1.0, c, (0,)*nd)] for c in range(ncomp)], 1 if space.is_composite_space else 0)
+        return Expr(u, [[(1.0, c, (0,)*nd, u)] for c in range(ncomp)], 1 if space.is_composite_space else 0)
     raise TypeError(f'cannot interpret {type(u)} as an expression')
 
 
@@ -120,7 +132,7 @@ def Dx(u, x, k=1):
     u = as_expr(u)
     terms = []
     for t in u.terms:
-        terms.append([(s, c, tuple(d[i]+(k if i == x else 0) for i in range(len(d)))) for (s, c, d) in t])
+        terms.append([(s, c, tuple(d[i]+(k if i == x else 0) for i in range(len(d))), r) for (s, c, d, r) in t])
     return Expr(u.basis, terms, u.rank)
 
 
@@ -183,35 +195,98 @@ def _bilinear(test, trial):
     ncomp = len(test.terms)
     assert len(trial.terms) == ncomp
     for c in range(ncomp):
-        for (s0, c0, d0) in test.terms[c]:
-            for (s1, c1, d1) in trial.terms[c]:
-                tsp = _scalar_space(test.function_space(), c0)
-                usp = _scalar_space(trial.function_space(), c1)
+        for (s0, c0, d0, r0) in test.terms[c]:
+            for (s1, c1, d1, r1) in trial.terms[c]:
+                tsp = _scalar_space(r0.function_space(), c0)
+                usp = _scalar_space(r1.function_space(), c1)
                 mats.append(TPMatrix.assemble(tsp, usp, d0, d1, s0*s1, global_index=(c0, c1)))
     return mats
 
 
+class Inner:
+    """Cached linear form (expr(Function), v): the matrices are assembled once, every call is
+    a handful of mat-vec launches (forms/inner.py:514-566).  Terms that share the source
+    Function component and the test component are fused into one line operator."""
+
+    def __init__(self, v, uh):
+        from .la import LinearFormOperator
+        assert isinstance(v, TestFunction)
+        self.space = v.function_space()
+        self.output_array = Function(self.space)
+        self.parts = []
+        if isinstance(uh, Array):
+            self.parts.append(('array', uh, None, None))
+            return
+        e = as_expr(uh)
+        assert e.argument == 2, 'Inner needs an expression of known Functions'
+        ncomp = len(v.terms)
+        assert len(e.terms) == ncomp, 'test and trial expressions must have the same number of components'
+        groups = {}
+        for c in range(ncomp):
+            for (s0, c0, d0, r0) in v.terms[c]:
+                for (s1, c1, d1, r1) in e.terms[c]:
+                    from .matrices import TPMatrix
+                    tsp = _scalar_space(self.space, c0)
+                    usp = _scalar_space(r1.function_space(), c1)
+                    M = TPMatrix.assemble(tsp, usp, d0, d1, s0*s1)
+                    groups.setdefault((c0, id(r1), c1), [r1, c0, c1, []])[3].append(M)
+        for (r1, c0, c1, mats) in groups.values():
+            self.parts.append(('op', r1, (c0, c1), LinearFormOperator(mats)))
+
+    def __call__(self):
+        out = ops.plain(self.output_array)
+        out.zero_()
+        for kind, ref, idx, op in self.parts:
+            if kind == 'array':
+                tmp = self.space.scalar_product(ref, Function(self.space))
+                out.add_(ops.plain(tmp))
+                continue
+            c0, c1 = idx
+            src = ops.plain(ref)
+            if ref.function_space().is_composite_space:
+                src = src[c1]
+            dst = out[c0] if self.space.is_composite_space else out
+            op.matvec(src, dst, accumulate=True)
+        return self.output_array
+
+    def __add__(self, other):
+        assert isinstance(other, Inner) and other.space is self.space
+        new = Inner.__new__(Inner)
+        new.space = self.space
+        new.output_array = Function(self.space)
+        new.parts = self.parts+other.parts
+        return new
+
+    __radd__ = __add__
+
+
+class Project:
+    """Cached projection of an expression onto T (forms/project.py:172-272): right hand side
+    through `Inner`, then the mass matrix of T (banded solve along the non-periodic axis)."""
+
+    def __init__(self, uh, T, output_array=None):
+        self.T = T
+        self.rhs = Inner(TestFunction(T), uh)
+        self.output_array = Function(T) if output_array is None else output_array
+
+    def __call__(self):
+        from .la import mass_solve
+        rhs = self.rhs()
+        flat = self.T.flatten() if self.T.is_composite_space else [self.T]
+        if all(all(b.family() == 'fourier' for b in s.bases) for s in flat):
+            ops.plain(self.output_array).copy_(ops.plain(rhs))
+        else:
+            mass_solve(self.T, rhs, self.output_array)
+        return self.output_array
+
+
 def _linear(test, expr, output_array):
-    """Evaluate (expr(Function), test) -> coefficients, component by component."""
-    from .matrices import TPMatrix
-    uf = expr.basis
-    tspace = test.function_space()
+    """One-off evaluation of (expr(Function), test)."""
+    I = Inner(test, expr)
+    res = I()
     if output_array is None:
-        output_array = Function(tspace)
-    out = ops.plain(output_array)
-    uv = ops.plain(uf)
-    out.zero_()
-    ncomp = len(test.terms)
-    assert len(expr.terms) == ncomp, 'test and trial expressions must have the same number of components'
-    for c in range(ncomp):
-        for (s0, c0, d0) in test.terms[c]:
-            dst = out[c0] if tspace.is_composite_space else out
-            for (s1, c1, d1) in expr.terms[c]:
-                tsp = _scalar_space(tspace, c0)
-                usp = _scalar_space(uf.function_space(), c1)
-                M = TPMatrix.assemble(tsp, usp, d0, d1, s0*s1)
-                src = uv[c1] if uf.function_space().is_composite_space else uv
-                M.matvec(src, dst, accumulate=True)
+        return res
+    ops.plain(output_array).copy_(ops.plain(res))
     return output_array
 
 
@@ -221,7 +296,7 @@ def inner(expr0, expr1, output_array=None, assemble=None, kind=None, **kw):
     * test x trial            -> list of TPMatrix (a single one is returned bare)
     * test x expr(Function)   -> Function of coefficients (linear form, matvec)
     * test x Array            -> scalar product of the Array (forms/inner.py:361-364)
-    * number x Array          -> integral over the domain (forms/inner.py:268)
+    * number x Array/Function -> integral over the domain (forms/inner.py:182-199)
     """
     if isinstance(expr0, numbers.Number) or isinstance(expr1, numbers.Number):
         a, arr = (expr0, expr1) if isinstance(expr0, numbers.Number) else (expr1, expr0)
@@ -244,22 +319,27 @@ def inner(expr0, expr1, output_array=None, assemble=None, kind=None, **kw):
 
 
 def _integrate(arr):
-    """(1, u) with the quadrature weights of every axis (utilities/__init__.py:26-61 `dx`
-    up to the weight function; forms/inner.py:268)."""
+    """(1, u) = integral of u over the true domain: un-weighted quadrature weights of every
+    axis divided by the domain factors (forms/inner.py:182-199 with utilities `dx` :26-61).
+    A Function is transformed to physical space first."""
+    if isinstance(arr, Function):
+        arr = arr.backward()
     space = arr.function_space()
     t = ops.plain(arr)
-    nd = space.dimensions
-    sl = space.local_slice(False)
-    for ax, b in enumerate(space.flatten()[0].bases if space.is_composite_space else space.bases):
-        w = b.points_and_weights(b.physical_len())[1]
-        w = np.broadcast_to(w, (b.physical_len(),))[sl[ax]]/b.domain_factor() if b.family() != 'fourier' \
-            else np.broadcast_to(w, (b.physical_len(),))[sl[ax]]
+    sc = space.flatten()[0] if space.is_composite_space else space
+    nd = sc.dimensions
+    sl = sc.local_slice(False)
+    df = 1.0
+    for ax, b in enumerate(sc.bases):
+        w = b.points_and_weights(b.physical_len(), weighted=False)[1]
+        w = np.broadcast_to(w, (b.physical_len(),))[sl[ax]]
+        df *= float(b.domain_factor())
         shape = [1]*nd
         shape[ax] = len(w)
         t = t*torch.as_tensor(np.ascontiguousarray(w), device=t.device).view(shape)
     val = t.sum()
     val = space.comm.allreduce(val)
-    val = val.item()
+    val = val.item()/df
     return val.real if isinstance(val, complex) and abs(val.imag) < 1e-14*max(1.0, abs(val)) else val
 
 
@@ -272,13 +352,4 @@ def project(uh, T, output_array=None, fill=True, use_to_ortho=True, use_assign=T
         output_array = Function(T)
     if isinstance(uh, Array):
         return T.forward(uh, output_array)
-    e = as_expr(uh)
-    v = TestFunction(T)
-    rhs = _linear(v, e, None if False else Function(T))
-    flat = T.flatten() if T.is_composite_space else [T]
-    if all(s.is_orthogonal() and all(b.family() == 'fourier' for b in s.bases) for s in flat):
-        # Fourier mass matrix is the identity (weight 1/L, fourier/bases.py:79-81)
-        ops.plain(output_array).copy_(ops.plain(rhs))
-        return output_array
-    from .matrices import mass_solve
-    return mass_solve(T, rhs, output_array)
+    return Project(uh, T, output_array=output_array)()

@@ -13,7 +13,7 @@ from .forms import TrialFunction, TestFunction, inner, Expr
 from .matrices import TPMatrix, get_simplified_tpmatrices
 from . import ops
 
-__all__ = ('IntegratorBase', 'RK4')
+__all__ = ('IntegratorBase', 'RK4', 'PDEIMEXRK', 'IMEXRK011', 'IMEXRK111', 'IMEXRK222', 'IMEXRK443')
 
 
 class IntegratorBase:
@@ -97,3 +97,124 @@ class RK4(IntegratorBase):
                               self.b[rk]*dt if rk < 3 else 0.0, rk == 3)
             self.update(u, u_hat, t, tstep, **self.params)
         return u_hat
+
+
+class PDEIMEXRK:
+    """Implicit-explicit Runge-Kutta for du/dt = N + L u (Ascher, Ruuth, Spiteri 1997):
+    shenfun/utilities/integrators.py:702-817.  One linear solve per stage (the diagonal of the
+    implicit tableau is constant), right hand sides through cached `Inner` mat-vecs."""
+
+    def __init__(self, v, u, L, N, dt, solver=None, name='U-equation', latex=None):
+        from .forms import as_expr, Expr
+        from . import la
+        self.v = v
+        self.u = as_expr(u)
+        self.u_ = self.u.basis          # the Function that holds the solution
+        self.L = L
+        self.N = N
+        self.dt = dt
+        self._solver = solver if solver is not None else la.SolverGeneric1ND
+        self.solvers = []
+        self.name = name
+        self.latex = latex
+        T = self.T = v.function_space()
+        dev = ops.plain(self.u_).device
+        shape = tuple(T.shape(True))
+        self.rhs = Function(T)
+        self.Krhs = torch.zeros((self.steps(),)+shape, dtype=torch.complex128 if T.spectral_dtype.is_complex
+                                else torch.float64, device=dev)
+        self.Lrhs = torch.zeros((max(self.steps()-1, 1),)+shape, dtype=self.Krhs.dtype, device=dev)
+        self.mask = T._device_mask() if hasattr(T, '_device_mask') else None
+
+    @classmethod
+    def steps(cls):
+        raise NotImplementedError
+
+    def stages(self):
+        raise NotImplementedError
+
+    def assemble(self):
+        from .forms import inner, Inner, TrialFunction, Expr
+        a = self.stages()[0]
+        dt = self.dt
+        ul = self.u.with_basis(TrialFunction(self.u_.function_space()))
+        mats = inner(self.v, ul - (dt*a[1, 1])*self.L(ul))
+        self.solvers.append(self._solver(mats))
+        self.linear_rhs = Inner(self.v, self.L(self.u))
+        self.u0_rhs = Inner(self.v, self.u)
+        if isinstance(self.N, (list, tuple)):
+            parts = [Inner(self.v, f) for f in self.N]
+            nl = parts[0]
+            for p in parts[1:]:
+                nl = nl+p
+            self.nonlinear_rhs = nl
+        else:
+            self.nonlinear_rhs = Inner(self.v, self.N)
+
+    def compute_rhs(self, rk=0):
+        a, b = self.stages()[:2]
+        self.Krhs[rk].copy_(ops.plain(self.nonlinear_rhs()))
+        if rk == 0:
+            self.u0_rhs()        # only at the start of a step
+        rhs = ops.plain(self.rhs)
+        rhs.copy_(ops.plain(self.u0_rhs.output_array))
+        for j in range(0, rk+1):
+            rhs.add_(self.Krhs[j], alpha=self.dt*b[rk+1, j])
+        if rk > 0:
+            self.Lrhs[rk-1].copy_(ops.plain(self.linear_rhs()))
+            for j in range(0, rk):
+                rhs.add_(self.Lrhs[j], alpha=self.dt*a[rk+1, j+1])
+        if self.mask is not None:
+            ops.apply_mask(rhs, self.mask)
+        return self.rhs
+
+    def solve_step(self, rk=0):
+        return self.solvers[0](self.rhs, self.u_)
+
+
+class IMEXRK011(PDEIMEXRK):
+    @classmethod
+    def steps(cls):
+        return 1
+
+    def stages(self):
+        a = np.array([[0, 0], [0, 0]])
+        b = np.array([[0, 0], [1, 0]])
+        return a, b, (1, 0)
+
+
+class IMEXRK111(PDEIMEXRK):
+    @classmethod
+    def steps(cls):
+        return 1
+
+    def stages(self):
+        a = np.array([[0, 0], [0, 1]])
+        b = np.array([[0, 0], [1, 0]])
+        return a, b, (0, 1)
+
+
+class IMEXRK222(PDEIMEXRK):
+    @classmethod
+    def steps(cls):
+        return 2
+
+    def stages(self):
+        gamma = (2-np.sqrt(2))/2
+        delta = 1-1/(2*gamma)
+        a = np.array([[0, 0, 0], [0, gamma, 0], [0, 1-gamma, gamma]])
+        b = np.array([[0, 0, 0], [gamma, 0, 0], [delta, 1-delta, 0]])
+        return a, b, (0, gamma, 1)
+
+
+class IMEXRK443(PDEIMEXRK):
+    @classmethod
+    def steps(cls):
+        return 4
+
+    def stages(self):
+        a = np.array([[0, 0, 0, 0, 0], [0, 1/2, 0, 0, 0], [0, 1/6, 1/2, 0, 0], [0, -1/2, 1/2, 1/2, 0],
+                      [0, 3/2, -3/2, 1/2, 1/2]])
+        b = np.array([[0, 0, 0, 0, 0], [1/2, 0, 0, 0, 0], [11/18, 1/18, 0, 0, 0], [5/6, -5/6, 1/2, 0, 0],
+                      [1/4, 7/4, 3/4, -7/4, 0]])
+        return a, b, (0, 1/2, 2/3, 1/2, 1)

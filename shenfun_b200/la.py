@@ -16,7 +16,7 @@ import torch
 from .matrices import SparseMatrix, TPMatrix, get_simplified_tpmatrices
 from . import ops
 
-__all__ = ('Biharmonic', 'BandedFactor', 'TDMA', 'TDMA_O', 'PDMA', 'FDMA', 'TwoDMA', 'ThreeDMA', 'HeptaDMA', 'DiagMA',
+__all__ = ('LinearFormOperator', 'Biharmonic', 'BandedFactor', 'TDMA', 'TDMA_O', 'PDMA', 'FDMA', 'TwoDMA', 'ThreeDMA', 'HeptaDMA', 'DiagMA',
            'Solve', 'Solver', 'SolverGeneric1ND', 'SolverDiagonal', 'Helmholtz', 'tp_matvec')
 
 
@@ -233,6 +233,184 @@ def _line_scales(tpmat, axis):
     return np.ascontiguousarray(np.broadcast_to(arr, shape)).reshape(-1)
 
 
+def _line_scales_complex(tpmat, axis):
+    """Like `_line_scales` but returns (real, imag) parts (imag None when it vanishes)."""
+    space = tpmat.space
+    sl = space.local_slice(True)
+    nd = tpmat.dimensions
+    arr = np.ones([1]*nd, dtype=complex)
+    for ax, m in enumerate(tpmat.mats):
+        if ax == axis:
+            continue
+        v = m.scaled_diagonal(0)
+        full = np.zeros(space.bases[ax].spectral_len(), dtype=complex)
+        full[space.bases[ax].slice()] = v
+        shape = [1]*nd
+        shape[ax] = sl[ax].stop-sl[ax].start
+        arr = arr*full[sl[ax]].reshape(shape)
+    arr = arr*tpmat.scale
+    shape = list(space.shape(True))
+    if axis is not None:
+        shape[axis] = 1
+    arr = np.ascontiguousarray(np.broadcast_to(arr, shape)).reshape(-1)
+    re = np.ascontiguousarray(arr.real)
+    im = np.ascontiguousarray(arr.imag) if np.abs(arr.imag).max() > 0 else None
+    if im is not None and np.abs(re).max() == 0:
+        re = None
+    return re, im
+
+
+class LinearFormOperator:
+    """out (+)= sum_m scale_m(line) M_m u for the TPMatrices of one linear form (same source and
+    target component): banded 1-D matrices go through `shb_banded_matvec`, the dense upper
+    triangular Chebyshev matrices through the structured kernels (constant rows:
+    `shb_helmholtz_matvec`; rank-2 tail: `shb_biharmonic_matvec`), anything else through the
+    tensor-core contraction.  Fourier scales may be complex (odd derivative orders)."""
+
+    MAXDIAG = 16
+
+    def __init__(self, mats):
+        self.mats = list(mats)
+        m0 = self.mats[0]
+        self.space = m0.space             # test space
+        self.trialspace = m0.trialspace
+        nd_axes = set()
+        for m in self.mats:
+            for ax, mm in enumerate(m.mats):
+                if m.space.bases[ax].family() != 'fourier':
+                    nd_axes.add(ax)
+        if len(nd_axes) > 1:
+            raise NotImplementedError('linear forms with more than one non-periodic axis')
+        self.axis = nd_axes.pop() if nd_axes else None
+        shape_out = self.space.shape(True)
+        shape_in = self.trialspace.shape(True)
+        self.parts = []
+        if self.axis is None:
+            d = None
+            for m in self.mats:
+                a = m.diagonal_array()
+                d = a if d is None else d+a
+            self.parts.append(('diag', d))
+            return
+        ax = self.axis
+        self.outer = int(np.prod(shape_out[:ax], dtype=np.int64))
+        self.inner = int(np.prod(shape_out[ax+1:], dtype=np.int64))
+        self.n_out, self.n_u = shape_out[ax], shape_in[ax]
+        groups = {}
+        for m in self.mats:
+            m1 = m.mats[ax]
+            sig = (m1.shape, tuple(sorted(m1.keys())))+tuple(np.asarray(m1[k]*m1.scale).tobytes() for k in sorted(m1.keys()))
+            re, im = _line_scales_complex(m, ax)
+            g = groups.setdefault(sig, [m1, None, None])
+            if re is not None:
+                g[1] = re if g[1] is None else g[1]+re
+            if im is not None:
+                g[2] = im if g[2] is None else g[2]+im
+        banded = {False: [], True: []}     # keyed by "imaginary scales"
+        for m1, re, im in groups.values():
+            wide = len(m1.keys()) > self.MAXDIAG
+            for imag, sc in ((False, re), (True, im)):
+                if sc is None:
+                    continue
+                scd = ops.as_device_tensor(sc)
+                if wide:
+                    self.parts.append(self._wide_part(m1, scd, imag))
+                else:
+                    banded[imag].append((m1, scd))
+        for imag, lst in banded.items():
+            for i in range(0, len(lst), 4):
+                chunk = lst[i:i+4]
+                offs = sorted(set(o for m1, _ in chunk for o in m1.keys()))
+                if len(offs) > self.MAXDIAG:
+                    for m1, scd in chunk:
+                        self.parts.append(self._banded_part([(m1, scd)], imag))
+                else:
+                    self.parts.append(self._banded_part(chunk, imag))
+
+    def _banded_part(self, chunk, imag):
+        offs = sorted(set(o for m1, _ in chunk for o in m1.keys()))
+        n_rows, n_cols = chunk[0][0].shape
+        tabs = []
+        for m1, _ in chunk:
+            assert m1.shape == (n_rows, n_cols)
+            t = np.zeros((len(offs), n_rows))
+            for k, off in enumerate(offs):
+                if off in m1:
+                    v = np.real(m1[off])*np.real(m1.scale)
+                    if off >= 0:
+                        t[k, :len(v)] = v
+                    else:
+                        t[k, -off:-off+len(v)] = v
+            tabs.append(ops.as_device_tensor(t))
+        return ('banded', offs, tabs, [s for _, s in chunk], n_rows, n_cols, imag)
+
+    def _wide_part(self, m1, scd, imag):
+        n = m1.shape[0]
+        assert m1.shape[0] == m1.shape[1], 'wide 1-D matrices must be square'
+        sc = float(np.real(m1.scale))
+        offs = sorted(m1.keys())
+
+        def diag(off):
+            v = np.zeros(n)
+            if off in m1:
+                d = np.real(m1[off])*sc
+                v[:len(d)] = d
+            return v
+        zeros = ops.as_device_tensor(np.zeros(n))
+        if min(offs) >= 0 and all(o % 2 == 0 for o in offs):
+            # constant rows beyond +4?  (Chebyshev Dirichlet stiffness)
+            if all(np.allclose(m1[o], m1[4][:len(m1[o])], rtol=1e-11, atol=0) for o in offs if o > 4):
+                tabs = [ops.as_device_tensor(diag(0)), ops.as_device_tensor(diag(2)), ops.as_device_tensor(diag(4)),
+                        zeros, zeros, zeros]
+                return ('helm', tabs, scd, zeros.new_zeros(scd.shape), n, imag)
+            # rank-2 tail beyond +4?  (Chebyshev biharmonic fourth-derivative matrix)
+            k = np.arange(n, dtype=float)
+            al = 8*np.pi*k*(k+1)*(k+2)*(k+4)*sc
+            be = 24*np.pi*(k+1)*(k+2)*sc
+            ok = True
+            for o in offs:
+                if o >= 6:
+                    j = np.arange(len(m1[o]))+o
+                    ok = ok and np.allclose(m1[o]*sc, (al[:len(j)]+be[:len(j)]*(j+2.0)**2)/(j+3.0), rtol=1e-10)
+            if ok:
+                tab = np.zeros((13, n))
+                tab[0], tab[1], tab[2], tab[3], tab[4] = diag(0), diag(2), diag(4), al, be
+                return ('bih', ops.as_device_tensor(tab), scd, zeros.new_zeros(scd.shape), n, imag)
+        return ('dense', ops.as_device_tensor(np.ascontiguousarray(m1.diags())), scd, n, imag)
+
+    def matvec(self, u, out, accumulate=False):
+        u, out = ops.plain(u), ops.plain(out)
+        if not accumulate:
+            out.zero_()
+        for part in self.parts:
+            kind = part[0]
+            if kind == 'diag':
+                d = part[1]
+                out.addcmul_(u, d.to(u.dtype) if d.dtype != u.dtype else d)
+            elif kind == 'banded':
+                _, offs, tabs, scales, n_rows, n_cols, imag = part
+                ops.banded_matvec(u, out, offs, tabs, scales, self.outer, self.inner, n_rows, n_cols,
+                                  self.n_u, self.n_out, 1 | (2 if imag else 0))
+            else:
+                tmp = torch.empty_like(out)
+                if kind == 'helm':
+                    _, tabs, sc, z, n, imag = part
+                    ops.helmholtz_matvec(u, tmp, tabs, sc, z, self.outer, self.inner, n, self.n_u)
+                elif kind == 'bih':
+                    _, tab, sc, z, n, imag = part
+                    ops.biharmonic_matvec(u, tmp, tab, sc, z, z, self.outer, self.inner, n, self.n_u)
+                else:
+                    _, M, sc, n, imag = part
+                    assert self.n_u == self.n_out
+                    full = torch.zeros((self.n_out, self.n_u), dtype=torch.float64, device=u.device)
+                    full[:n, :n] = M
+                    ops.gemm_axis(full, u, tmp, self.outer, self.inner)
+                    shape = [self.outer, 1, self.inner]
+                    tmp.view(self.outer, self.n_out, self.inner).mul_(sc.view(shape))
+                out.add_(tmp*1j if imag else tmp)
+        return out
+
+
 def _nondiagonal_axis(mats):
     axes = set()
     for m in mats:
@@ -298,7 +476,7 @@ class _LineOperator:
 
 def tp_matvec(tpmat, u, out, accumulate=False):
     if not hasattr(tpmat, '_lineop'):
-        tpmat._lineop = _LineOperator([tpmat])
+        tpmat._lineop = LinearFormOperator([tpmat])
     return tpmat._lineop.matvec(ops.plain(u), ops.plain(out), accumulate)
 
 

@@ -400,6 +400,18 @@ class TensorProductSpace:
     def slice(self):
         return tuple(b.slice() for b in self.bases)
 
+    @property
+    def domains(self):
+        return [tuple(b.domain) for b in self.bases]
+
+    @property
+    def volume(self):
+        """tensorproductspace.py:1030-1036"""
+        vol = 1.0
+        for d in self.domains:
+            vol *= float(d[1]-d[0])
+        return vol
+
     def get_nonperiodic_axes(self):
         return [i for i, b in enumerate(self.bases) if b.family() != 'fourier']
 

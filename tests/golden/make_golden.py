@@ -307,6 +307,49 @@ def solvers():
     save('solvers', **out)
 
 
+def channel_flow():
+    """demo/MKM.py (KMM channel flow, Chebyshev x Fourier^2, IMEXRK222, 3/2 padding): velocity
+    coefficients after 1 and 3 time steps for both convection forms.  File output and
+    checkpointing (HDF5, absent here) are stubbed out; everything else is the reference's code."""
+    import shenfun
+
+    class _NoFile:
+        def __init__(self, *a, **k):
+            pass
+
+        def update(self, *a, **k):
+            pass
+
+        def write(self, *a, **k):
+            pass
+
+    shenfun.ShenfunFile = _NoFile
+    shenfun.Checkpoint = _NoFile
+    sys.path.insert(0, '/root/reference/demo')
+    import types
+    if 'matplotlib' not in sys.modules:          # plotting is never reached (modplot < 0)
+        mpl = types.ModuleType('matplotlib')
+        mpl.pyplot = types.ModuleType('matplotlib.pyplot')
+        sys.modules['matplotlib'] = mpl
+        sys.modules['matplotlib.pyplot'] = mpl.pyplot
+    from MKM import MKM
+    out = {}
+    for conv in (0, 1):
+        N = (32, 16, 16)
+        c = MKM(N=N, Re=180., dt=0.001, conv=conv, modplot=-1, modsave=10**8, moderror=-1, filename='golden_mkm',
+                family='C', checkpoint=10**8, padding_factor=(1.5, 1.5, 1.5), timestepper='IMEXRK222')
+        t, tstep = c.initialize(from_checkpoint=False)
+        out[f'u0_conv{conv}'] = np.array(c.u_)
+        out[f'g0_conv{conv}'] = np.array(c.g_)
+        c.solve(t=t, tstep=tstep, end_time=0.001)
+        out[f'u1_conv{conv}'] = np.array(c.u_)
+        out[f'H1_conv{conv}'] = np.array(c.H_)
+        c.solve(t=0.001, tstep=1, end_time=0.003)
+        out[f'u3_conv{conv}'] = np.array(c.u_)
+        out[f'g3_conv{conv}'] = np.array(c.g_)
+    save('mkm_32_16_16', **out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or None
     fns = {k: v for k, v in globals().items() if callable(v) and getattr(v, '__module__', '') == '__main__'

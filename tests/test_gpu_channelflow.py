@@ -1,0 +1,25 @@
+"""Channel flow (BASELINE config 5, demo/MKM.py) at 32x16x16 against the reference's own run
+(tests/golden/mkm_32_16_16.npz): initial condition, one and three IMEXRK222 time steps, both
+convection forms."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l2
+from shenfun_b200.demos.channelflow import MKM
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('conv', [0, 1])
+def test_mkm_matches_reference(conv):
+    g = load_golden('mkm_32_16_16')
+    c = MKM(N=(32, 16, 16), Re=180., dt=0.001, conv=conv, padding_factor=(1.5, 1.5, 1.5), timestepper='IMEXRK222')
+    t, tstep = c.initialize()
+    assert rel_l2(c.u_.get(), g[f'u0_conv{conv}']) < 1e-12
+    assert rel_l2(c.g_.get(), g[f'g0_conv{conv}']) < 1e-12
+    t, tstep = c.solve(t=t, tstep=tstep, end_time=0.001)
+    assert rel_l2(c.H_.get(), g[f'H1_conv{conv}']) < 1e-10
+    assert rel_l2(c.u_.get(), g[f'u1_conv{conv}']) < 1e-10
+    t, tstep = c.solve(t=t, tstep=tstep, end_time=0.003)
+    assert rel_l2(c.u_.get(), g[f'u3_conv{conv}']) < 1e-10
+    assert rel_l2(c.g_.get(), g[f'g3_conv{conv}']) < 1e-9
