@@ -103,6 +103,23 @@ class Orthogonal(PolyBase):
             return {0: np.ones(len(k), dtype=k.dtype), 2: (-2.0*k-4)/(k+3), 4: (k+1.0)/(k+3)}
         return st
 
+    def closed_form_matrix(self, d_test, d_trial, trial):
+        """(phi_j^(4), phi_k)_w on the biharmonic basis (Shen 1995; the reference's SSBSBmat,
+        chebyshev/matrices.py:1429-1462): upper triangular, every even off-diagonal follows
+        8 (k+1)(k+2)(k(k+4) + 3(j+2)^2) pi / (j+3)."""
+        if (d_test, d_trial) == (0, 4) and trial.boundary_condition() == 'Biharmonic' \
+                and self.boundary_condition() == 'Biharmonic' and not self._scaled and not trial._scaled:
+            n = self.dim()
+            ki = np.arange(n, dtype=np.longdouble)
+            pi = np.longdouble('3.14159265358979323846264338327950288')
+            d = {0: np.asarray(pi*8*(ki+1)**2*(ki+2)*(ki+4), dtype=float)}
+            for off in range(2, n, 2):
+                k = ki[:-off]
+                j = ki[off:]
+                d[off] = np.asarray(8*(k+1)*(k+2)*(k*(k+4)+3*(j+2)**2)*pi/(j+3), dtype=float)
+            return d
+        return None
+
     # ---- device transforms ---------------------------------------------------------------------
     def _scalar_product_axis(self, u, out, outer, inner):
         offs, arrs = self._device_stencil()

@@ -346,9 +346,11 @@ class LinearFormOperator:
 
     def _wide_part(self, m1, scd, imag):
         n = m1.shape[0]
-        assert m1.shape[0] == m1.shape[1], 'wide 1-D matrices must be square'
         sc = float(np.real(m1.scale))
         offs = sorted(m1.keys())
+        if m1.shape[0] != m1.shape[1]:
+            # cross-basis matrices with a dense upper part (e.g. (phi_j', T_k)_w): tensor-core contraction
+            return ('dense', ops.as_device_tensor(np.ascontiguousarray(m1.diags())), scd, n, imag)
 
         def diag(off):
             v = np.zeros(n)
@@ -401,9 +403,13 @@ class LinearFormOperator:
                     ops.biharmonic_matvec(u, tmp, tab, sc, z, z, self.outer, self.inner, n, self.n_u)
                 else:
                     _, M, sc, n, imag = part
-                    assert self.n_u == self.n_out
-                    full = torch.zeros((self.n_out, self.n_u), dtype=torch.float64, device=u.device)
-                    full[:n, :n] = M
+                    if not hasattr(self, '_dense_cache'):
+                        self._dense_cache = {}
+                    full = self._dense_cache.get(id(M))
+                    if full is None:
+                        full = torch.zeros((self.n_out, self.n_u), dtype=torch.float64, device=u.device)
+                        full[:M.shape[0], :M.shape[1]] = M
+                        self._dense_cache[id(M)] = full
                     ops.gemm_axis(full, u, tmp, self.outer, self.inner)
                     shape = [self.outer, 1, self.inner]
                     tmp.view(self.outer, self.n_out, self.inner).mul_(sc.view(shape))

@@ -109,6 +109,14 @@ class Orthogonal(PolyBase):
             G = self._deriv_ld(N, d_test).T @ G
         return G, ld(1)
 
+    def closed_form_matrix(self, d_test, d_trial, trial):
+        """(phi_j^(4), phi_k) = 2 (2k+3)^2 (2k+5) delta_kj on the Legendre biharmonic basis (Shen 1994)."""
+        if (d_test, d_trial) == (0, 4) and trial.boundary_condition() == 'Biharmonic' \
+                and self.boundary_condition() == 'Biharmonic' and not self._scaled and not trial._scaled:
+            k = np.arange(self.dim(), dtype=float)
+            return {0: 2*(2*k+3)**2*(2*k+5)}
+        return None
+
     def boundary_values(self, n, order, side):
         n = np.asarray(n, dtype=float)
         sgn = 1.0 if side == 'right' else -1.0
