@@ -65,6 +65,15 @@ SHB_API int shb_fft_c2c_forward(const void *d_in, void *d_out, int64_t outer, in
 SHB_API int shb_fft_c2c_backward(const void *d_in, void *d_out, int64_t outer, int64_t inner,
                          int n_fft, int N, double scale, int flags, void *stream);
 
+/* Complex-to-real backward transform of the three components of a vector field fused with the
+ * cross product:  out = irfft_pad(in) x b  on [3][nlines][.] arrays (in: N//2+1 complex modes per
+ * line, b / out: n_fft reals per line).  The velocity never reaches HBM in physical space.
+ * Replaces `U = U_hat.backward(U); W[:] = np.cross(U, curl_, axis=0)` of demo/NavierStokes.py:39-40
+ * (utilities.cross, optimization/cython/cross.pyx:25-40).  SHB_ERR_UNSUPPORTED when no
+ * register-resident kernel covers n_fft (callers then run c2r and shb_cross3d separately). */
+SHB_API int shb_fft_c2r_cross(const void *d_in, const void *d_b, void *d_out, int64_t nlines, int n_fft,
+                              int N, double scale, int flags, void *stream);
+
 /* C2C transform fused with the local half of the slab all-to-all (replaces the pack /
  * unpack that mpi4py_fft.pencil.Transfer expresses as MPI sub-array datatypes; call sites
  * shenfun/tensorproductspace.py:89,183,252).  With chunk_rows = cr != 0 the rows of the

@@ -27,6 +27,18 @@ static int dispatch(int mode, const void *in, void *out, int64_t outer, int64_t 
 
 extern "C" {
 
+int shb_fft_c2r_cross(const void *d_in, const void *d_b, void *d_out, int64_t nlines, int n_fft, int N,
+                      double scale, int flags, void *stream) {
+    if (!d_in || !d_b || !d_out || d_b == d_out || nlines < 0 || n_fft < 1 || N < 1 || N > n_fft) {
+        set_error("fft_c2r_cross: bad arguments");
+        return SHB_ERR_ARG;
+    }
+    int rc = fft_c2r_cross_launch(d_in, d_b, d_out, nlines, n_fft, N, scale, flags,
+                                  reinterpret_cast<cudaStream_t>(stream));
+    if (rc == SHB_ERR_UNSUPPORTED) set_error("fft_c2r_cross: no fused kernel for n_fft=%d", n_fft);
+    return rc;
+}
+
 int shb_fft_c2c_peer(int backward, const void *d_in, void *const *d_peer_out, int nranks, int64_t outer,
                      int64_t inner, int n_fft, int N, double scale, int flags, int in_chunk_rows,
                      int out_chunk_rows, void *stream) {

@@ -55,6 +55,10 @@ struct DctArgs {
     const double *bc_lift;
 };
 
+// out = irfft(in) x b on [3][L][n] arrays (C2R of the three components fused with the cross product)
+int fft_c2r_cross_launch(const void *in, const void *b, void *out, int64_t L, int n_fft, int N, double scale,
+                         int flags, cudaStream_t st);
+
 // register-resident DCT kernels (strided axes, headline sizes); SHB_ERR_UNSUPPORTED otherwise
 int dct_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner, int n_phys, int n_spec,
                     double scale, const DctArgs &a, cudaStream_t st);

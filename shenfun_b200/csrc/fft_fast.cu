@@ -892,6 +892,167 @@ __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_cons
     }
 }
 
+// ---- kernel B, C2R fused with the cross product (Navier-Stokes nonlinear term) --------------
+// out = irfft(in) x b  on [3][L][n] arrays: a CTA transforms the three components of G spatial
+// lines, exchanges them through shared memory and writes W_c = U_{c+1} b_{c+2} - U_{c+2} b_{c+1}
+// directly, so the velocity never goes to HBM in physical space and the separate cross-product
+// pass (read 6, write 3 arrays of the padded size) disappears
+// (demo/NavierStokes.py:39-40: `U = U_hat.backward(U); W[:] = np.cross(U, curl_, axis=0)`).
+template <class SC, int G>
+__global__ void __launch_bounds__(SC::P * 3 * G) fft_c2r_cross_kernel(const __grid_constant__ FastDesc d,
+                                                                        const double *__restrict__ bvec,
+                                                                        const int64_t L) {
+    constexpr int M = SC::M, P = SC::P;
+    static_assert(P % 32 == 0, "a line is owned by whole warps");
+    static_assert(P == 32 || 3 * G <= 15, "one named barrier per line");
+    constexpr int LP = M + (M >> 3) + 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int j = threadIdx.x % P;
+    const int l = threadIdx.x / P;          // slot: 3*g + comp
+    const int g = l / 3, comp = l % 3;
+    cplx *sm_all = reinterpret_cast<cplx *>(smem_raw);
+    cplx *sm = sm_all + (size_t)l * LP;
+    const int64_t sp = (int64_t)blockIdx.x * G + g;      // spatial line
+    const bool valid = sp < L;
+    const int64_t line = (int64_t)comp * L + sp;
+    const int N = d.N;
+    const int n_fft = d.n_fft;
+    const bool padded = (N < n_fft);
+    const bool evenN = (N % 2 == 0);
+    const int h = N / 2;
+    const double scale = d.scale;
+    auto s = [&](int pos) -> cplx & { return sm[skew(pos)]; };
+    const GroupSync<P> sync{l + 1};
+
+    cplx v[SC::EMAX];
+    {
+        const cplx *__restrict__ in = reinterpret_cast<const cplx *>(d.in) + (valid ? line : 0) * d.n_in;
+        const int ns = h + 1;
+        const bool dd = (d.flags & 1) && !padded;
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q) {
+                cplx wq = make_double2(1.0, 0.0);
+                constexpr int HB = (SC::R0 + 1) / 2;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    cplx xa[HB], xb[HB];
+#pragma unroll
+                    for (int mm = 0; mm < HB; ++mm) {
+                        const int m = half * HB + mm;
+                        if (m < SC::R0) {
+                            const int n = (j + q * P) + m * SC::NB0;
+                            const int nm = M - n;
+                            xa[mm] = (valid && n < ns) ? in[n] : make_double2(0.0, 0.0);
+                            xb[mm] = (valid && nm < ns) ? in[nm] : make_double2(0.0, 0.0);
+                        }
+                    }
+#pragma unroll
+                    for (int mm = 0; mm < HB; ++mm) {
+                        const int m = half * HB + mm;
+                        if (m < SC::R0) {
+                            const int n = (j + q * P) + m * SC::NB0;
+                            const int nm = M - n;
+                            cplx xk = xa[mm], xc = xb[mm];
+                            if (dd && n >= N / 3) xk = make_double2(0.0, 0.0);
+                            if (dd && nm >= N / 3) xc = make_double2(0.0, 0.0);
+                            if (padded && evenN && n == ns - 1) xk = make_double2(0.5 * xk.x, 0.0);
+                            if (padded && evenN && nm == ns - 1) xc = make_double2(0.5 * xc.x, 0.0);
+                            if (n == 0) { xk.y = 0.0; xc.y = 0.0; }
+                            xc.y = -xc.y;
+                            const cplx sum = cadd(xk, xc), df = csub(xk, xc);
+                            cplx w;
+                            if constexpr (48 % (2 * SC::R0) == 0) {
+                                if (m == 0) wq = __ldg(&d.tw2[j + q * P]);
+                                w = root48_rt<48 / (2 * SC::R0)>(wq, m);
+                            } else {
+                                w = __ldg(&d.tw2[n]);
+                            }
+                            const cplx iw = make_double2(w.y, w.x);
+                            v[q * SC::R0 + m] = cadd(sum, cmul(iw, df));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    fft_stages<SC, true, true>(v, j, s, sync, d.tw);
+
+    // publish this component's real line (as pairs) for the other two components of the same g
+    __syncthreads();
+    if (j < SC::NBL) {
+#pragma unroll
+        for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) s((j + q * P) + m * SC::NBL) = cscale(v[q * SC::RL + m], scale);
+    }
+    __syncthreads();
+    if (j < SC::NBL && valid) {
+        const int c1 = (comp + 1) % 3, c2 = (comp + 2) % 3;
+        const cplx *u1 = sm_all + (size_t)(3 * g + c1) * LP;
+        const cplx *u2 = sm_all + (size_t)(3 * g + c2) * LP;
+        const double2 *__restrict__ b1 = reinterpret_cast<const double2 *>(bvec + ((int64_t)c1 * L + sp) * n_fft);
+        const double2 *__restrict__ b2 = reinterpret_cast<const double2 *>(bvec + ((int64_t)c2 * L + sp) * n_fft);
+        double2 *__restrict__ out = reinterpret_cast<double2 *>(
+            reinterpret_cast<double *>(d.out) + line * (int64_t)n_fft);
+#pragma unroll
+        for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) {
+                const int n = (j + q * P) + m * SC::NBL;
+                const double2 x1 = u1[skew(n)], x2 = u2[skew(n)];
+                const double2 w1 = b1[n], w2 = b2[n];
+                out[n] = make_double2(x1.x * w2.x - x2.x * w1.x, x1.y * w2.y - x2.y * w1.y);
+            }
+    }
+}
+
+template <class SC, int G>
+static int launch_c2r_cross(const FastDesc &d, const double *b, int64_t L, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(SC::M + (SC::M >> 3) + 2) * 3 * G * sizeof(cplx);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SHB_CUDA(cudaFuncSetAttribute(fft_c2r_cross_kernel<SC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        attr_set = true;
+    }
+    const int64_t ntiles = (L + G - 1) / G;
+    fft_c2r_cross_kernel<SC, G><<<(unsigned)ntiles, SC::P * 3 * G, smem, st>>>(d, b, L);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int fft_c2r_cross_launch(const void *in, const void *b, void *out, int64_t L, int n_fft, int N, double scale,
+                         int flags, cudaStream_t st) {
+    if (n_fft % 2) return SHB_ERR_UNSUPPORTED;
+    const int M = n_fft / 2;
+    FastDesc d;
+    d.in = in; d.out = out; d.outer = 3 * L; d.inner = 1; d.nlines = 3 * L;
+    d.n_fft = n_fft; d.N = N; d.flags = flags; d.scale = scale;
+    d.n_in = N / 2 + 1; d.n_out = n_fft;
+    d.in_cr = d.out_cr = 0; d.in_cs = d.out_cs = 0; d.use_peer = 0;
+    for (int p = 0; p < 8; ++p) d.out_peer[p] = nullptr;
+    if (L == 0) return SHB_OK;
+    static const int sizes[] = {32, 64, 128, 256, 384, 512, 768};
+    bool ok = false;
+    for (int x : sizes) ok = ok || (x == M);
+    if (!ok) return SHB_ERR_UNSUPPORTED;
+    d.tw = twiddle_table(0, M);
+    d.tw2 = twiddle_table(1, M);
+    if (!d.tw || !d.tw2) { set_error("fft: twiddle table allocation failed"); return SHB_ERR_NOMEM; }
+    const double *bb = reinterpret_cast<const double *>(b);
+    switch (M) {
+    case 32:  return launch_c2r_cross<Sched<32, 8, 4, 1, 32>, 2>(d, bb, L, st);
+    case 64:  return launch_c2r_cross<Sched<64, 8, 8, 1, 32>, 2>(d, bb, L, st);
+    case 128: return launch_c2r_cross<Sched<128, 8, 4, 4, 32>, 2>(d, bb, L, st);
+    case 256: return launch_c2r_cross<Sched<256, 8, 8, 4, 32>, 2>(d, bb, L, st);
+    case 384: return launch_c2r_cross<Sched<384, 8, 8, 6, 64>, 2>(d, bb, L, st);
+    case 512: return launch_c2r_cross<Sched<512, 8, 8, 8, 64>, 1>(d, bb, L, st);
+    case 768: return launch_c2r_cross<Sched<768, 12, 8, 8, 96>, 1>(d, bb, L, st);
+    }
+    return SHB_ERR_UNSUPPORTED;
+}
+
 // ---- host-side dispatch ---------------------------------------------------------------
 template <class SC, int MODE, int T, bool CH>
 static int launch_strided_ch(const FastDesc &d, cudaStream_t st) {

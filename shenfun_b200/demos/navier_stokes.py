@@ -86,6 +86,7 @@ class FusedNS:
         self.T, self.TV = make_spaces(N, comm)
         pad = abs(padding_factor-1) > 1e-8
         self.TVp = self.TV.get_dealiased((padding_factor,)*3) if pad else self.TV
+        self.Tp = self.TVp.flatten()[0]
         T = self.T
         self.K = [k.reshape(-1).contiguous() for k in T.local_wavenumbers(scaled=True, device=True)]
         self.U = sf.Array(self.TV)
@@ -117,8 +118,8 @@ class FusedNS:
         for rk in range(4):
             ops.curl_hat(uh, self.curl_hat.v, k0, k1, k2)
             self.TVp.backward(self.curl_hat, self.curl_p)
-            self.TVp.backward(self.U_hat, self.Up)
-            ops.cross3d(self.Up.v, self.curl_p.v, self.Up.v)        # W overwrites U (same index)
+            # W = backward(U_hat) x curl with the cross product fused into the last axis pass
+            self.Tp.backward_cross(self.U_hat, self.curl_p, self.Up)
             self.TVp.forward(self.Up, self.dU)
             ops.ns_rk_stage(dU, uh, U0, U1, self.P_hat.v if self.pressure else None, k0, k1, k2, nu,
                             self.a[rk]*dt, self.b[rk]*dt, rk == 3, keep_dU=False)

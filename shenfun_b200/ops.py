@@ -72,6 +72,12 @@ def fft_c2c_peer(backward, u, peer_ptrs, outer, inner, n_fft, N, scale, dealias_
           scale, int(dealias_direct), int(in_chunk), int(out_chunk), _lib.stream_ptr())
 
 
+def fft_c2r_cross(uh, b, out, nlines, n_fft, N, scale=1.0, dealias_direct=False):
+    """out = irfft(uh) x b for (3, nlines, .) arrays (C2R fused with the cross product)."""
+    _call('shb_fft_c2r_cross', _req(uh, C128, 'in'), _req(b, F64, 'b'), _req(out, F64, 'out'), nlines, n_fft, N,
+          scale, int(dealias_direct), _lib.stream_ptr())
+
+
 def fft_r2c_forward(u, out, outer, inner, n_fft, N, scale):
     _call('shb_fft_r2c_forward', _req(u, F64, 'in'), _req(out, C128, 'out'),
           outer, inner, n_fft, N, scale, _lib.stream_ptr())

@@ -87,8 +87,9 @@ class _Transform:
     def output_shape(self):
         return self.steps[-1].out_shape
 
-    def _run(self, u, out, ncomp):
+    def _run(self, u, out, ncomp, last_override=None):
         from ._lib import ShenB200Error
+        self._last_override = last_override
         try:
             return self._run_impl(u, out, ncomp)
         except ShenB200Error as e:
@@ -178,7 +179,9 @@ class _Transform:
                         nxt.exchange._peer_broken = True
                         kw.pop('peers', None)
                         peer_done = None
-                if bwd:
+                if i == n-1 and getattr(self, '_last_override', None) is not None:
+                    self._last_override(cur, dst, outer, inner)
+                elif bwd:
                     s.base._backward_axis(cur, dst, outer, inner, **kw)
                 else:
                     s.base._forward_axis(cur, dst, outer, inner,
@@ -336,6 +339,35 @@ class TensorProductSpace:
         self.forward = _Transform(self, fsteps, 'forward')
         self.backward = _Transform(self, bsteps, 'backward')
         self.scalar_product = _Transform(self, fsteps, 'scalar_product')
+
+    def backward_cross(self, u_hat, b, out):
+        """out = backward(u_hat) x b for three-component fields: the last (complex-to-real) axis
+        pass is fused with the cross product (`shb_fft_c2r_cross`), falling back to a separate
+        cross-product pass when no fused kernel covers the size.  u_hat: (3,)+spectral shape,
+        b / out: (3,)+physical shape (out may not alias b)."""
+        from ._lib import ShenB200Error
+        uh, bt, ot = ops.as_device_tensor(u_hat), ops.plain(b), ops.plain(out)
+        last = self.backward.steps[-1]
+        base = last.base
+        ok = (last.kind == 'axis' and base.family() == 'fourier' and base.short_name() == 'R2C'
+              and last.axis == self.dimensions-1 and not getattr(self, '_no_cross_fusion', False))
+        if ok:
+            def fused(cur, dst, outer, inner):
+                assert inner == 1 and outer % 3 == 0
+                ops.fft_c2r_cross(cur, bt, dst, outer//3, base.physical_len(), base.N, 1.0, base.dealias_direct)
+            try:
+                self.backward._run(uh if uh.is_contiguous() else uh.contiguous(), ot, 3, last_override=fused)
+                return out
+            except ShenB200Error as e:
+                if 'fft_c2r_cross' not in str(e):
+                    raise
+                self._no_cross_fusion = True
+            finally:
+                self.backward._last_override = None
+        tmp = torch.empty_like(ot)
+        self.backward._run(uh if uh.is_contiguous() else uh.contiguous(), tmp, 3)
+        ops.cross3d(tmp, bt, ot)
+        return out
 
     # ---- bookkeeping API (mpi4py_fft.PFFT + tensorproductspace.py:580-1180) ------------
     @property
