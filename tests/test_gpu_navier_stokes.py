@@ -73,3 +73,21 @@ def test_full_size_divergence_free_and_energy_decay():
     assert divu.abs().max().item() < 1e-13
     # dk/dt = -2 nu Omega, Omega = 3/8 for Taylor-Green at t=0 -> relative change ~ 6 nu dt
     assert 0 < (k0-k1)/k0 < 1e-5
+
+
+@pytest.mark.parametrize('N,pf', [((8, 8, 64), 1.0), ((6, 10, 128), 1.0), ((4, 6, 512), 1.5), ((4, 4, 256), 1.5),
+                                  ((8, 8, 20), 1.0)])
+def test_backward_fused_with_cross_product(N, pf):
+    """`backward_cross` (C2R + cross in one kernel; the last size falls back to two passes)
+    equals backward followed by numpy's cross product."""
+    rng = np.random.default_rng(5)
+    T, TV = ns.make_spaces(N)
+    TVp = TV.get_dealiased((pf,)*3) if pf > 1 else TV
+    Tp = TVp.flatten()[0]
+    vh = rng.standard_normal(TV.shape(True))+1j*rng.standard_normal(TV.shape(True))
+    b = rng.standard_normal(TVp.shape(False))
+    Uh = sf.Function(TV, buffer=vh)
+    ref = np.cross(TVp.backward(Uh).get(), b, axis=0)
+    out = sf.Array(TVp)
+    Tp.backward_cross(Uh, sf.Array(TVp, buffer=b), out)
+    assert rel_l2(out.get(), ref) < TOL
