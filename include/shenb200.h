@@ -124,9 +124,10 @@ SHB_API int shb_curl_hat(const void *d_u, void *d_out, const double *d_k0, const
 /* One Runge-Kutta stage of the triply periodic Navier-Stokes demo, fused:
  * pressure solve + gradient (demo/NavierStokes.py:41-43), viscous term and
  * the RK4 stage update (shenfun/utilities/integrators.py:590-598).
- * d_P may be NULL.  `last` bit 0: final stage (u_hat <- U1); bit 1: do not write dU back. */
+ * d_P may be NULL; d_curl (may be NULL) receives i k x u_hat of the UPDATED velocity, i.e. the
+ * curl the next stage starts from.  `last` bit 0: final stage (u_hat <- U1); bit 1: do not write dU back. */
 SHB_API int shb_ns_rk_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, void *d_P,
-                            const double *d_k0, const double *d_k1, const double *d_k2,
+                            void *d_curl, const double *d_k0, const double *d_k1, const double *d_k2,
                             int n0, int n1, int n2, double nu, double a_dt, double b_dt, int last,
                             void *stream);
 

@@ -84,8 +84,9 @@ __global__ void __launch_bounds__(PW_THREADS) curl_hat_kernel(
 //   U1   <- U1 + a_dt*dU ;  u_hat <- U0 + b_dt*dU (stages 0..2)  or  u_hat <- U1 (last stage)
 __global__ void __launch_bounds__(PW_THREADS) ns_rk_stage_kernel(
     cplx *__restrict__ dU, cplx *__restrict__ u_hat, const cplx *__restrict__ U0, cplx *__restrict__ U1,
-    cplx *__restrict__ P, const double *__restrict__ k0, const double *__restrict__ k1,
-    const double *__restrict__ k2, int n0, int n1, int n2, double nu, double a_dt, double b_dt, int last) {
+    cplx *__restrict__ P, cplx *__restrict__ curl_out, const double *__restrict__ k0,
+    const double *__restrict__ k1, const double *__restrict__ k2, int n0, int n1, int n2, double nu,
+    double a_dt, double b_dt, int last) {
     const int64_t n = (int64_t)n0 * n1 * n2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int i2 = (int)(i % n2);
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(PW_THREADS) ns_rk_stage_kernel(
         if (P) P[i] = p;
         const double kv[3] = {kx, ky, kz};
         const double lin = -nu * kk;
+        cplx un[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const cplx uh = u_hat[c * n + i];
@@ -115,11 +117,21 @@ __global__ void __launch_bounds__(PW_THREADS) ns_rk_stage_kernel(
             u1.y = fma(a_dt, d.y, u1.y);
             U1[c * n + i] = u1;
             if (last & 1) {
-                u_hat[c * n + i] = u1;
+                un[c] = u1;
             } else {
                 const cplx u0 = U0[c * n + i];
-                u_hat[c * n + i] = make_double2(fma(b_dt, d.x, u0.x), fma(b_dt, d.y, u0.y));
+                un[c] = make_double2(fma(b_dt, d.x, u0.x), fma(b_dt, d.y, u0.y));
             }
+            u_hat[c * n + i] = un[c];
+        }
+        if (curl_out) {
+            // curl of the updated velocity for the next stage: i k x u
+            const cplx cx = make_double2(ky * un[2].x - kz * un[1].x, ky * un[2].y - kz * un[1].y);
+            const cplx cy = make_double2(kz * un[0].x - kx * un[2].x, kz * un[0].y - kx * un[2].y);
+            const cplx cz = make_double2(kx * un[1].x - ky * un[0].x, kx * un[1].y - ky * un[0].y);
+            curl_out[i] = make_double2(-cx.y, cx.x);
+            curl_out[n + i] = make_double2(-cy.y, cy.x);
+            curl_out[2 * n + i] = make_double2(-cz.y, cz.x);
         }
     }
 }
@@ -196,14 +208,14 @@ int shb_curl_hat(const void *d_u, void *d_out, const double *d_k0, const double 
     return SHB_OK;
 }
 
-int shb_ns_rk_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, void *d_P,
+int shb_ns_rk_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, void *d_P, void *d_curl,
                     const double *d_k0, const double *d_k1, const double *d_k2, int n0, int n1, int n2,
                     double nu, double a_dt, double b_dt, int last, void *stream) {
     SHB_REQUIRE(d_dU && d_u_hat && d_U0 && d_U1 && d_k0 && d_k1 && d_k2, "null pointer");
     const int64_t n = (int64_t)n0 * n1 * n2;
     if (n == 0) return SHB_OK;
     ns_rk_stage_kernel<<<pw_blocks(n), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        (cplx *)d_dU, (cplx *)d_u_hat, (const cplx *)d_U0, (cplx *)d_U1, (cplx *)d_P, d_k0, d_k1, d_k2,
+        (cplx *)d_dU, (cplx *)d_u_hat, (const cplx *)d_U0, (cplx *)d_U1, (cplx *)d_P, (cplx *)d_curl, d_k0, d_k1, d_k2,
         n0, n1, n2, nu, a_dt, b_dt, last);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;

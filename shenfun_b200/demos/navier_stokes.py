@@ -102,10 +102,12 @@ class FusedNS:
         self.b = [0.5, 0.5, 1.0, 0.0]
         self.t = 0.0
         self.tstep = 0
+        self._curl_ready = False
 
     def initialize(self):
         taylor_green(self.TV, self.U)
         self.TV.forward(self.U, self.U_hat)
+        self._curl_ready = False
         return self
 
     def step(self):
@@ -116,13 +118,15 @@ class FusedNS:
         U1.copy_(uh)
         k0, k1, k2 = self.K
         for rk in range(4):
-            ops.curl_hat(uh, self.curl_hat.v, k0, k1, k2)
+            if not self._curl_ready:
+                ops.curl_hat(uh, self.curl_hat.v, k0, k1, k2)
             self.TVp.backward(self.curl_hat, self.curl_p)
             # W = backward(U_hat) x curl with the cross product fused into the last axis pass
             self.Tp.backward_cross(self.U_hat, self.curl_p, self.Up)
             self.TVp.forward(self.Up, self.dU)
             ops.ns_rk_stage(dU, uh, U0, U1, self.P_hat.v if self.pressure else None, k0, k1, k2, nu,
-                            self.a[rk]*dt, self.b[rk]*dt, rk == 3, keep_dU=False)
+                            self.a[rk]*dt, self.b[rk]*dt, rk == 3, keep_dU=False, curl_out=self.curl_hat.v)
+            self._curl_ready = True      # the stage kernel left i k x u_hat of the updated velocity
         self.t += dt
         self.tstep += 1
 

@@ -105,10 +105,11 @@ def curl_hat(u_hat, out, k0, k1, k2):
     return out
 
 
-def ns_rk_stage(dU, u_hat, U0, U1, P, k0, k1, k2, nu, a_dt, b_dt, last, keep_dU=True):
+def ns_rk_stage(dU, u_hat, U0, U1, P, k0, k1, k2, nu, a_dt, b_dt, last, keep_dU=True, curl_out=None):
     n0, n1, n2 = u_hat.shape[1:]
     _call('shb_ns_rk_stage', _req(dU, C128, 'dU'), _req(u_hat, C128, 'u_hat'), _req(U0, C128, 'U0'),
-          _req(U1, C128, 'U1'), None if P is None else _req(P, C128, 'P'), _req(k0, F64, 'k0'),
+          _req(U1, C128, 'U1'), None if P is None else _req(P, C128, 'P'),
+          None if curl_out is None else _req(curl_out, C128, 'curl_out'), _req(k0, F64, 'k0'),
           _req(k1, F64, 'k1'), _req(k2, F64, 'k2'), n0, n1, n2, float(nu), float(a_dt), float(b_dt),
           int(bool(last)) | (0 if keep_dU else 2), _lib.stream_ptr())
 
