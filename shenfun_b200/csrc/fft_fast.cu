@@ -685,6 +685,123 @@ int dct_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t 
     return mode == FFT_DCT2 ? dct2_fast(n_phys, d, st) : dct3_fast(n_phys, d, st);
 }
 
+// ---- kernel A, 3/2-rule zero-padded backward transform split by output residue -------------
+// Inverse DFT of length M = 3 M' of a line that holds N = 2 M' modes (rows M'+1 .. 2M'-1 of the
+// padded line are zero).  Writing the output index as n = 3 n1 + n2 turns it into three
+// independent M'-point inverse DFTs, one per residue n2, of the pre-twiddled sequence
+//     Z_n2[k'] = w^(n2 k') (X[k'] + f X[M'+k']),  w = e^(2 pi i / M),  f = e^(4 pi i n2 / 3)
+// (k' = 0 picks up the two halves of the split Nyquist mode: f = 1, -1/2, -1/2).  Each residue is
+// its own 256-thread CTA with the register-resident M'-point schedule (3 CTAs per SM instead of one
+// 768-thread CTA), the all-zero third of the padded line is never touched, and the input tile is
+// re-read from L2 by the two sibling CTAs.  Reference semantics: fourier/bases.py:579-593.
+template <class SC, int T, bool CH>
+__global__ void __launch_bounds__(SC::P *T, (SC::P * T <= 256 ? 3 : 1)) fft_strided_pad3_kernel(const __grid_constant__ FastDesc d) {
+    constexpr int MP = SC::M, P = SC::P;          // M' and threads per line
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *sm = reinterpret_cast<cplx *>(smem_raw);
+    const int c = threadIdx.x % T;
+    const int j = threadIdx.x / T;
+    const int n2 = blockIdx.x % 3;
+    const int64_t line = (int64_t)(blockIdx.x / 3) * T + c;
+    const bool valid = line < d.nlines;
+    const int64_t o = valid ? line / d.inner : 0, cc = valid ? line % d.inner : 0;
+    const cplx *__restrict__ inb = reinterpret_cast<const cplx *>(d.in);
+    cplx *__restrict__ outb = reinterpret_cast<cplx *>(d.out);
+    auto in_at = [&](int r) -> const cplx & {
+        if (CH && d.in_cr) {
+            const int p = r / d.in_cr;
+            return inb[p * d.in_cs + ((o * d.in_cr + (r - p * d.in_cr)) * d.inner + cc)];
+        }
+        return inb[(o * d.n_in + r) * d.inner + cc];
+    };
+    auto out_at = [&](int r) -> cplx & {
+        if (CH && d.out_cr) {
+            const int p = r / d.out_cr;
+            const int64_t off = (o * d.out_cr + (r - p * d.out_cr)) * d.inner + cc;
+            if (d.use_peer) return d.out_peer[p][off];
+            return outb[p * d.out_cs + off];
+        }
+        return outb[(o * d.n_out + r) * d.inner + cc];
+    };
+    // f = e^(4 pi i n2 / 3)
+    const double fr = (n2 == 0) ? 1.0 : -0.5;
+    const double fi = (n2 == 0) ? 0.0 : (n2 == 1 ? -0.86602540378443864676372317075294 : 0.86602540378443864676372317075294);
+
+    cplx v[SC::EMAX];
+    if (j < SC::NB0) {
+        cplx xa[SC::B0 * SC::R0], xb[SC::B0 * SC::R0];
+#pragma unroll
+        for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m) {
+                const int k = (j + q * P) + m * SC::NB0;
+                xa[q * SC::R0 + m] = valid ? in_at(k) : make_double2(0.0, 0.0);
+                xb[q * SC::R0 + m] = valid ? in_at(k + MP) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+        for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m) {
+                const int k = (j + q * P) + m * SC::NB0;
+                const cplx a = xa[q * SC::R0 + m], b = xb[q * SC::R0 + m];
+                cplx z;
+                if (k == 0) {
+                    const double f0 = (n2 == 0) ? 1.0 : -0.5;
+                    z = make_double2(fma(f0, b.x, a.x), fma(f0, b.y, a.y));
+                } else {
+                    z = make_double2(a.x + fr * b.x - fi * b.y, a.y + fr * b.y + fi * b.x);
+                    if (n2 > 0) z = cmulc(z, __ldg(&d.tw2[n2 * k]));      // * e^(+2 pi i n2 k / M)
+                }
+                v[q * SC::R0 + m] = z;
+            }
+    }
+    auto s = [&](int pos) -> cplx & { return sm[pos * T + c]; };
+    fft_stages<SC, true, true>(v, j, s, CtaSync(), d.tw);
+    const double scale = d.scale;
+    if (j < SC::NBL && valid) {
+#pragma unroll
+        for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::RL; ++m) {
+                const int n1 = (j + q * P) + m * SC::NBL;
+                out_at(3 * n1 + n2) = cscale(v[q * SC::RL + m], scale);
+            }
+    }
+}
+
+template <class SC, int T>
+static int launch_pad3(FastDesc d, cudaStream_t st) {
+    constexpr size_t smem = (size_t)SC::M * T * sizeof(cplx);
+    d.tw = twiddle_table(0, SC::M);
+    d.tw2 = twiddle_table(0, 3 * SC::M);         // e^(-2 pi i k / M): conjugated in the kernel
+    if (!d.tw || !d.tw2) { set_error("fft: twiddle table allocation failed"); return SHB_ERR_NOMEM; }
+    const int64_t ntiles = (d.nlines + T - 1) / T;
+    if (d.in_cr || d.out_cr) {
+        static bool a1 = false;
+        if (!a1) { SHB_CUDA(cudaFuncSetAttribute(fft_strided_pad3_kernel<SC, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); a1 = true; }
+        fft_strided_pad3_kernel<SC, T, true><<<(unsigned)(3 * ntiles), SC::P * T, smem, st>>>(d);
+    } else {
+        static bool a0 = false;
+        if (!a0) { SHB_CUDA(cudaFuncSetAttribute(fft_strided_pad3_kernel<SC, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); a0 = true; }
+        fft_strided_pad3_kernel<SC, T, false><<<(unsigned)(3 * ntiles), SC::P * T, smem, st>>>(d);
+    }
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+static const bool g_no_pad3 = getenv("SHB_FFT_NO_PAD3") != nullptr;
+
+// 3/2-rule backward with N == 2M/3, N even, no dealias_direct: residue-split kernel
+static int strided_pad3(int M, const FastDesc &d, cudaStream_t st) {
+    switch (M / 3) {
+    case 64:  return launch_pad3<Sched<64, 8, 8, 1, 8>, 8>(d, st);
+    case 128: return launch_pad3<Sched<128, 8, 4, 4, 32>, 8>(d, st);
+    case 256: return launch_pad3<Sched<256, 8, 8, 4, 32>, 8>(d, st);
+    case 512: return launch_pad3<Sched<512, 8, 8, 8, 64>, 8>(d, st);
+    default: return SHB_ERR_UNSUPPORTED;
+    }
+}
+
 // ---- kernel B ---------------------------------------------------------------------
 __device__ __forceinline__ int skew(int pos) { return pos + (pos >> 3); }
 
@@ -1206,6 +1323,10 @@ int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t 
     if (!d.tw || ((mode == FFT_R2C || mode == FFT_C2R) && !d.tw2)) {
         set_error("fft: twiddle table allocation failed");
         return SHB_ERR_NOMEM;
+    }
+    if (strided && mode == FFT_C2C_BWD && !g_no_pad3 && M % 3 == 0 && 3 * N == 2 * M && N % 2 == 0 && !(flags & 1)) {
+        const int rc = strided_pad3(M, d, st);
+        if (rc != SHB_ERR_UNSUPPORTED) return rc;
     }
     if (strided) return mode == FFT_C2C_FWD ? strided_fwd(M, d, st) : strided_bwd(M, d, st);
     switch (mode) {
