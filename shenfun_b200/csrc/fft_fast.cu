@@ -1206,6 +1206,7 @@ static int launch_strided_pipe(const FastDesc &d, cudaStream_t st) {
 }
 
 static const bool g_no_pipe = getenv("SHB_FFT_NO_PIPE") != nullptr;
+static const bool g_peer_t16 = getenv("SHB_PEER_T8") == nullptr;   // 256 B peer stores: +6% over 128 B on NVLink 5
 static const bool g_t4 = getenv("SHB_T4") != nullptr;
 
 template <class SC, int MODE, int T>
@@ -1244,7 +1245,8 @@ static int launch_contig(const FastDesc &d, cudaStream_t st) {
     case 64:   return launch_strided<Sched<64, 8, 8, 1, 8>, MODE, 8>(d, st);                        \
     case 128:  return launch_strided<Sched<128, 8, 4, 4, 32>, MODE, 8>(d, st);                      \
     case 256:  return launch_strided<Sched<256, 8, 8, 4, 32>, MODE, 8>(d, st);                      \
-    case 512:  return launch_strided<Sched<512, 8, 8, 8, 64>, MODE, 8>(d, st);                      \
+    case 512:  if (d.use_peer && g_peer_t16) return launch_strided_ch<Sched<512, 8, 8, 8, 64>, MODE, 16, true>(d, st); \
+               return launch_strided<Sched<512, 8, 8, 8, 64>, MODE, 8>(d, st);                      \
     case 1024: return launch_strided<Sched<1024, 16, 8, 8, 128>, MODE, 4>(d, st);                   \
     case 96:   return FIRSTWIDE ? launch_strided<Sched<96, 12, 8, 1, 12>, MODE, 8>(d, st)           \
                                 : launch_strided<Sched<96, 8, 12, 1, 12>, MODE, 8>(d, st);          \
