@@ -158,6 +158,10 @@ SHB_API int shb_banded_factor(int kl, int ku, int step, int nmat, const double *
                               int n, int64_t pin_line, void *stream);
 
 /* In-place forward/backward substitution on u[outer][n_u][inner] (first n rows).
+ * fac_shared: 0 = per-line factors in the batch layout above; 1 = one table [d][n];
+ * 2 = one table in the reference's scipy-DIA layout (data[d][j] holds the entry of COLUMN j,
+ * exactly what TDMA_LU / PDMA_LU / ... leave in `data`, shenfun/la.py:346-353); 3 = per-line
+ * DIA tables [line][d][n] (the `data` argument of SolverGeneric1ND_solve_data).
  * Replaces TDMA_Solve / PDMA_Solve / FDMA_Solve / TwoDMA / ThreeDMA / HeptaDMA /
  * DiagMA_Solve and SolverGeneric1ND_solve_data (la.pyx:371-611).             */
 SHB_API int shb_banded_solve(int kl, int ku, int step, void *d_u, const double *d_fac, int64_t outer,
@@ -172,14 +176,21 @@ SHB_API int shb_banded_matvec(const void *d_u, void *d_out, int nmat, int ndiag,
                               int is_complex, void *stream);
 
 /* Chebyshev-Galerkin Helmholtz (alfa*A + beta*B), per-line alfa/beta[outer*inner]:
- * factor into fac[4][outer][n][inner] = (d0, d1, d2, L) and solve.  Replaces
+ * factor into the four arrays d0, d1, d2, L, each [outer][n_fac][inner] with n_fac >= n rows
+ * along the axis (the reference allocates n + 2, chebyshev/la.py:270-274), and solve.
+ * `neumann` (factor) / flags bit 0 (solve): the reference's Neumann variant -- the caller passes
+ * the column-scaled diagonals (la.pyx:737-745), lines with |beta| < 1e-8 get d0[0] = 1, and the
+ * solve divides u_k by k^2 and zeroes the pinned mode (la.pyx:942-947).  flags bit 1 (solve): the
+ * four factor arrays are single lines [n_fac] shared by every line (Poisson_Solve_ADD).  Replaces
  * LU_Helmholtz / Solve_Helmholtz (chebyshev/la.py:131-351, la.pyx:708-947).   */
 SHB_API int shb_helmholtz_factor(const double *d_A0, const double *d_A2, const double *d_A4,
                                  const double *d_Bm2, const double *d_B0, const double *d_B2,
-                                 const double *d_alfa, const double *d_beta, double *d_fac, int64_t outer,
-                                 int64_t inner, int n, void *stream);
-SHB_API int shb_helmholtz_solve(const void *d_b, void *d_u, const double *d_fac, int64_t outer, int64_t inner,
-                                int n, int n_u, int is_complex, void *stream);
+                                 const double *d_alfa, const double *d_beta, double *d_d0, double *d_d1,
+                                 double *d_d2, double *d_L, int64_t outer, int64_t inner, int n, int n_fac,
+                                 int neumann, void *stream);
+SHB_API int shb_helmholtz_solve(const void *d_b, void *d_u, const double *d_d0, const double *d_d1,
+                                const double *d_d2, const double *d_L, int64_t outer, int64_t inner, int n,
+                                int n_fac, int n_u, int is_complex, int flags, void *stream);
 /* c = (alfa*A + beta*B) v with running sums over the constant rows of A; replaces
  * Helmholtz_matvec (optimization/cython/Matvec.pyx:656-712).                    */
 SHB_API int shb_helmholtz_matvec(const void *d_v, void *d_c, const double *d_A0, const double *d_A2,

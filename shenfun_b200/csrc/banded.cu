@@ -146,9 +146,15 @@ __global__ void __launch_bounds__(BD_THREADS) banded_solve_kernel(T *__restrict_
     if (line >= outer * inner) return;
     const int64_t o = line / inner, c = line % inner;
     T *x = u + (o * n_u) * inner + c;
+    // fac_shared: 0 = per line, batch layout [d][outer][n][inner];  1 = one table [d][n];
+    //             2 = one table in scipy DIA layout (entry of column j stored at [d][j], as
+    //                 the reference's X_LU leaves it);  3 = per line DIA, [line][d][n]
+    //                 (the `data` of SolverGeneric1ND_solve_data)
     const int64_t fs_i = fac_shared ? 1 : inner;                                   // between rows
     const int64_t fs_d = fac_shared ? (int64_t)n : outer * (int64_t)n * inner;     // between diagonals
-    const double *fac = fac_shared ? facp : facp + (o * n) * inner + c;
+    const double *fac = fac_shared == 0 ? facp + (o * n) * inner + c
+                      : fac_shared == 3 ? facp + line * (int64_t)(KL + 1 + KU) * n : facp;
+    const int sh = fac_shared >= 2 ? step : 0;      // DIA: L_p of row i sits at column i - p*step, U_q at i + q*step
     for (int par = 0; par < step; ++par) {
         // forward: y_i = b_i - sum_p L_p[i] y_{i-p*step}
         T w[KL > 0 ? KL : 1];
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(BD_THREADS) banded_solve_kernel(T *__restrict_
                 T y = x[(int64_t)i * inner];
 #pragma unroll
                 for (int p = 1; p <= KL; ++p)
-                    y = Num<T>::fnma(fac[(KL - p) * fs_d + i * fs_i], w[p - 1], y);
+                    if (i - p * step >= 0) y = Num<T>::fnma(fac[(KL - p) * fs_d + i * fs_i - p * sh], w[p - 1], y);
                 x[(int64_t)i * inner] = y;
 #pragma unroll
                 for (int p = KL - 1; p >= 1; --p) w[p] = w[p - 1];
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(BD_THREADS) banded_solve_kernel(T *__restrict_
             T y = x[(int64_t)i * inner];
 #pragma unroll
             for (int q = 1; q <= KU; ++q)
-                y = Num<T>::fnma(fac[(KL + q) * fs_d + i * fs_i], z[q - 1], y);
+                if (i + q * step < n) y = Num<T>::fnma(fac[(KL + q) * fs_d + i * fs_i + q * sh], z[q - 1], y);
             y = Num<T>::div(y, fac[KL * fs_d + i * fs_i]);
             x[(int64_t)i * inner] = y;
 #pragma unroll
@@ -241,58 +247,65 @@ __global__ void __launch_bounds__(256) banded_matvec_kernel(const T *__restrict_
 __global__ void __launch_bounds__(BD_THREADS) helmholtz_factor_kernel(
     const double *__restrict__ A0, const double *__restrict__ A2, const double *__restrict__ A4,
     const double *__restrict__ Bm2, const double *__restrict__ B0, const double *__restrict__ B2,
-    const double *__restrict__ alfa, const double *__restrict__ beta, double *__restrict__ fac,
-    int64_t outer, int64_t inner, int n) {
+    const double *__restrict__ alfa, const double *__restrict__ beta, double *__restrict__ fd0,
+    double *__restrict__ fd1, double *__restrict__ fd2, double *__restrict__ fL,
+    int64_t outer, int64_t inner, int n, int n_fac, int neumann) {
     const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= outer * inner) return;
     const int64_t o = line / inner, c = line % inner;
     const double al = alfa[line], be = beta[line];
-    const int64_t fs_d = outer * (int64_t)n * inner;
-    double *f = fac + (o * n) * inner + c;     // f[d*fs_d + i*inner]: d = 0:d0 1:d1 2:d2 3:L
+    const int64_t base = (o * n_fac) * inner + c;       // each factor array is [outer][n_fac][inner]
+    fd0 += base; fd1 += base; fd2 += base; fL += base;
     // two interleaved chains (even / odd rows)
     double pd0[2], pd1[2], pd2[2];
     for (int i = 0; i < n; ++i) {
         const int par = i & 1;
         double d0 = al * __ldg(&A0[i]) + be * __ldg(&B0[i]);
+        if (neumann && i == 0 && fabs(be) < 1e-8) d0 = 1.0;      // singular mode pinned (la.pyx:733-736)
         double d1 = (i < n - 2) ? al * __ldg(&A2[i]) + be * __ldg(&B2[i]) : 0.0;
         double d2 = (i < n - 4) ? al * __ldg(&A4[i]) : 0.0;
         if (i >= 2) {
             const double L = be * __ldg(&Bm2[i - 2]) / pd0[par];
-            f[3 * fs_d + (int64_t)(i - 2) * inner] = L;
+            fL[(int64_t)(i - 2) * inner] = L;
             d0 -= L * pd1[par];
             if (i < n - 2) d1 -= L * pd2[par];
             if (i < n - 4) d2 -= L * pd2[par];
         }
-        f[0 * fs_d + (int64_t)i * inner] = d0;
-        f[1 * fs_d + (int64_t)i * inner] = d1;
-        f[2 * fs_d + (int64_t)i * inner] = d2;
+        fd0[(int64_t)i * inner] = d0;
+        fd1[(int64_t)i * inner] = d1;
+        fd2[(int64_t)i * inner] = d2;
         pd0[par] = d0; pd1[par] = d1; pd2[par] = d2;
     }
     if (n >= 2) {
-        f[3 * fs_d + (int64_t)(n - 2) * inner] = 0.0;
-        f[3 * fs_d + (int64_t)(n - 1) * inner] = 0.0;
+        fL[(int64_t)(n - 2) * inner] = 0.0;
+        fL[(int64_t)(n - 1) * inner] = 0.0;
     } else if (n == 1) {
-        f[3 * fs_d] = 0.0;
+        fL[0] = 0.0;
     }
 }
 
 // Solve (la.pyx:871-947): y_i = b_i - L[i-2] y_{i-2};  u_i = (y_i - d1[i] u_{i+2} - d2[i] sum_{q>=2} u_{i+2q}) / d0[i]
 template <class T>
 __global__ void __launch_bounds__(BD_THREADS) helmholtz_solve_kernel(
-    const T *__restrict__ b, T *__restrict__ u, const double *__restrict__ fac, int64_t outer, int64_t inner,
-    int n, int n_u) {
+    const T *__restrict__ b, T *__restrict__ u, const double *__restrict__ fd0, const double *__restrict__ fd1,
+    const double *__restrict__ fd2, const double *__restrict__ fL, int64_t outer, int64_t inner,
+    int n, int n_fac, int n_u, int flags) {
     const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= outer * inner) return;
     const int64_t o = line / inner, c = line % inner;
-    const int64_t fs_d = outer * (int64_t)n * inner;
-    const double *f = fac + (o * n) * inner + c;
+    const bool shared = flags & 2, neumann = flags & 1;
+    const int64_t fi = shared ? 1 : inner;                 // factor stride between rows
+    if (!shared) {
+        const int64_t base = (o * n_fac) * inner + c;
+        fd0 += base; fd1 += base; fd2 += base; fL += base;
+    }
     const T *bl = b + (o * n_u) * inner + c;
     T *x = u + (o * n_u) * inner + c;
     T y[2] = {Num<T>::zero(), Num<T>::zero()};
     for (int i = 0; i < n; ++i) {
         const int par = i & 1;
         T v = bl[(int64_t)i * inner];
-        if (i >= 2) v = Num<T>::fnma(f[3 * fs_d + (int64_t)(i - 2) * inner], y[par], v);
+        if (i >= 2) v = Num<T>::fnma(fL[(int64_t)(i - 2) * fi], y[par], v);
         x[(int64_t)i * inner] = v;
         y[par] = v;
     }
@@ -301,12 +314,18 @@ __global__ void __launch_bounds__(BD_THREADS) helmholtz_solve_kernel(
     for (int i = n - 1; i >= 0; --i) {
         const int par = i & 1;
         T v = x[(int64_t)i * inner];
-        v = Num<T>::fnma(f[1 * fs_d + (int64_t)i * inner], un[par], v);
-        v = Num<T>::fnma(f[2 * fs_d + (int64_t)i * inner], sum[par], v);
-        v = Num<T>::div(v, f[0 * fs_d + (int64_t)i * inner]);
-        x[(int64_t)i * inner] = v;
+        v = Num<T>::fnma(fd1[(int64_t)i * fi], un[par], v);
+        v = Num<T>::fnma(fd2[(int64_t)i * fi], sum[par], v);
+        const double dd = fd0[(int64_t)i * fi];
+        v = Num<T>::div(v, dd);
         sum[par] = Num<T>::add(sum[par], un[par]);
         un[par] = v;
+        if (neumann) {
+            // unknowns were scaled by k^2; the pinned constant mode is zero (la.pyx:942-947)
+            if (i == 0) { if ((dd - 1.0) * (dd - 1.0) < 1e-16) v = Num<T>::zero(); }
+            else v = Num<T>::div(v, (double)i * (double)i);
+        }
+        x[(int64_t)i * inner] = v;
     }
 }
 
@@ -584,26 +603,29 @@ int shb_banded_matvec(const void *d_u, void *d_out, int nmat, int ndiag, const i
 
 int shb_helmholtz_factor(const double *d_A0, const double *d_A2, const double *d_A4, const double *d_Bm2,
                          const double *d_B0, const double *d_B2, const double *d_alfa, const double *d_beta,
-                         double *d_fac, int64_t outer, int64_t inner, int n, void *stream) {
-    SHB_REQUIRE(d_A0 && d_A2 && d_A4 && d_Bm2 && d_B0 && d_B2 && d_alfa && d_beta && d_fac && n >= 1, "bad arguments");
+                         double *d_d0, double *d_d1, double *d_d2, double *d_L, int64_t outer, int64_t inner,
+                         int n, int n_fac, int neumann, void *stream) {
+    SHB_REQUIRE(d_A0 && d_A2 && d_A4 && d_Bm2 && d_B0 && d_B2 && d_alfa && d_beta && d_d0 && d_d1 && d_d2 && d_L &&
+                n >= 1 && n_fac >= n, "bad arguments");
     if (outer * inner == 0) return SHB_OK;
     helmholtz_factor_kernel<<<bd_blocks(outer * inner), BD_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        d_A0, d_A2, d_A4, d_Bm2, d_B0, d_B2, d_alfa, d_beta, d_fac, outer, inner, n);
+        d_A0, d_A2, d_A4, d_Bm2, d_B0, d_B2, d_alfa, d_beta, d_d0, d_d1, d_d2, d_L, outer, inner, n, n_fac, neumann);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }
 
-int shb_helmholtz_solve(const void *d_b, void *d_u, const double *d_fac, int64_t outer, int64_t inner, int n,
-                        int n_u, int is_complex, void *stream) {
-    SHB_REQUIRE(d_b && d_u && d_fac && n >= 1 && n_u >= n, "bad arguments");
+int shb_helmholtz_solve(const void *d_b, void *d_u, const double *d_d0, const double *d_d1, const double *d_d2,
+                        const double *d_L, int64_t outer, int64_t inner, int n, int n_fac, int n_u, int is_complex,
+                        int flags, void *stream) {
+    SHB_REQUIRE(d_b && d_u && d_d0 && d_d1 && d_d2 && d_L && n >= 1 && n_u >= n && n_fac >= n, "bad arguments");
     if (outer * inner == 0) return SHB_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (is_complex)
         helmholtz_solve_kernel<cplx><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
-            (const cplx *)d_b, (cplx *)d_u, d_fac, outer, inner, n, n_u);
+            (const cplx *)d_b, (cplx *)d_u, d_d0, d_d1, d_d2, d_L, outer, inner, n, n_fac, n_u, flags);
     else
         helmholtz_solve_kernel<double><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
-            (const double *)d_b, (double *)d_u, d_fac, outer, inner, n, n_u);
+            (const double *)d_b, (double *)d_u, d_d0, d_d1, d_d2, d_L, outer, inner, n, n_fac, n_u, flags);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }

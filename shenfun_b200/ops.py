@@ -18,7 +18,8 @@ def as_device_tensor(x):
     if isinstance(x, torch.Tensor):
         t = plain(x)
     else:
-        t = torch.from_numpy(np.ascontiguousarray(x))
+        a = np.ascontiguousarray(x)
+        t = torch.from_numpy(a if a.flags.writeable else a.copy())
     if not t.is_cuda:
         if not torch.cuda.is_available():
             raise _lib.ShenB200Error('no CUDA device: shenfun_b200 has no CPU fallback')
@@ -164,15 +165,22 @@ def banded_matvec(u, out, offsets, mats, scales, outer, inner, n_rows, n_cols, n
           _lib.stream_ptr())
 
 
-def helmholtz_factor(A0, A2, A4, Bm2, B0, B2, alfa, beta, fac, outer, inner, n):
+def helmholtz_factor(A0, A2, A4, Bm2, B0, B2, alfa, beta, fac, outer, inner, n, n_fac=None, neumann=False):
+    """`fac` is either one packed tensor [4][outer][n][inner] or the four arrays (d0, d1, d2, L),
+    each [outer][n_fac][inner]."""
+    parts = [fac[i] for i in range(4)] if isinstance(fac, torch.Tensor) else list(fac)
+    n_fac = n if n_fac is None else n_fac
     _call('shb_helmholtz_factor', *[_req(t, F64, 'table') for t in (A0, A2, A4, Bm2, B0, B2, alfa, beta)],
-          _req(fac, F64, 'fac'), outer, inner, n, _lib.stream_ptr())
+          *[_req(t, F64, 'fac') for t in parts], outer, inner, n, n_fac, int(neumann), _lib.stream_ptr())
 
 
-def helmholtz_solve(b, u, fac, outer, inner, n, n_u):
+def helmholtz_solve(b, u, fac, outer, inner, n, n_u, n_fac=None, neumann=False, shared=False):
     assert b.dtype == u.dtype
-    _call('shb_helmholtz_solve', _req(b, b.dtype, 'b'), _req(u, u.dtype, 'u'), _req(fac, F64, 'fac'), outer, inner,
-          n, n_u, int(u.dtype.is_complex), _lib.stream_ptr())
+    parts = [fac[i] for i in range(4)] if isinstance(fac, torch.Tensor) else list(fac)
+    n_fac = n if n_fac is None else n_fac
+    _call('shb_helmholtz_solve', _req(b, b.dtype, 'b'), _req(u, u.dtype, 'u'), *[_req(t, F64, 'fac') for t in parts],
+          outer, inner, n, n_fac, n_u, int(u.dtype.is_complex), int(neumann) | (2 if shared else 0),
+          _lib.stream_ptr())
 
 
 def _stencil_args(soff, sten):

@@ -350,6 +350,175 @@ def channel_flow():
     save('mkm_32_16_16', **out)
 
 
+def plugin_kernels():
+    """The kernels the reference resolves BY NAME (optimization/__init__.py:47-84), called
+    directly from its numba module with the reference's positional signatures: banded LU and
+    solves, SolverGeneric1ND_solve_data, Helmholtz (Dirichlet and Neumann), Poisson_Solve_ADD,
+    the Chebyshev biharmonic trio, the matvecs and the recursive Legendre/Jacobi transforms."""
+    from shenfun.optimization import numba as ref
+    from shenfun import la
+    out = {}
+    N = 18
+    offs = {'TDMA': (-2, 0, 2), 'TDMA_O': (-1, 0, 1), 'PDMA': (-4, -2, 0, 2, 4), 'FDMA': (-2, 0, 2, 4),
+            'TwoDMA': (0, 2), 'ThreeDMA': (0, 2, 4), 'HeptaDMA': (-4, -2, 0, 2, 4, 6, 8), 'DiagMA': (0,)}
+
+    def rand_data(kind, lead=()):
+        o = offs[kind]
+        d = rng.uniform(-1, 1, lead+(len(o), N))
+        d[..., o.index(0), :] += 6.0          # diagonally dominant: LU without pivoting is stable
+        return d
+
+    for kind in offs:
+        data = rand_data(kind)
+        out[f'{kind}_data'] = data.copy()
+        lu = data.copy()
+        if hasattr(ref, f'{kind}_LU'):
+            getattr(ref, f'{kind}_LU')(lu)
+        out[f'{kind}_lu'] = lu.copy()
+        for axis in (0, 1, 2):
+            shape = [4, 5, 6]
+            shape[axis] = N
+            u = rng.standard_normal(shape)+1j*rng.standard_normal(shape)
+            out[f'{kind}_b{axis}'] = u.copy()
+            getattr(ref, f'{kind}_Solve')(u, lu, axis)
+            out[f'{kind}_u{axis}'] = u
+        ur = rng.standard_normal(N+2)          # real 1-D line, longer than the matrix
+        out[f'{kind}_b1d'] = ur.copy()
+        getattr(ref, f'{kind}_inner_solve')(ur, lu)
+        out[f'{kind}_u1d'] = ur
+    # SolverGeneric1ND_solve_data: per-line factors data[i, j] (la.py:1300-1319)
+    for kind in ('TDMA', 'PDMA', 'FDMA'):
+        for naxes in (0, 1, 2):
+            lines = (3, 4)
+            data = rand_data(kind, lines)
+            for i in range(lines[0]):
+                for j in range(lines[1]):
+                    getattr(ref, f'{kind}_LU')(data[i, j])
+            shape = list(lines)
+            shape.insert(naxes, N)
+            u = rng.standard_normal(shape)+1j*rng.standard_normal(shape)
+            out[f'g1nd_{kind}_{naxes}_data'] = data.copy()
+            out[f'g1nd_{kind}_{naxes}_b'] = u.copy()
+            ref.SolverGeneric1ND_solve_data(u, data, getattr(ref, f'{kind}_inner_solve'), naxes, True)
+            out[f'g1nd_{kind}_{naxes}_u'] = u
+    # Chebyshev Helmholtz, Dirichlet and Neumann (chebyshev/la.py:131-351)
+    Nc = 20
+    for tag, bc in (('D', (0, 0)), ('N', {'left': {'N': 0}, 'right': {'N': 0}})):
+        S = sf.FunctionSpace(Nc, 'C', bc=bc)
+        A = sf.inner(sf.Dx(sf.TrialFunction(S), 0, 2), sf.TestFunction(S))
+        B = sf.inner(sf.TrialFunction(S), sf.TestFunction(S))
+        B[2] = np.broadcast_to(B[2], A[2].shape)         # as the call site does, chebyshev/la.py:254-255
+        B[-2] = np.broadcast_to(B[-2], A[2].shape)
+        for k in (0, 2, 4):
+            out[f'helm{tag}_A{k}'] = np.broadcast_to(np.asarray(A[k], dtype=float), (A.shape[0]-k,)).copy()
+        for k in (-2, 0, 2):
+            out[f'helm{tag}_B{k}'] = np.broadcast_to(np.asarray(B[k], dtype=float), (B.shape[0]-abs(k),)).copy()
+        neumann = tag == 'N'
+        for axis in (0, 1, 2):
+            shape = [3, 4, 5]
+            shape[axis] = Nc
+            sshape = list(shape)
+            sshape[axis] = 1
+            alfa = rng.uniform(0.5, 1.5, sshape)
+            beta = -rng.uniform(0.5, 30.0, sshape)
+            if neumann:
+                # the singular constant mode (la.pyx:733-736).  Put it on the LAST line: the numba
+                # LU_Helmholtz_1D pins it by writing A_0[0] = 1/A_scale into the array shared by all
+                # lines (numba/helmholtz.py:74-76), which would leak into every later line; the Cython
+                # kernel works on per-call copies (la.pyx:726-736) and is the behaviour mirrored.
+                beta.flat[-1] = 0.0
+            d0, d1, d2, L = (np.zeros(shape) for _ in range(4))
+            ref.LU_Helmholtz(A, B, alfa, beta, neumann, d0, d1, d2, L, axis)
+            b = rng.standard_normal(shape)+1j*rng.standard_normal(shape)
+            sl = [slice(None)]*3
+            sl[axis] = slice(Nc-2, None)
+            b[tuple(sl)] = 0
+            u = np.zeros_like(b)
+            ref.Solve_Helmholtz(b.copy(), u, neumann, d0, d1, d2, L, axis)
+            for nm, arr in (('alfa', alfa), ('beta', beta), ('d0', d0), ('d1', d1), ('d2', d2), ('L', L), ('b', b), ('u', u)):
+                out[f'helm{tag}_{axis}_{nm}'] = arr
+            if not neumann:
+                c = np.zeros_like(b)
+                ref.Helmholtz_matvec(u, c, alfa, beta, A, B, axis)
+                out[f'helm{tag}_{axis}_matvec'] = c
+    # Poisson_Solve_ADD (chebyshev/la.py:13-30)
+    S = sf.FunctionSpace(Nc, 'C', bc=(0, 0))
+    A = sf.inner(sf.Dx(sf.TrialFunction(S), 0, 2), sf.TestFunction(S))
+    out['add_A0'] = np.asarray(A[0], dtype=float).copy()
+    out['add_A2'] = np.asarray(A[2], dtype=float).copy()
+    out['add_scale'] = np.array(float(A.scale))
+    for axis in (0, 1, 2):
+        shape = [3, 4, 5]
+        shape[axis] = Nc
+        b = rng.standard_normal(shape)+1j*rng.standard_normal(shape)
+        u = np.zeros_like(b)
+        u = ref.Poisson_Solve_ADD(A, b.copy(), u, axis)
+        out[f'add_{axis}_b'] = b
+        out[f'add_{axis}_u'] = u
+    # Chebyshev biharmonic (chebyshev/la.py:354-558)
+    Nb = 24
+    SBs = sf.FunctionSpace(Nb, 'C', bc=(0, 0, 0, 0))
+    u_, v_ = sf.TrialFunction(SBs), sf.TestFunction(SBs)
+    Sm = sf.inner(sf.Dx(u_, 0, 4), v_)
+    Am = sf.inner(sf.Dx(u_, 0, 2), v_)
+    Bm = sf.inner(u_, v_)
+    dg = {'sii': Sm[0], 'siu': Sm[2], 'siuu': Sm[4], 'ail': Am[-2], 'aii': Am[0], 'aiu': Am[2],
+          'bill': Bm[-4], 'bil': Bm[-2], 'bii': Bm[0], 'biu': Bm[2], 'biuu': Bm[4]}
+    names = list(dg)
+    for k in names:
+        out[f'bih_{k}'] = np.asarray(dg[k], dtype=float).copy()
+    M = Nb//2-2
+    for axis in (0, 1, 2):
+        shape = [3, 4, 5]
+        shape[axis] = Nb
+        sshape = list(shape)
+        sshape[axis] = 1
+        fshape = list(shape)
+        fshape[axis] = M
+        fshape = [2]+fshape
+        a0 = 1.3
+        alfa = -rng.uniform(0.5, 20.0, sshape)
+        beta = rng.uniform(0.5, 200.0, sshape)
+        u0, u1, u2, l0, l1, ak, bk = (np.zeros(fshape) for _ in range(7))
+        ref.LU_Biharmonic(a0, alfa, beta, *[dg[k] for k in names], u0, u1, u2, l0, l1, axis)
+        ref.Biharmonic_factor_pr(ak, bk, l0, l1, axis)
+        b = rng.standard_normal(shape)+1j*rng.standard_normal(shape)
+        sl = [slice(None)]*3
+        sl[axis] = slice(Nb-4, None)
+        b[tuple(sl)] = 0
+        u = np.zeros_like(b)
+        ref.Biharmonic_Solve(b.copy(), u, u0, u1, u2, l0, l1, ak, bk, a0, axis)
+        c = np.zeros_like(b)
+        ref.Biharmonic_matvec(u, c, a0, alfa, beta, *[dg[k] for k in names], axis)
+        for nm, arr in (('alfa', alfa), ('beta', beta), ('u0', u0), ('u1', u1), ('u2', u2), ('l0', l0), ('l1', l1),
+                        ('ak', ak), ('bk', bk), ('b', b), ('u', u), ('matvec', c)):
+            out[f'bih_{axis}_{nm}'] = arr
+        out['bih_a0'] = np.array(a0)
+    # recursive transforms: Legendre and a Jacobi family (spectralbase.py:448-491, 516-558)
+    for tag, S in (('leg', sf.FunctionSpace(20, 'L')), ('jac', sf.FunctionSpace(20, 'J', alpha=0.5, beta=-0.25)),
+                   ('chebu', sf.FunctionSpace(20, 'U'))):
+        x, w = S.points_and_weights()
+        a = np.array(S.get_recursion_matrix(S.N+3, S.N+3).diags('dia').data)
+        out[f'tr_{tag}_x'] = x
+        out[f'tr_{tag}_w'] = w
+        out[f'tr_{tag}_a'] = a
+        for axis in (0, 1, 2):
+            shape = [3, 4, 5]
+            shape[axis] = S.N
+            for dt in ('real', 'cplx'):
+                uin = rng.standard_normal(shape)
+                if dt == 'cplx':
+                    uin = uin+1j*rng.standard_normal(shape)
+                sp = np.zeros_like(uin)
+                ref.transforms.scalar_product(uin, sp, x, w, axis, a)
+                ev = np.zeros_like(uin)
+                ref.transforms.evaluate_expansion_all(sp, ev, x, axis, a)
+                out[f'tr_{tag}_{axis}_{dt}_in'] = uin
+                out[f'tr_{tag}_{axis}_{dt}_sp'] = sp
+                out[f'tr_{tag}_{axis}_{dt}_ev'] = ev
+    save('plugin', **out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or None
     fns = {k: v for k, v in globals().items() if callable(v) and getattr(v, '__module__', '') == '__main__'
