@@ -69,8 +69,12 @@ SHB_API int shb_fft_c2c_backward(const void *d_in, void *d_out, int64_t outer, i
  * cross product:  out = irfft_pad(in) x b  on [3][nlines][.] arrays (in: N//2+1 complex modes per
  * line, b / out: n_fft reals per line).  The velocity never reaches HBM in physical space.
  * Replaces `U = U_hat.backward(U); W[:] = np.cross(U, curl_, axis=0)` of demo/NavierStokes.py:39-40
- * (utilities.cross, optimization/cython/cross.pyx:25-40).  SHB_ERR_UNSUPPORTED when no
- * register-resident kernel covers n_fft (callers then run c2r and shb_cross3d separately). */
+ * (utilities.cross, optimization/cython/cross.pyx:25-40).  flags bit 0: dealias_direct; bit 1:
+ * `d_b` is itself a SPECTRAL vector field with the layout of `d_in` and is transformed in the same
+ * kernel (out = irfft_pad(in) x irfft_pad(b), `scale` applies to `in` only) -- then neither
+ * physical field reaches HBM: the whole of NavierStokes.py:35-41 after the x/y passes.
+ * SHB_ERR_UNSUPPORTED when no register-resident kernel covers n_fft (callers then run c2r and
+ * shb_cross3d separately). */
 SHB_API int shb_fft_c2r_cross(const void *d_in, const void *d_b, void *d_out, int64_t nlines, int n_fft,
                               int N, double scale, int flags, void *stream);
 

@@ -1015,18 +1015,21 @@ __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_cons
 // directly, so the velocity never goes to HBM in physical space and the separate cross-product
 // pass (read 6, write 3 arrays of the padded size) disappears
 // (demo/NavierStokes.py:39-40: `U = U_hat.backward(U); W[:] = np.cross(U, curl_, axis=0)`).
-template <class SC, int G>
-__global__ void __launch_bounds__(SC::P * 3 * G) fft_c2r_cross_kernel(const __grid_constant__ FastDesc d,
-                                                                        const double *__restrict__ bvec,
-                                                                        const int64_t L) {
+template <class SC, int G, bool DUAL>
+__global__ void __launch_bounds__(SC::P * (DUAL ? 6 : 3) * G) fft_c2r_cross_kernel(const __grid_constant__ FastDesc d,
+                                                                                    const double *__restrict__ bvec,
+                                                                                    const int64_t L) {
+    // DUAL: `bvec` is a second SPECTRAL vector field (same layout as d.in); both fields are
+    // transformed here (six lines per spatial line) and neither physical field reaches HBM.
     constexpr int M = SC::M, P = SC::P;
+    constexpr int NSL = DUAL ? 6 : 3;       // line slots per spatial line
     static_assert(P % 32 == 0, "a line is owned by whole warps");
-    static_assert(P == 32 || 3 * G <= 15, "one named barrier per line");
+    static_assert(P == 32 || NSL * G <= 15, "one named barrier per line");
     constexpr int LP = M + (M >> 3) + 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int j = threadIdx.x % P;
-    const int l = threadIdx.x / P;          // slot: 3*g + comp
-    const int g = l / 3, comp = l % 3;
+    const int l = threadIdx.x / P;          // slot: NSL*g + 3*field + comp
+    const int g = l / NSL, fld = (l % NSL) / 3, comp = l % 3;
     cplx *sm_all = reinterpret_cast<cplx *>(smem_raw);
     cplx *sm = sm_all + (size_t)l * LP;
     const int64_t sp = (int64_t)blockIdx.x * G + g;      // spatial line
@@ -1043,7 +1046,8 @@ __global__ void __launch_bounds__(SC::P * 3 * G) fft_c2r_cross_kernel(const __gr
 
     cplx v[SC::EMAX];
     {
-        const cplx *__restrict__ in = reinterpret_cast<const cplx *>(d.in) + (valid ? line : 0) * d.n_in;
+        const cplx *__restrict__ in = (DUAL && fld ? reinterpret_cast<const cplx *>(bvec)
+                                                   : reinterpret_cast<const cplx *>(d.in)) + (valid ? line : 0) * d.n_in;
         const int ns = h + 1;
         const bool dd = (d.flags & 1) && !padded;
         if (j < SC::NB0) {
@@ -1098,12 +1102,33 @@ __global__ void __launch_bounds__(SC::P * 3 * G) fft_c2r_cross_kernel(const __gr
     // publish this component's real line (as pairs) for the other two components of the same g
     __syncthreads();
     if (j < SC::NBL) {
+        const double sc = (DUAL && fld) ? 1.0 : scale;
 #pragma unroll
         for (int q = 0; q < SC::BL; ++q)
 #pragma unroll
-            for (int m = 0; m < SC::RL; ++m) s((j + q * P) + m * SC::NBL) = cscale(v[q * SC::RL + m], scale);
+            for (int m = 0; m < SC::RL; ++m) s((j + q * P) + m * SC::NBL) = cscale(v[q * SC::RL + m], sc);
     }
     __syncthreads();
+    if constexpr (DUAL) {
+        // out[comp] = a[c1] b[c2] - a[c2] b[c1], a = field 0, b = field 1, all six lines in shared
+        // memory; the two slots of a component each write half of its output line
+        if (valid) {
+            const int c1 = (comp + 1) % 3, c2 = (comp + 2) % 3;
+            const cplx *a1 = sm_all + (size_t)(NSL * g + c1) * LP;
+            const cplx *a2 = sm_all + (size_t)(NSL * g + c2) * LP;
+            const cplx *w1p = sm_all + (size_t)(NSL * g + 3 + c1) * LP;
+            const cplx *w2p = sm_all + (size_t)(NSL * g + 3 + c2) * LP;
+            double2 *__restrict__ out = reinterpret_cast<double2 *>(
+                reinterpret_cast<double *>(d.out) + line * (int64_t)n_fft);
+            for (int idx = j; idx < M / 2; idx += P) {
+                const int n = fld * (M / 2) + idx;
+                const double2 x1 = a1[skew(n)], x2 = a2[skew(n)];
+                const double2 w1 = w1p[skew(n)], w2 = w2p[skew(n)];
+                out[n] = make_double2(x1.x * w2.x - x2.x * w1.x, x1.y * w2.y - x2.y * w1.y);
+            }
+        }
+        return;
+    }
     if (j < SC::NBL && valid) {
         const int c1 = (comp + 1) % 3, c2 = (comp + 2) % 3;
         const cplx *u1 = sm_all + (size_t)(3 * g + c1) * LP;
@@ -1124,28 +1149,31 @@ __global__ void __launch_bounds__(SC::P * 3 * G) fft_c2r_cross_kernel(const __gr
     }
 }
 
-template <class SC, int G>
+template <class SC, int G, bool DUAL>
 static int launch_c2r_cross(const FastDesc &d, const double *b, int64_t L, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(SC::M + (SC::M >> 3) + 2) * 3 * G * sizeof(cplx);
+    constexpr int NSL = DUAL ? 6 : 3;
+    constexpr size_t smem = (size_t)(SC::M + (SC::M >> 3) + 2) * NSL * G * sizeof(cplx);
     static bool attr_set = false;
     if (!attr_set) {
-        SHB_CUDA(cudaFuncSetAttribute(fft_c2r_cross_kernel<SC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SHB_CUDA(cudaFuncSetAttribute(fft_c2r_cross_kernel<SC, G, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         attr_set = true;
     }
     const int64_t ntiles = (L + G - 1) / G;
-    fft_c2r_cross_kernel<SC, G><<<(unsigned)ntiles, SC::P * 3 * G, smem, st>>>(d, b, L);
+    fft_c2r_cross_kernel<SC, G, DUAL><<<(unsigned)ntiles, SC::P * NSL * G, smem, st>>>(d, b, L);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }
 
+// flags bit 0: dealias_direct; bit 1: `b` is a spectral vector field (both fields transformed here)
 int fft_c2r_cross_launch(const void *in, const void *b, void *out, int64_t L, int n_fft, int N, double scale,
                          int flags, cudaStream_t st) {
     if (n_fft % 2) return SHB_ERR_UNSUPPORTED;
     const int M = n_fft / 2;
+    const bool dual = flags & 2;
     FastDesc d;
     d.in = in; d.out = out; d.outer = 3 * L; d.inner = 1; d.nlines = 3 * L;
-    d.n_fft = n_fft; d.N = N; d.flags = flags; d.scale = scale;
+    d.n_fft = n_fft; d.N = N; d.flags = flags & 1; d.scale = scale;
     d.n_in = N / 2 + 1; d.n_out = n_fft;
     d.in_cr = d.out_cr = 0; d.in_cs = d.out_cs = 0; d.use_peer = 0;
     for (int p = 0; p < 8; ++p) d.out_peer[p] = nullptr;
@@ -1158,14 +1186,26 @@ int fft_c2r_cross_launch(const void *in, const void *b, void *out, int64_t L, in
     d.tw2 = twiddle_table(1, M);
     if (!d.tw || !d.tw2) { set_error("fft: twiddle table allocation failed"); return SHB_ERR_NOMEM; }
     const double *bb = reinterpret_cast<const double *>(b);
+    if (dual) {
+        switch (M) {
+        case 32:  return launch_c2r_cross<Sched<32, 8, 4, 1, 32>, 1, true>(d, bb, L, st);
+        case 64:  return launch_c2r_cross<Sched<64, 8, 8, 1, 32>, 1, true>(d, bb, L, st);
+        case 128: return launch_c2r_cross<Sched<128, 8, 4, 4, 32>, 1, true>(d, bb, L, st);
+        case 256: return launch_c2r_cross<Sched<256, 8, 8, 4, 32>, 1, true>(d, bb, L, st);
+        case 384: return launch_c2r_cross<Sched<384, 8, 8, 6, 64>, 1, true>(d, bb, L, st);
+        case 512: return launch_c2r_cross<Sched<512, 8, 8, 8, 64>, 1, true>(d, bb, L, st);
+        case 768: return launch_c2r_cross<Sched<768, 12, 8, 8, 96>, 1, true>(d, bb, L, st);
+        }
+        return SHB_ERR_UNSUPPORTED;
+    }
     switch (M) {
-    case 32:  return launch_c2r_cross<Sched<32, 8, 4, 1, 32>, 2>(d, bb, L, st);
-    case 64:  return launch_c2r_cross<Sched<64, 8, 8, 1, 32>, 2>(d, bb, L, st);
-    case 128: return launch_c2r_cross<Sched<128, 8, 4, 4, 32>, 2>(d, bb, L, st);
-    case 256: return launch_c2r_cross<Sched<256, 8, 8, 4, 32>, 2>(d, bb, L, st);
-    case 384: return launch_c2r_cross<Sched<384, 8, 8, 6, 64>, 2>(d, bb, L, st);
-    case 512: return launch_c2r_cross<Sched<512, 8, 8, 8, 64>, 1>(d, bb, L, st);
-    case 768: return launch_c2r_cross<Sched<768, 12, 8, 8, 96>, 1>(d, bb, L, st);
+    case 32:  return launch_c2r_cross<Sched<32, 8, 4, 1, 32>, 2, false>(d, bb, L, st);
+    case 64:  return launch_c2r_cross<Sched<64, 8, 8, 1, 32>, 2, false>(d, bb, L, st);
+    case 128: return launch_c2r_cross<Sched<128, 8, 4, 4, 32>, 2, false>(d, bb, L, st);
+    case 256: return launch_c2r_cross<Sched<256, 8, 8, 4, 32>, 2, false>(d, bb, L, st);
+    case 384: return launch_c2r_cross<Sched<384, 8, 8, 6, 64>, 2, false>(d, bb, L, st);
+    case 512: return launch_c2r_cross<Sched<512, 8, 8, 8, 64>, 1, false>(d, bb, L, st);
+    case 768: return launch_c2r_cross<Sched<768, 12, 8, 8, 96>, 1, false>(d, bb, L, st);
     }
     return SHB_ERR_UNSUPPORTED;
 }

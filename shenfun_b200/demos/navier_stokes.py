@@ -90,14 +90,16 @@ class FusedNS:
         T = self.T
         self.K = [k.reshape(-1).contiguous() for k in T.local_wavenumbers(scaled=True, device=True)]
         self.U = sf.Array(self.TV)
-        self.U_hat = sf.Function(self.TV)
+        # [U_hat; curl_hat] stacked: the nonlinear term transforms both in one batched backward
+        self._uw_hat = torch.zeros((6,)+tuple(self.TV.shape(True))[1:], dtype=torch.complex128,
+                                   device=self.K[0].device)
+        self.U_hat = sf.Function(self.TV, buffer=self._uw_hat[:3])
         self.U_hat0 = sf.Function(self.TV)
         self.U_hat1 = sf.Function(self.TV)
         self.dU = sf.Function(self.TV)
-        self.curl_hat = sf.Function(self.TV)
+        self.curl_hat = sf.Function(self.TV, buffer=self._uw_hat[3:])
         self.P_hat = sf.Function(T)
         self.Up = sf.Array(self.TVp)
-        self.curl_p = sf.Array(self.TVp)
         self.a = [1./6., 1./3., 1./3., 1./6.]
         self.b = [0.5, 0.5, 1.0, 0.0]
         self.t = 0.0
@@ -120,9 +122,9 @@ class FusedNS:
         for rk in range(4):
             if not self._curl_ready:
                 ops.curl_hat(uh, self.curl_hat.v, k0, k1, k2)
-            self.TVp.backward(self.curl_hat, self.curl_p)
-            # W = backward(U_hat) x curl with the cross product fused into the last axis pass
-            self.Tp.backward_cross(self.U_hat, self.curl_p, self.Up)
+            # W = backward(U_hat) x backward(curl_hat): one batched backward over the six spectral
+            # components, the last axis pass fused with the cross product (no physical U / curl)
+            self.Tp.backward_cross_hat(self._uw_hat, self.Up)
             self.TVp.forward(self.Up, self.dU)
             ops.ns_rk_stage(dU, uh, U0, U1, self.P_hat.v if self.pressure else None, k0, k1, k2, nu,
                             self.a[rk]*dt, self.b[rk]*dt, rk == 3, keep_dU=False, curl_out=self.curl_hat.v)

@@ -74,9 +74,11 @@ def fft_c2c_peer(backward, u, peer_ptrs, outer, inner, n_fft, N, scale, dealias_
 
 
 def fft_c2r_cross(uh, b, out, nlines, n_fft, N, scale=1.0, dealias_direct=False):
-    """out = irfft(uh) x b for (3, nlines, .) arrays (C2R fused with the cross product)."""
-    _call('shb_fft_c2r_cross', _req(uh, C128, 'in'), _req(b, F64, 'b'), _req(out, F64, 'out'), nlines, n_fft, N,
-          scale, int(dealias_direct), _lib.stream_ptr())
+    """out = irfft(uh) x b for (3, nlines, .) arrays (C2R fused with the cross product).  A complex
+    `b` is a second spectral field, transformed in the same kernel: out = irfft(uh) x irfft(b)."""
+    spectral_b = b.dtype == C128
+    _call('shb_fft_c2r_cross', _req(uh, C128, 'in'), _req(b, C128 if spectral_b else F64, 'b'), _req(out, F64, 'out'),
+          nlines, n_fft, N, scale, int(dealias_direct) | (2 if spectral_b else 0), _lib.stream_ptr())
 
 
 def fft_r2c_forward(u, out, outer, inner, n_fft, N, scale):

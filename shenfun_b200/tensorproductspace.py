@@ -369,6 +369,38 @@ class TensorProductSpace:
         ops.cross3d(tmp, bt, ot)
         return out
 
+    def backward_cross_hat(self, ab_hat, out):
+        """out = backward(a_hat) x backward(b_hat) with both spectral fields stacked in one
+        (6,)+spectral array `ab_hat` = [a_hat; b_hat]: the earlier axis passes run once over the six
+        components, the last pass transforms all six lines of a spatial line in one kernel and
+        writes only the cross product (`shb_fft_c2r_cross`, spectral `b`).  Falls back to
+        `backward` + `backward_cross` when no fused kernel covers the size."""
+        from ._lib import ShenB200Error
+        ab, ot = ops.as_device_tensor(ab_hat), ops.plain(out)
+        assert ab.shape[0] == 6 and ab.is_contiguous()
+        last = self.backward.steps[-1]
+        base = last.base
+        ok = (last.kind == 'axis' and base.family() == 'fourier' and base.short_name() == 'R2C'
+              and last.axis == self.dimensions-1 and not getattr(self, '_no_cross_fusion', False))
+        if ok:
+            def fused(cur, dst, outer, inner):
+                assert inner == 1 and outer % 6 == 0
+                half = cur.view(2, -1)
+                ops.fft_c2r_cross(half[0], half[1], dst, outer//6, base.physical_len(), base.N, 1.0,
+                                  base.dealias_direct)
+            try:
+                self.backward._run(ab, ot, 6, last_override=fused)
+                return out
+            except ShenB200Error as e:
+                if 'fft_c2r_cross' not in str(e):
+                    raise
+                self._no_cross_fusion = True
+            finally:
+                self.backward._last_override = None
+        bp = torch.empty_like(ot)
+        self.backward._run(ab[3:], bp, 3)
+        return self.backward_cross(ab[:3], bp, out)
+
     # ---- bookkeeping API (mpi4py_fft.PFFT + tensorproductspace.py:580-1180) ------------
     @property
     def dimensions(self):

@@ -91,3 +91,23 @@ def test_backward_fused_with_cross_product(N, pf):
     out = sf.Array(TVp)
     Tp.backward_cross(Uh, sf.Array(TVp, buffer=b), out)
     assert rel_l2(out.get(), ref) < TOL
+
+
+@pytest.mark.parametrize('N,pf', [((8, 8, 64), 1.0), ((6, 10, 128), 1.0), ((4, 6, 512), 1.5), ((4, 4, 256), 1.5),
+                                  ((4, 4, 1024), 1.5), ((6, 4, 1024), 1.0), ((8, 8, 20), 1.0)])
+def test_backward_of_two_fields_fused_with_cross_product(N, pf):
+    """`backward_cross_hat`: both spectral fields go through one batched backward and one
+    C2R-cross kernel (the last size falls back) == two backwards and numpy's cross product."""
+    import torch
+    rng = np.random.default_rng(6)
+    T, TV = ns.make_spaces(N)
+    TVp = TV.get_dealiased((pf,)*3) if pf > 1 else TV
+    Tp = TVp.flatten()[0]
+    ah = rng.standard_normal(TV.shape(True))+1j*rng.standard_normal(TV.shape(True))
+    bh = rng.standard_normal(TV.shape(True))+1j*rng.standard_normal(TV.shape(True))
+    ref = np.cross(TVp.backward(sf.Function(TV, buffer=ah)).get(), TVp.backward(sf.Function(TV, buffer=bh)).get(),
+                   axis=0)
+    ab = torch.from_numpy(np.concatenate([ah, bh], axis=0)).cuda()
+    out = sf.Array(TVp)
+    Tp.backward_cross_hat(ab, out)
+    assert rel_l2(out.get(), ref) < TOL
