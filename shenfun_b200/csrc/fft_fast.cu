@@ -769,6 +769,86 @@ __global__ void __launch_bounds__(SC::P *T, (SC::P * T <= 256 ? 3 : 1)) fft_stri
     }
 }
 
+template <class SC, int T, bool CH>
+__global__ void __launch_bounds__(SC::P *T, (SC::P * T <= 256 ? 2 : 1)) fft_strided_pad3x_kernel(const __grid_constant__ FastDesc d) {
+    constexpr int MP = SC::M, P = SC::P;          // M' and threads per line
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *sm = reinterpret_cast<cplx *>(smem_raw);
+    const int c = threadIdx.x % T;
+    const int j = threadIdx.x / T;
+    const int64_t line = (int64_t)blockIdx.x * T + c;
+    const bool valid = line < d.nlines;
+    const int64_t o = valid ? line / d.inner : 0, cc = valid ? line % d.inner : 0;
+    const cplx *__restrict__ inb = reinterpret_cast<const cplx *>(d.in);
+    cplx *__restrict__ outb = reinterpret_cast<cplx *>(d.out);
+    auto in_at = [&](int r) -> const cplx & {
+        if (CH && d.in_cr) {
+            const int p = r / d.in_cr;
+            return inb[p * d.in_cs + ((o * d.in_cr + (r - p * d.in_cr)) * d.inner + cc)];
+        }
+        return inb[(o * d.n_in + r) * d.inner + cc];
+    };
+    auto out_at = [&](int r) -> cplx & {
+        if (CH && d.out_cr) {
+            const int p = r / d.out_cr;
+            const int64_t off = (o * d.out_cr + (r - p * d.out_cr)) * d.inner + cc;
+            if (d.use_peer) return d.out_peer[p][off];
+            return outb[p * d.out_cs + off];
+        }
+        return outb[(o * d.n_out + r) * d.inner + cc];
+    };
+    // every thread keeps its 2 x EMAX inputs in registers and runs the three residue transforms
+    // (n2 = 0, 1, 2) back to back: the inputs are read from HBM/L2 once instead of three times
+    cplx xa[SC::B0 * SC::R0], xb[SC::B0 * SC::R0];
+    if (j < SC::NB0) {
+#pragma unroll
+        for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m) {
+                const int k = (j + q * P) + m * SC::NB0;
+                xa[q * SC::R0 + m] = valid ? in_at(k) : make_double2(0.0, 0.0);
+                xb[q * SC::R0 + m] = valid ? in_at(k + MP) : make_double2(0.0, 0.0);
+            }
+    }
+    auto s = [&](int pos) -> cplx & { return sm[pos * T + c]; };
+    const double scale = d.scale;
+#pragma unroll 1
+    for (int n2 = 0; n2 < 3; ++n2) {
+        // f = e^(4 pi i n2 / 3)
+        const double fr = (n2 == 0) ? 1.0 : -0.5;
+        const double fi = (n2 == 0) ? 0.0 : (n2 == 1 ? -0.86602540378443864676372317075294 : 0.86602540378443864676372317075294);
+        cplx v[SC::EMAX];
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int k = (j + q * P) + m * SC::NB0;
+                    const cplx a = xa[q * SC::R0 + m], b = xb[q * SC::R0 + m];
+                    cplx z;
+                    if (k == 0) {
+                        z = make_double2(fma(fr, b.x, a.x), fma(fr, b.y, a.y));
+                    } else {
+                        z = make_double2(a.x + fr * b.x - fi * b.y, a.y + fr * b.y + fi * b.x);
+                        if (n2 > 0) z = cmulc(z, __ldg(&d.tw2[n2 * k]));      // * e^(+2 pi i n2 k / M)
+                    }
+                    v[q * SC::R0 + m] = z;
+                }
+        }
+        fft_stages<SC, true, true>(v, j, s, CtaSync(), d.tw);
+        if (j < SC::NBL && valid) {
+#pragma unroll
+            for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m) {
+                    const int n1 = (j + q * P) + m * SC::NBL;
+                    out_at(3 * n1 + n2) = cscale(v[q * SC::RL + m], scale);
+                }
+        }
+        __syncthreads();      // shared exchange buffer is reused by the next residue
+    }
+}
+
 template <class SC, int T>
 static int launch_pad3(FastDesc d, cudaStream_t st) {
     constexpr size_t smem = (size_t)SC::M * T * sizeof(cplx);
@@ -776,7 +856,21 @@ static int launch_pad3(FastDesc d, cudaStream_t st) {
     d.tw2 = twiddle_table(0, 3 * SC::M);         // e^(-2 pi i k / M): conjugated in the kernel
     if (!d.tw || !d.tw2) { set_error("fft: twiddle table allocation failed"); return SHB_ERR_NOMEM; }
     const int64_t ntiles = (d.nlines + T - 1) / T;
-    if (d.in_cr || d.out_cr) {
+    // default: one CTA runs the three residues over register-held inputs (inputs read once);
+    // SHB_PAD3_SPLIT=1 selects the one-residue-per-CTA variant (inputs re-read through L2)
+    static const bool split = getenv("SHB_PAD3_SPLIT") != nullptr;
+    const bool ch = d.in_cr || d.out_cr;
+    if (!split) {
+        if (ch) {
+            static bool a1 = false;
+            if (!a1) { SHB_CUDA(cudaFuncSetAttribute(fft_strided_pad3x_kernel<SC, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); a1 = true; }
+            fft_strided_pad3x_kernel<SC, T, true><<<(unsigned)ntiles, SC::P * T, smem, st>>>(d);
+        } else {
+            static bool a0 = false;
+            if (!a0) { SHB_CUDA(cudaFuncSetAttribute(fft_strided_pad3x_kernel<SC, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); a0 = true; }
+            fft_strided_pad3x_kernel<SC, T, false><<<(unsigned)ntiles, SC::P * T, smem, st>>>(d);
+        }
+    } else if (ch) {
         static bool a1 = false;
         if (!a1) { SHB_CUDA(cudaFuncSetAttribute(fft_strided_pad3_kernel<SC, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); a1 = true; }
         fft_strided_pad3_kernel<SC, T, true><<<(unsigned)(3 * ntiles), SC::P * T, smem, st>>>(d);
@@ -801,6 +895,7 @@ static int strided_pad3(int M, const FastDesc &d, cudaStream_t st) {
     default: return SHB_ERR_UNSUPPORTED;
     }
 }
+
 
 // ---- kernel B ---------------------------------------------------------------------
 __device__ __forceinline__ int skew(int pos) { return pos + (pos >> 3); }
