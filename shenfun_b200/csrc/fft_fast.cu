@@ -1260,6 +1260,7 @@ static int launch_c2r_cross(const FastDesc &d, const double *b, int64_t L, cudaS
     return SHB_OK;
 }
 
+
 // flags bit 0: dealias_direct; bit 1: `b` is a spectral vector field (both fields transformed here)
 int fft_c2r_cross_launch(const void *in, const void *b, void *out, int64_t L, int n_fft, int N, double scale,
                          int flags, cudaStream_t st) {

@@ -94,7 +94,8 @@ def test_backward_fused_with_cross_product(N, pf):
 
 
 @pytest.mark.parametrize('N,pf', [((8, 8, 64), 1.0), ((6, 10, 128), 1.0), ((4, 6, 512), 1.5), ((4, 4, 256), 1.5),
-                                  ((4, 4, 1024), 1.5), ((6, 4, 1024), 1.0), ((8, 8, 20), 1.0)])
+                                  ((4, 4, 1024), 1.5), ((6, 4, 1024), 1.0), ((4, 6, 256), 1.0), ((6, 4, 512), 1.0),
+                                  ((8, 8, 20), 1.0)])
 def test_backward_of_two_fields_fused_with_cross_product(N, pf):
     """`backward_cross_hat`: both spectral fields go through one batched backward and one
     C2R-cross kernel (the last size falls back) == two backwards and numpy's cross product."""
