@@ -155,39 +155,80 @@ __global__ void __launch_bounds__(BD_THREADS) banded_solve_kernel(T *__restrict_
     const double *fac = fac_shared == 0 ? facp + (o * n) * inner + c
                       : fac_shared == 3 ? facp + line * (int64_t)(KL + 1 + KU) * n : facp;
     const int sh = fac_shared >= 2 ? step : 0;      // DIA: L_p of row i sits at column i - p*step, U_q at i + q*step
+    // The recurrence is serial along the line, but the right-hand side and the factor entries of
+    // later rows do not depend on it: rows are taken in batches of U whose loads are all issued
+    // before the dependent arithmetic, so a thread keeps U*(1+KL) (resp. U*(2+KU)) loads in flight
+    // instead of exposing the memory latency once per row.
+    constexpr int U = (KL + KU <= 4) ? 8 : 4;
     for (int par = 0; par < step; ++par) {
         // forward: y_i = b_i - sum_p L_p[i] y_{i-p*step}
         T w[KL > 0 ? KL : 1];
 #pragma unroll
         for (int p = 0; p < (KL > 0 ? KL : 1); ++p) w[p] = Num<T>::zero();
         if (KL > 0) {
-            for (int i = par; i < n; i += step) {
-                T y = x[(int64_t)i * inner];
+            for (int i0 = par; i0 < n; i0 += step * U) {
+                T bb[U];
+                double ll[U][KL > 0 ? KL : 1];
 #pragma unroll
-                for (int p = 1; p <= KL; ++p)
-                    if (i - p * step >= 0) y = Num<T>::fnma(fac[(KL - p) * fs_d + i * fs_i - p * sh], w[p - 1], y);
-                x[(int64_t)i * inner] = y;
+                for (int k = 0; k < U; ++k) {
+                    const int i = i0 + k * step;
+                    if (i < n) {
+                        bb[k] = x[(int64_t)i * inner];
 #pragma unroll
-                for (int p = KL - 1; p >= 1; --p) w[p] = w[p - 1];
-                w[0] = y;
+                        for (int p = 1; p <= KL; ++p)
+                            ll[k][p - 1] = (i - p * step >= 0) ? fac[(KL - p) * fs_d + i * fs_i - p * sh] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const int i = i0 + k * step;
+                    if (i < n) {
+                        T y = bb[k];
+#pragma unroll
+                        for (int p = 1; p <= KL; ++p) y = Num<T>::fnma(ll[k][p - 1], w[p - 1], y);
+                        x[(int64_t)i * inner] = y;
+#pragma unroll
+                        for (int p = KL - 1; p >= 1; --p) w[p] = w[p - 1];
+                        w[0] = y;
+                    }
+                }
             }
         }
         // backward: x_i = (y_i - sum_q U_q[i] x_{i+q*step}) / D[i]
         T z[KU > 0 ? KU : 1];
 #pragma unroll
         for (int q = 0; q < (KU > 0 ? KU : 1); ++q) z[q] = Num<T>::zero();
-        int last = par + ((n - 1 - par) / step) * step;
         if (n - 1 - par < 0) continue;
-        for (int i = last; i >= par; i -= step) {
-            T y = x[(int64_t)i * inner];
+        const int last = par + ((n - 1 - par) / step) * step;
+        for (int i0 = last; i0 >= par; i0 -= step * U) {
+            T bb[U];
+            double dg[U];
+            double uu[U][KU > 0 ? KU : 1];
 #pragma unroll
-            for (int q = 1; q <= KU; ++q)
-                if (i + q * step < n) y = Num<T>::fnma(fac[(KL + q) * fs_d + i * fs_i + q * sh], z[q - 1], y);
-            y = Num<T>::div(y, fac[KL * fs_d + i * fs_i]);
-            x[(int64_t)i * inner] = y;
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 - k * step;
+                if (i >= par) {
+                    bb[k] = x[(int64_t)i * inner];
+                    dg[k] = fac[KL * fs_d + i * fs_i];
 #pragma unroll
-            for (int q = KU - 1; q >= 1; --q) z[q] = z[q - 1];
-            if (KU > 0) z[0] = y;
+                    for (int q = 1; q <= KU; ++q)
+                        uu[k][q - 1] = (i + q * step < n) ? fac[(KL + q) * fs_d + i * fs_i + q * sh] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 - k * step;
+                if (i >= par) {
+                    T y = bb[k];
+#pragma unroll
+                    for (int q = 1; q <= KU; ++q) y = Num<T>::fnma(uu[k][q - 1], z[q - 1], y);
+                    y = Num<T>::div(y, dg[k]);
+                    x[(int64_t)i * inner] = y;
+#pragma unroll
+                    for (int q = KU - 1; q >= 1; --q) z[q] = z[q - 1];
+                    if (KU > 0) z[0] = y;
+                }
+            }
         }
     }
 }
@@ -301,31 +342,67 @@ __global__ void __launch_bounds__(BD_THREADS) helmholtz_solve_kernel(
     }
     const T *bl = b + (o * n_u) * inner + c;
     T *x = u + (o * n_u) * inner + c;
+    // rows in batches of U: all loads of a batch are issued before the serial arithmetic
+    constexpr int U = 8;
     T y[2] = {Num<T>::zero(), Num<T>::zero()};
-    for (int i = 0; i < n; ++i) {
-        const int par = i & 1;
-        T v = bl[(int64_t)i * inner];
-        if (i >= 2) v = Num<T>::fnma(fL[(int64_t)(i - 2) * fi], y[par], v);
-        x[(int64_t)i * inner] = v;
-        y[par] = v;
+    for (int i0 = 0; i0 < n; i0 += U) {
+        T bb[U];
+        double ll[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 + k;
+            if (i < n) {
+                bb[k] = bl[(int64_t)i * inner];
+                ll[k] = (i >= 2) ? fL[(int64_t)(i - 2) * fi] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 + k;
+            if (i < n) {
+                const int par = k & 1;          // U is even: parity of i0 + k == parity of k
+                T v = Num<T>::fnma(ll[k], y[par], bb[k]);
+                x[(int64_t)i * inner] = v;
+                y[par] = v;
+            }
+        }
     }
     T un[2] = {Num<T>::zero(), Num<T>::zero()};     // u_{i+2} per parity
     T sum[2] = {Num<T>::zero(), Num<T>::zero()};    // sum_{q>=2} u_{i+2q} per parity
-    for (int i = n - 1; i >= 0; --i) {
-        const int par = i & 1;
-        T v = x[(int64_t)i * inner];
-        v = Num<T>::fnma(fd1[(int64_t)i * fi], un[par], v);
-        v = Num<T>::fnma(fd2[(int64_t)i * fi], sum[par], v);
-        const double dd = fd0[(int64_t)i * fi];
-        v = Num<T>::div(v, dd);
-        sum[par] = Num<T>::add(sum[par], un[par]);
-        un[par] = v;
-        if (neumann) {
-            // unknowns were scaled by k^2; the pinned constant mode is zero (la.pyx:942-947)
-            if (i == 0) { if ((dd - 1.0) * (dd - 1.0) < 1e-16) v = Num<T>::zero(); }
-            else v = Num<T>::div(v, (double)i * (double)i);
+    // walk down from the last row in batches whose first row is odd-aligned so that parity is static
+    const int top = (n + 1) & ~1;                   // even, >= n
+    for (int i0 = top - 1; i0 >= 0; i0 -= U) {
+        T bb[U];
+        double e0[U], e1[U], e2[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 - k;
+            if (i >= 0 && i < n) {
+                bb[k] = x[(int64_t)i * inner];
+                e0[k] = fd0[(int64_t)i * fi];
+                e1[k] = fd1[(int64_t)i * fi];
+                e2[k] = fd2[(int64_t)i * fi];
+            }
         }
-        x[(int64_t)i * inner] = v;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 - k;
+            if (i >= 0 && i < n) {
+                const int par = (k & 1) ^ 1;    // i0 is odd
+                T v = bb[k];
+                v = Num<T>::fnma(e1[k], un[par], v);
+                v = Num<T>::fnma(e2[k], sum[par], v);
+                v = Num<T>::div(v, e0[k]);
+                sum[par] = Num<T>::add(sum[par], un[par]);
+                un[par] = v;
+                if (neumann) {
+                    // unknowns were scaled by k^2; the pinned constant mode is zero (la.pyx:942-947)
+                    if (i == 0) { if ((e0[k] - 1.0) * (e0[k] - 1.0) < 1e-16) v = Num<T>::zero(); }
+                    else v = Num<T>::div(v, (double)i * (double)i);
+                }
+                x[(int64_t)i * inner] = v;
+            }
+        }
     }
 }
 
@@ -433,38 +510,74 @@ __global__ void __launch_bounds__(BD_THREADS) biharmonic_solve_kernel(
     const double *f = fac + (o * n) * inner + c;
     const T *bl = b + (o * n_u) * inner + c;
     T *x = u + (o * n_u) * inner + c;
+    // rows in batches of U: all loads of a batch are issued before the serial arithmetic
+    constexpr int U = 4;
     for (int par = 0; par < 2; ++par) {
         T y1 = Num<T>::zero(), y2 = Num<T>::zero();
-        for (int i = par; i < n; i += 2) {
-            const int64_t r = (int64_t)i * inner;
-            T v = bl[r];
-            v = Num<T>::fnma(f[0 * fs + r], y1, v);
-            v = Num<T>::fnma(f[1 * fs + r], y2, v);
-            x[r] = v;
-            y2 = y1; y1 = v;
+        for (int i0 = par; i0 < n; i0 += 2 * U) {
+            T bb[U];
+            double l1[U], l2[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 + 2 * k;
+                if (i < n) {
+                    const int64_t r = (int64_t)i * inner;
+                    bb[k] = bl[r];
+                    l1[k] = f[0 * fs + r];
+                    l2[k] = f[1 * fs + r];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 + 2 * k;
+                if (i < n) {
+                    T v = bb[k];
+                    v = Num<T>::fnma(l1[k], y1, v);
+                    v = Num<T>::fnma(l2[k], y2, v);
+                    x[(int64_t)i * inner] = v;
+                    y2 = y1; y1 = v;
+                }
+            }
         }
         if (n - 1 - par < 0) continue;
         const int last = par + ((n - 1 - par) / 2) * 2;
         T x1 = Num<T>::zero(), x2 = Num<T>::zero(), x3 = Num<T>::zero();   // x_{i+2}, x_{i+4}, x_{i+6}
         T s1 = Num<T>::zero(), s2 = Num<T>::zero();
-        for (int i = last; i >= par; i -= 2) {
-            const int64_t r = (int64_t)i * inner;
-            // tail sums over j >= i+6: add x_{i+6} (j = i+6)
-            if (i + 6 <= last) {
-                const int j = i + 6;
-                const double w = 1.0 / (double)(j + 3);
-                const double jp2 = (double)(j + 2);
-                s1 = Num<T>::fnma(-w, x3, s1);
-                s2 = Num<T>::fnma(-(w * jp2 * jp2), x3, s2);
+        for (int i0 = last; i0 >= par; i0 -= 2 * U) {
+            T bb[U];
+            double g[U][5];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 - 2 * k;
+                if (i >= par) {
+                    const int64_t r = (int64_t)i * inner;
+                    bb[k] = x[r];
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) g[k][t] = f[(2 + t) * fs + r];
+                }
             }
-            T v = x[r];
-            v = Num<T>::fnma(f[3 * fs + r], x1, v);
-            v = Num<T>::fnma(f[4 * fs + r], x2, v);
-            v = Num<T>::fnma(f[5 * fs + r], s1, v);
-            v = Num<T>::fnma(f[6 * fs + r], s2, v);
-            v = Num<T>::div(v, f[2 * fs + r]);
-            x[r] = v;
-            x3 = x2; x2 = x1; x1 = v;
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int i = i0 - 2 * k;
+                if (i >= par) {
+                    // tail sums over j >= i+6: add x_{i+6} (j = i+6)
+                    if (i + 6 <= last) {
+                        const int j = i + 6;
+                        const double w = 1.0 / (double)(j + 3);
+                        const double jp2 = (double)(j + 2);
+                        s1 = Num<T>::fnma(-w, x3, s1);
+                        s2 = Num<T>::fnma(-(w * jp2 * jp2), x3, s2);
+                    }
+                    T v = bb[k];
+                    v = Num<T>::fnma(g[k][1], x1, v);
+                    v = Num<T>::fnma(g[k][2], x2, v);
+                    v = Num<T>::fnma(g[k][3], s1, v);
+                    v = Num<T>::fnma(g[k][4], s2, v);
+                    v = Num<T>::div(v, g[k][0]);
+                    x[(int64_t)i * inner] = v;
+                    x3 = x2; x2 = x1; x1 = v;
+                }
+            }
         }
     }
 }
