@@ -6,7 +6,10 @@ composite bases defined by their stencils (`ShenDirichlet` :476-554, `ShenNeuman
 transforms are DCT-II/III built on the complex FFT kernels, with the quadrature
 scaling, the Shen stencil recombination and zero-padding fused
 (`shb_cheb_scalar_product`, `shb_cheb_backward`); complex data is transformed in one
-pass.  Only quad='GC' (the reference default) is on the device path.
+pass.  quad='GC' (the reference default) takes that path; quad='GL' (Gauss-Lobatto points,
+DCT-I in the reference, chebyshev/bases.py:331-338, 349-353) is evaluated as the same quadrature
+sums through the fp64 tensor-core contraction (`shb_gemm_axis`) with the operator matrices built
+once on the host -- the route the Legendre bases take.
 """
 import numpy as np
 
@@ -20,8 +23,8 @@ class Orthogonal(PolyBase):
     def __init__(self, N, quad='GC', padding_factor=1, domain=(-1., 1.), dtype=float, dealias_direct=False,
                  bc=None, scaled=False, **kw):
         quad = 'GC' if quad is None else quad
-        if quad != 'GC':
-            raise NotImplementedError("Chebyshev quad='GC' only on the device path (DCT-I for 'GL' is not built)")
+        if quad not in ('GC', 'GL'):
+            raise NotImplementedError("Chebyshev quad='GC' or 'GL' on the device path")
         PolyBase.__init__(self, N, quad, padding_factor=padding_factor, domain=domain, dtype=dtype,
                           dealias_direct=dealias_direct, bc=bc, scaled=scaled)
 
@@ -37,6 +40,22 @@ class Orthogonal(PolyBase):
         """chebyshev/bases.py:201-216: x_j = cos(pi (2j+1)/(2N)), w = pi/N."""
         if N is None:
             N = self.physical_len()
+        if self.quad == 'GL':
+            # chebyshev/bases.py:206-210, 224-234: x_j = cos(pi j/(N-1)), end weights halved
+            import scipy.fft as sfft
+            points = np.cos(np.arange(N)*np.pi/(N-1))
+            if weighted:
+                weights = np.full(N, np.pi/(N-1))
+            else:
+                d = np.zeros(N)
+                k = 2*(1+np.arange((N-1)//2))
+                d[::2] = (2.0/(N-1))/np.hstack((1.0, 1.0-k*k))
+                weights = sfft.dct(d, type=1)
+            weights[0] *= 0.5
+            weights[-1] *= 0.5
+            if map_true_domain:
+                points = self.map_true_domain(points)
+            return points, weights
         points, weights = np.polynomial.chebyshev.chebgauss(N)
         points = points.astype(float)
         weights = weights.astype(float)
@@ -56,6 +75,8 @@ class Orthogonal(PolyBase):
         N = self.N if N is None else N
         h = np.full(N, np.pi/2)
         h[0] = np.pi
+        if self.quad == 'GL' and N == self.N:
+            h[-1] = np.pi           # discrete norm of T_{N-1} on the Lobatto points (bases.py:271-280)
         return h
 
     def ortho_deriv_matrix(self, N, k):
@@ -75,6 +96,8 @@ class Orthogonal(PolyBase):
         ld = np.longdouble
         c = np.ones(N, dtype=ld)
         c[0] = 2
+        if self.quad == 'GL' and N == self.N and d_test == 0 and d_trial == 0:
+            c[-1] = 2               # mass matrix with the Lobatto quadrature (matrices.py BSDSDmat: d[0][-1] = 1.5 pi)
         G = c[:, None]*self._deriv_ld(N, d_trial)
         if d_test > 0:
             G = self._deriv_ld(N, d_test).T @ G
@@ -121,13 +144,50 @@ class Orthogonal(PolyBase):
         return None
 
     # ---- device transforms ---------------------------------------------------------------------
+    def _gl_operators(self):
+        """Operator matrices of the Lobatto-point transforms.  Forward (N x Np): rows k < dim =
+        K (V^T W)/df, zero rows for the boundary dofs.  Backward (Np x N): V K^T on the dofs plus
+        the boundary functions on the bc rows.  V[j, k] = T_k(x_j) = cos(pi j k/(Np-1))."""
+        if 'gl_ops' not in self._tables:
+            F, B = self._gl_operators_host()
+            self._tables['gl_ops'] = (ops.as_device_tensor(F), ops.as_device_tensor(B))
+        return self._tables['gl_ops']
+
+    def _gl_operators_host(self):
+        if True:
+            Np = self.physical_len()
+            ld = np.longdouble
+            pi = ld('3.14159265358979323846264338327950288')
+            jk = np.outer(np.arange(Np), np.arange(self.N)) % (2*(Np-1))       # exact integer phase
+            V = np.cos(pi*jk.astype(ld)/(Np-1))
+            w = np.full(Np, pi/(Np-1))
+            w[0] /= 2
+            w[-1] /= 2
+            K = self.stencil_matrix().diags().astype(ld)             # (dim, N)
+            dim = self.dim()
+            F = np.zeros((self.N, Np), dtype=ld)
+            F[:dim] = K @ (V.T*w[None, :])/ld(float(self.domain_factor()))
+            B = np.zeros((Np, self.N), dtype=ld)
+            B[:, :dim] = V @ K.T
+            nbc = self.bcs.num_bcs()
+            if nbc and self.N >= 4:
+                L = self.bc_basis()                                   # (nbc, 4)
+                B[:, dim:] = V[:, :4] @ L[:, :4].T.astype(ld)
+            return np.ascontiguousarray(F.astype(np.float64)), np.ascontiguousarray(B.astype(np.float64))
+
     def _scalar_product_axis(self, u, out, outer, inner):
+        if self.quad == 'GL':
+            ops.gemm_axis(self._gl_operators()[0], u, out, outer, inner)
+            return
         offs, arrs = self._device_stencil()
         n = self.physical_len()
         scale = np.pi/(2*float(self.domain_factor())*n)
         ops.cheb_scalar_product(u, out, outer, inner, n, self.N, scale, self.dim(), offs, arrs)
 
     def _backward_axis(self, uh, out, outer, inner):
+        if self.quad == 'GL':
+            ops.gemm_axis(self._gl_operators()[1], uh, out, outer, inner)
+            return
         offs, arrs = self._device_stencil()
         nbc = self.bcs.num_bcs() if self.has_nonhomogeneous_bcs else 0
         lift = None

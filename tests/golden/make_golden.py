@@ -181,6 +181,41 @@ def poly_1d():
         save('poly1d_'+fam, **out)
 
 
+def poly_1d_gl():
+    """Chebyshev bases on the Gauss-Lobatto points (quad='GL': DCT-I in the reference,
+    chebyshev/bases.py:331-338, 349-353): scalar product, forward, backward, plain and padded,
+    plus the mass and stiffness matrices."""
+    out = {}
+    for name, bc in BCS.items():
+        for N in (16, 15):
+            S = sf.FunctionSpace(N, 'C', bc=bc, quad='GL') if bc is not None else sf.FunctionSpace(N, 'C', quad='GL')
+            tag = f'{name}_{N}'
+            u = rng.standard_normal(N)
+            out[f'u_{tag}'] = u
+            out[f'sp_{tag}'] = np.array(S.scalar_product(u.copy()))
+            uh = np.array(S.forward(u.copy()))
+            out[f'fw_{tag}'] = uh
+            vh = np.zeros(N)
+            vh[:S.dim()] = rng.standard_normal(S.dim())
+            if name == 'inhom':
+                vh[S.dim():] = uh[S.dim():]
+            out[f'vh_{tag}'] = vh
+            out[f'bw_{tag}'] = np.array(S.backward(vh.copy()))
+            Sp = S.get_dealiased(1.5)
+            out[f'bwpad_{tag}'] = np.array(Sp.backward(vh.copy()))
+            w = rng.standard_normal(Sp.shape(False))
+            out[f'w_{tag}'] = w
+            out[f'fwpad_{tag}'] = np.array(Sp.forward(w.copy()))
+            if N == 16:
+                for (a, b) in ((0, 0), (0, 2)):
+                    try:
+                        M = sf.SpectralMatrix((S, a), (S, b))
+                        out[f'M{a}{b}_{tag}'] = M.diags().toarray()
+                    except Exception as e:  # noqa: BLE001
+                        print('skip matrix GL', name, a, b, repr(e)[:80])
+    save('poly1d_CGL', **out)
+
+
 def poly_3d():
     """Chebyshev/Legendre x Fourier^2 tensor spaces, two axis orders, plain and 3/2-padded."""
     out = {}

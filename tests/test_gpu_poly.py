@@ -15,12 +15,19 @@ TOL = 1e-12
 NAMES = ['ortho', 'dirichlet', 'neumann', 'biharmonic', 'dn']
 
 
-@pytest.mark.parametrize('fam', ['C', 'L'])
+def _space1d(N, fam, bc):
+    """'CGL' = Chebyshev on the Gauss-Lobatto points (quad='GL')."""
+    if fam == 'CGL':
+        return sf.FunctionSpace(N, 'C', bc=bc, quad='GL')
+    return sf.FunctionSpace(N, fam, bc=bc)
+
+
+@pytest.mark.parametrize('fam', ['C', 'L', 'CGL'])
 @pytest.mark.parametrize('name', NAMES)
 @pytest.mark.parametrize('N', [16, 15])
 def test_1d_transforms_golden(fam, name, N):
     g = load_golden('poly1d_'+fam)
-    S = sf.FunctionSpace(N, fam, bc=BCS[name])
+    S = _space1d(N, fam, BCS[name])
     tag = f'{name}_{N}'
     d = S.dim()
     sp = S.scalar_product(g[f'u_{tag}']).cpu().numpy()
@@ -33,11 +40,11 @@ def test_1d_transforms_golden(fam, name, N):
     assert rel_l2(Sp.forward(g[f'w_{tag}']).cpu().numpy(), g[f'fwpad_{tag}']) < TOL
 
 
-@pytest.mark.parametrize('fam', ['C', 'L'])
+@pytest.mark.parametrize('fam', ['C', 'L', 'CGL'])
 @pytest.mark.parametrize('N', [16, 15])
 def test_1d_inhomogeneous_dirichlet(fam, N):
     g = load_golden('poly1d_'+fam)
-    S = sf.FunctionSpace(N, fam, bc=BCS['inhom'])
+    S = _space1d(N, fam, BCS['inhom'])
     tag = f'inhom_{N}'
     assert rel_l2(S.forward(g[f'u_{tag}']).cpu().numpy(), g[f'fw_{tag}']) < TOL
     assert rel_l2(S.backward(g[f'vh_{tag}']).cpu().numpy(), g[f'bw_{tag}']) < TOL
@@ -234,3 +241,21 @@ def test_chebyshev_biharmonic_larger_residual():
     x = H(sf.Function(T, buffer=f), sf.Function(T))
     c = H.matvec(x, sf.Function(T))
     assert rel_l2(c.get()[:SB.dim()], f[:SB.dim()]) < 1e-10
+
+
+def test_chebyshev_gauss_lobatto_in_a_tensor_product_space():
+    """quad='GL' along one axis of a 3-D space: forward o backward is the identity on the dofs and
+    the Lobatto points include both end points."""
+    SD = sf.FunctionSpace(20, 'C', bc=(0, 0), quad='GL')
+    K1 = sf.FunctionSpace(12, 'F', dtype='D')
+    K2 = sf.FunctionSpace(10, 'F', dtype='d')
+    T = sf.TensorProductSpace(sf.comm, (SD, K1, K2))
+    x = SD.points_and_weights()[0]
+    assert abs(x[0]-1) < 1e-15 and abs(x[-1]+1) < 1e-15
+    rng = np.random.default_rng(11)
+    vh = np.zeros(T.shape(True), dtype=complex)
+    vh[:SD.dim()] = rng.standard_normal((SD.dim(),)+tuple(T.shape(True)[1:]))
+    vh[:, :, 0] = vh[:, :, 0].real
+    u = T.backward(sf.Function(T, buffer=vh))
+    back = T.forward(T.backward(T.forward(u)))
+    assert rel_l2(back.get(), T.forward(u).get()) < TOL

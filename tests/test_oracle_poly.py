@@ -91,3 +91,27 @@ def test_oracle_chebyshev_biharmonic():
     u = ola.biharmonic_solve(S, A, B, np.ones((1, 1, 1)), -2*kk, kk**2, g['cheb_biharm_f'], 0)
     # LU of a matrix with condition number ~1e10 in two elimination orders: compare to cond*eps
     assert rel_l2(u, g['cheb_biharm_u']) < 1e-9
+
+
+@pytest.mark.parametrize('name', ['ortho', 'dirichlet', 'neumann', 'biharmonic', 'dn'])
+@pytest.mark.parametrize('N', [16, 15])
+def test_chebyshev_lobatto_operator_matrices_host(name, N):
+    """Host logic of quad='GL': the operator matrices handed to the device GEMM and the mass
+    matrix reproduce the reference's DCT-I based transforms (tests/golden/poly1d_CGL.npz)."""
+    import shenfun_b200 as sf
+    g = load_golden('poly1d_CGL')
+    S = sf.FunctionSpace(N, 'C', bc=BCS[name], quad='GL')
+    tag = f'{name}_{N}'
+    d = S.dim()
+    F, B = S._gl_operators_host()
+    sp = F @ g[f'u_{tag}']
+    assert rel_l2(sp[:d], g[f'sp_{tag}'][:d]) < 1e-13
+    assert rel_l2(B @ g[f'vh_{tag}'], g[f'bw_{tag}']) < 1e-13
+    Fp, Bp = S.get_dealiased(1.5)._gl_operators_host()
+    assert rel_l2(Bp @ g[f'vh_{tag}'], g[f'bwpad_{tag}']) < 1e-13
+    M = S.mass_matrix().diags()
+    fw = np.zeros(N)
+    fw[:d] = np.linalg.solve(M[:d, :d], sp[:d])
+    assert rel_l2(fw, g[f'fw_{tag}']) < 1e-12
+    if N == 16:
+        assert np.abs(M[:d, :d]-g[f'M00_{tag}'][:d, :d]).max() < 1e-13
