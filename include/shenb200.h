@@ -122,6 +122,12 @@ SHB_API int shb_cross3d(const void *d_a, const void *d_b, void *d_c, int64_t n, 
 /* out = i k x u on [3][n0][n1][n2] complex with per-axis wavenumber vectors:
  * what `project(curl(U_hat), TV)` evaluates for Fourier^3
  * (demo/NavierStokes.py:37; shenfun/fourier/matrices.py:149-176).          */
+/* Convective term in physical space, H_i = sum_j u_j * grad[3*i+j], on [3][n] / nine [n] real
+ * arrays (d_grad: HOST array of nine device pointers, d u_i / d x_j at index 3*i+j).  Replaces the
+ * products and sums of demo/ChannelFlow.py:213-215 (conv = 0). */
+SHB_API int shb_dot_grad3d(const double *d_u, const double *const *d_grad, double *d_out, int64_t n,
+                           void *stream);
+
 SHB_API int shb_curl_hat(const void *d_u, void *d_out, const double *d_k0, const double *d_k1,
                          const double *d_k2, int n0, int n1, int n2, void *stream);
 

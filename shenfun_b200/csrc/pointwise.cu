@@ -173,6 +173,24 @@ __global__ void __launch_bounds__(PW_THREADS) apply_mask_kernel(cplx *__restrict
     }
 }
 
+// H_i = sum_j u_j g[3 i + j]: the convective term u . grad u in physical space from the nine
+// gradient components (demo/ChannelFlow.py:213-215: three products and two sums per component
+// with numpy temporaries; here twelve arrays are read once and three written once).
+struct Grad9 { const double *p[9]; };
+__global__ void __launch_bounds__(PW_THREADS) dot_grad3d_kernel(const double *__restrict__ u, const Grad9 g,
+                                                                double *__restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double u0 = u[i], u1 = u[n + i], u2 = u[2 * n + i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double h = u0 * __ldg(&g.p[3 * c][i]);
+            h = fma(u1, __ldg(&g.p[3 * c + 1][i]), h);
+            h = fma(u2, __ldg(&g.p[3 * c + 2][i]), h);
+            out[c * n + i] = h;
+        }
+    }
+}
+
 }  // namespace shb
 
 using namespace shb;
@@ -193,6 +211,19 @@ int shb_cross3d(const void *d_a, const void *d_b, void *d_c, int64_t n, int is_c
         cross3d_real_tail_kernel<<<pw_blocks(n), PW_THREADS, 0, st>>>(
             (const double *)d_a, (const double *)d_b, (double *)d_c, n, 0);
     }
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_dot_grad3d(const double *d_u, const double *const *d_grad, double *d_out, int64_t n, void *stream) {
+    SHB_REQUIRE(d_u && d_grad && d_out && n >= 0, "bad arguments");
+    Grad9 g;
+    for (int k = 0; k < 9; ++k) {
+        SHB_REQUIRE(d_grad[k] != nullptr, "null gradient component");
+        g.p[k] = d_grad[k];
+    }
+    if (n == 0) return SHB_OK;
+    dot_grad3d_kernel<<<pw_blocks(n), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_u, g, d_out, n);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }

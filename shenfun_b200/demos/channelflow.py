@@ -110,12 +110,15 @@ class KMM:
         self.up = self.u_.backward(padding_factor=pf)
         up = self.up.v
         if self.conv == 0:
-            g = {}
+            g = []
             for name in ('dudx', 'dudy', 'dudz', 'dvdx', 'dvdy', 'dvdz', 'dwdx', 'dwdy', 'dwdz'):
-                g[name] = getattr(self, name)().backward(padding_factor=pf).v
-            self.TDp.forward(up[0]*g['dudx']+up[1]*g['dudy']+up[2]*g['dudz'], H[0])
-            self.TDp.forward(up[0]*g['dvdx']+up[1]*g['dvdy']+up[2]*g['dvdz'], H[1])
-            self.TDp.forward(up[0]*g['dwdx']+up[1]*g['dwdy']+up[2]*g['dwdz'], H[2])
+                g.append(ops.plain(getattr(self, name)().backward(padding_factor=pf).v).contiguous())
+            # u . grad u for the three components in one pass over the twelve physical arrays
+            if getattr(self, '_conv_work', None) is None or self._conv_work.shape != up.shape:
+                self._conv_work = torch.empty_like(ops.plain(up))
+            cb = ops.dot_grad3d(ops.plain(up), g, self._conv_work)
+            for i in range(3):
+                self.TDp.forward(cb[i], H[i])
         else:
             self.curly()
             self.curlz()

@@ -235,18 +235,35 @@ class Inner:
 
     def __call__(self):
         out = ops.plain(self.output_array)
-        out.zero_()
+        composite = self.space.is_composite_space
+        ncomp = out.shape[0] if composite else 1
+        written = [False]*ncomp          # the first term of a component overwrites: no zero fill
         for kind, ref, idx, op in self.parts:
             if kind == 'array':
                 tmp = self.space.scalar_product(ref, Function(self.space))
-                out.add_(ops.plain(tmp))
+                if all(written):
+                    out.add_(ops.plain(tmp))
+                else:
+                    for c in range(ncomp):
+                        dst = out[c] if composite else out
+                        src = ops.plain(tmp)[c] if composite else ops.plain(tmp)
+                        if written[c]:
+                            dst.add_(src)
+                        else:
+                            dst.copy_(src)
+                            written[c] = True
                 continue
             c0, c1 = idx
             src = ops.plain(ref)
             if ref.function_space().is_composite_space:
                 src = src[c1]
-            dst = out[c0] if self.space.is_composite_space else out
-            op.matvec(src, dst, accumulate=True)
+            dst = out[c0] if composite else out
+            k = c0 if composite else 0
+            op.matvec(src, dst, accumulate=written[k])
+            written[k] = True
+        for c in range(ncomp):
+            if not written[c]:
+                (out[c] if composite else out).zero_()
         return self.output_array
 
     def __add__(self, other):

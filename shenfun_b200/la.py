@@ -381,20 +381,27 @@ class LinearFormOperator:
         return ('dense', ops.as_device_tensor(np.ascontiguousarray(m1.diags())), scd, n, imag)
 
     def matvec(self, u, out, accumulate=False):
+        """out (+)= sum of the parts applied to u.  Without `accumulate` the first part overwrites
+        `out` (no separate zero fill, no temporary)."""
         u, out = ops.plain(u), ops.plain(out)
-        if not accumulate:
+        acc = bool(accumulate)
+        if not self.parts and not acc:
             out.zero_()
         for part in self.parts:
             kind = part[0]
             if kind == 'diag':
                 d = part[1]
-                out.addcmul_(u, d.to(u.dtype) if d.dtype != u.dtype else d)
+                d = d.to(u.dtype) if d.dtype != u.dtype else d
+                if acc:
+                    out.addcmul_(u, d)
+                else:
+                    torch.mul(u, d, out=out)
             elif kind == 'banded':
                 _, offs, tabs, scales, n_rows, n_cols, imag = part
                 ops.banded_matvec(u, out, offs, tabs, scales, self.outer, self.inner, n_rows, n_cols,
-                                  self.n_u, self.n_out, 1 | (2 if imag else 0))
+                                  self.n_u, self.n_out, (1 if acc else 0) | (2 if imag else 0))
             else:
-                tmp = torch.empty_like(out)
+                tmp = torch.empty_like(out) if acc else out
                 if kind == 'helm':
                     _, tabs, sc, z, n, imag = part
                     ops.helmholtz_matvec(u, tmp, tabs, sc, z, self.outer, self.inner, n, self.n_u)
@@ -413,7 +420,11 @@ class LinearFormOperator:
                     ops.gemm_axis(full, u, tmp, self.outer, self.inner)
                     shape = [self.outer, 1, self.inner]
                     tmp.view(self.outer, self.n_out, self.inner).mul_(sc.view(shape))
-                out.add_(tmp*1j if imag else tmp)
+                if acc:
+                    out.add_(tmp*1j if imag else tmp)
+                elif imag:
+                    out.mul_(1j)
+            acc = True
         return out
 
 

@@ -101,6 +101,14 @@ def cross3d(a, b, c):
     return c
 
 
+def dot_grad3d(u, grads, out):
+    """out[i] = sum_j u[j]*grads[3*i+j] on real (3, ...) arrays and nine (...) arrays."""
+    assert len(grads) == 9 and u.shape[0] == 3 and out.shape == u.shape
+    n = u[0].numel()
+    _call('shb_dot_grad3d', _req(u, F64, 'u'), _ptr_array(list(grads)), _req(out, F64, 'out'), n, _lib.stream_ptr())
+    return out
+
+
 def curl_hat(u_hat, out, k0, k1, k2):
     n0, n1, n2 = u_hat.shape[1:]
     _call('shb_curl_hat', _req(u_hat, C128, 'u_hat'), _req(out, C128, 'out'), _req(k0, F64, 'k0'),

@@ -23,3 +23,17 @@ def test_mkm_matches_reference(conv):
     t, tstep = c.solve(t=t, tstep=tstep, end_time=0.003)
     assert rel_l2(c.u_.get(), g[f"u3_conv{conv}"]) < 1e-11
     assert rel_l2(c.g_.get(), g[f"g3_conv{conv}"]) < 1e-11
+
+
+def test_dot_grad3d_kernel():
+    """H_i = sum_j u_j du_i/dx_j in one pass == the numpy expression of demo/ChannelFlow.py:213-215."""
+    import torch
+    from shenfun_b200 import ops
+    rng = np.random.default_rng(3)
+    shape = (5, 6, 7)
+    u = rng.standard_normal((3,)+shape)
+    g = [rng.standard_normal(shape) for _ in range(9)]
+    ref = np.stack([u[0]*g[3*i]+u[1]*g[3*i+1]+u[2]*g[3*i+2] for i in range(3)])
+    out = torch.empty((3,)+shape, dtype=torch.float64, device='cuda')
+    ops.dot_grad3d(torch.from_numpy(u).cuda(), [torch.from_numpy(x).cuda() for x in g], out)
+    assert np.abs(out.cpu().numpy()-ref).max() < 1e-14

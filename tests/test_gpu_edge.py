@@ -67,7 +67,7 @@ def test_shape_and_dtype_errors():
     with pytest.raises(AssertionError):
         sf.FunctionSpace(16, 'F', dtype='d', padding_factor=1.5, dealias_direct=True)
     with pytest.raises(NotImplementedError):
-        sf.FunctionSpace(16, 'C', quad='GL')
+        sf.FunctionSpace(16, 'C', quad='GU')
     lib = sf._lib.load()
     a = torch.zeros(8, dtype=torch.complex128, device='cuda')
     assert lib.shb_fft_c2c_forward(a.data_ptr(), a.data_ptr(), 1, 1, 12, 8, 1.0, None) == -1   # padded in place
