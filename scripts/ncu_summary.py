@@ -1,0 +1,53 @@
+"""Condense an `ncu --set full --csv --page raw` export into one line per launch."""
+import csv
+import re
+import sys
+
+rows = [r for r in csv.reader(open(sys.argv[1], newline='')) if len(r) > 20]
+hdr, units, data = rows[0], rows[1], rows[2:]
+
+
+def col(*subs):
+    for i, h in enumerate(hdr):
+        if all(s in h for s in subs):
+            return i
+    return None
+
+
+C = {
+    'time_ms': col('gpu__time_duration.sum'),
+    'rdGB': col('dram__bytes_read.sum') if col('dram__bytes_read.sum') is not None else None,
+    'wrGB': col('dram__bytes_write.sum'),
+    'dram%': col('dram__throughput.avg.pct_of_peak_sustained_elapsed'),
+    'regs': col('launch__registers_per_thread'),
+    'warps%': col('sm__warps_active.avg.pct_of_peak_sustained_active'),
+    'l1tex%': col('l1tex__throughput.avg.pct_of_peak_sustained'),
+    'lts%': col('lts__throughput.avg.pct_of_peak_sustained'),
+    'fp64%': col('sm__inst_executed_pipe_fp64', 'pct') if col('sm__inst_executed_pipe_fp64', 'pct') is not None
+    else col('pipe_fp64', 'pct'),
+    'grid': col('launch__grid_size'),
+    'block': col('launch__block_size'),
+}
+ki = col('Kernel Name')
+
+
+def val(r, name):
+    i = C[name]
+    if i is None:
+        return float('nan')
+    try:
+        v = float(r[i].replace(',', ''))
+    except ValueError:
+        return float('nan')
+    u = units[i]
+    if name == 'time_ms':
+        v *= {'ns': 1e-6, 'nsecond': 1e-6, 'us': 1e-3, 'usecond': 1e-3, 'ms': 1, 'msecond': 1, 's': 1e3, 'second': 1e3}.get(u, 1)
+    if name in ('rdGB', 'wrGB'):
+        v *= {'byte': 1e-9, 'Kbyte': 1e-6, 'Mbyte': 1e-3, 'Gbyte': 1}.get(u, 1e-9)
+    return v
+
+
+print('kernel | time_ms | rdGB | wrGB | dram% | regs | warps% | l1tex% | lts% | fp64% | grid | block')
+for r in data:
+    name = re.sub(r'\(.*', '', r[ki]).replace('shb::', '')[:90]
+    print(name, '|', ' | '.join(f'{val(r, k):.3f}' for k in C))
