@@ -282,6 +282,49 @@ __global__ void __launch_bounds__(256) banded_matvec_kernel(const T *__restrict_
     }
 }
 
+// Same product with the index arithmetic taken out of the inner loop: a thread owns one column
+// (line) and R consecutive rows, the grid carries (column block, row block, outer index), so no
+// 64-bit div/mod per element and the per-line scales are loaded once per R rows.  Used whenever
+// the batch index is the contiguous one (inner >= 32).
+template <class T, int R>
+__global__ void __launch_bounds__(128) banded_matvec_col_kernel(const T *__restrict__ u, T *__restrict__ out,
+                                                                const __grid_constant__ MatvecDesc d) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.inner) return;
+    const int64_t o = blockIdx.z;
+    const int i0 = blockIdx.y * R;
+    const int64_t line = o * d.inner + c;
+    const T *ul = u + (o * d.n_u) * d.inner + c;
+    T *ol = out + (o * d.n_out) * d.inner + c;
+    double s[BD_MAXMAT];
+#pragma unroll
+    for (int m = 0; m < BD_MAXMAT; ++m) s[m] = (m < d.nmat && d.scales[m]) ? d.scales[m][line] : 1.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r;
+        if (i >= d.n_out) break;
+        T acc = Num<T>::zero();
+        if (i < d.n_rows) {
+            for (int m = 0; m < d.nmat; ++m) {
+                T part = Num<T>::zero();
+                for (int k = 0; k < d.ndiag; ++k) {
+                    const int j = i + d.offs[k];
+                    if (j >= 0 && j < d.n_cols) {
+                        const double a = __ldg(&d.mats[m][k * d.n_rows + i]);
+                        part = Num<T>::fnma(-a, ul[(int64_t)j * d.inner], part);
+                    }
+                }
+                acc = Num<T>::fnma(-s[m], part, acc);
+            }
+        }
+        if (d.accumulate & 2) acc = times_i(acc);
+        T *dst = ol + (int64_t)i * d.inner;
+        if (d.accumulate & 1) *dst = Num<T>::add(*dst, acc);
+        else *dst = acc;
+    }
+}
+
+
 // ---- Chebyshev Helmholtz ------------------------------------------------------------------
 // (alfa*A + beta*B) u = b,  A: diagonals 0,2,4 with A[i, i+2q] = A4[i] for q >= 2 (constant rows),
 // B: diagonals -2, 0, 2.  Per line: forward recurrence for L, d0, d1, d2 (la.pyx:744-756).
@@ -704,6 +747,15 @@ int shb_banded_matvec(const void *d_u, void *d_out, int nmat, int ndiag, const i
     }
     const int64_t tot = outer * (int64_t)n_out * inner;
     if (tot == 0) return SHB_OK;
+    if (inner >= 32 && outer <= 65535) {
+        constexpr int R = 4;
+        dim3 grid((unsigned)((inner + 127) / 128), (unsigned)((n_out + R - 1) / R), (unsigned)outer);
+        cudaStream_t st2 = reinterpret_cast<cudaStream_t>(stream);
+        if (is_complex) banded_matvec_col_kernel<cplx, R><<<grid, 128, 0, st2>>>((const cplx *)d_u, (cplx *)d_out, d);
+        else banded_matvec_col_kernel<double, R><<<grid, 128, 0, st2>>>((const double *)d_u, (double *)d_out, d);
+        SHB_CUDA(cudaGetLastError());
+        return SHB_OK;
+    }
     int64_t blocks = (tot + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;
