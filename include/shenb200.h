@@ -185,6 +185,16 @@ SHB_API int shb_banded_matvec(const void *d_u, void *d_out, int nmat, int ndiag,
                               int64_t inner, int n_rows, int n_cols, int n_u, int n_out, int accumulate,
                               int is_complex, void *stream);
 
+/* Separable upper tail of a derivative matrix between Chebyshev bases:
+ *   out_k (+)= scale(line) * r[k] * sum_{j >= k + w, (j - k - w) even} t[j] * u_j,   k < n_rows,
+ * as running sums per parity (O(n) per line; rows n_rows..n_out-1 are zeroed unless accumulating).
+ * `accumulate` as in shb_banded_matvec.  Replaces the dense `SpectralMatrix.matvec` of the
+ * upper-triangular matrices (shenfun/matrixbase.py:87-144) and the specialised CDN/CTSD/... kernels
+ * of optimization/cython/Matvec.pyx:57-420. */
+SHB_API int shb_tail_matvec(const void *d_u, void *d_out, const double *d_r, const double *d_t,
+                            const double *d_scale, int w, int64_t outer, int64_t inner, int n_rows, int n_cols,
+                            int n_u, int n_out, int accumulate, int is_complex, void *stream);
+
 /* Chebyshev-Galerkin Helmholtz (alfa*A + beta*B), per-line alfa/beta[outer*inner]:
  * factor into the four arrays d0, d1, d2, L, each [outer][n_fac][inner] with n_fac >= n rows
  * along the axis (the reference allocates n + 2, chebyshev/la.py:270-274), and solve.

@@ -39,6 +39,7 @@ def _declare(lib):
         'shb_banded_factor': [i32, i32, i32, i32, vp, vp, vp, i64, i64, i32, i64, vp],
         'shb_banded_solve': [i32, i32, i32, vp, vp, i64, i64, i32, i32, i32, i32, vp],
         'shb_banded_matvec': [vp, vp, i32, i32, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, i32, vp],
+        'shb_tail_matvec': [vp, vp, vp, vp, vp, i32, i64, i64, i32, i32, i32, i32, i32, i32, vp],
         'shb_dot_grad3d': [vp, vp, vp, i64, vp],
         'shb_helmholtz_factor': [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp],
         'shb_helmholtz_solve': [vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, vp],

@@ -325,6 +325,59 @@ __global__ void __launch_bounds__(128) banded_matvec_col_kernel(const T *__restr
 }
 
 
+// Separable upper tail: out_k (+)= s(line) * r_k * sum_{j >= k + w, (j - k - w) even} t_j u_j.
+// Derivative matrices between Chebyshev bases are upper triangular with entries that depend on the
+// column only ((phi_j', T_k)_w = -2 pi for k < j, j + k odd) or on the row only (the Dirichlet
+// stiffness matrix): the product is a running sum per parity carried down the line, O(n) instead of
+// the O(n^2) dense contraction.  One thread per line, rows from the bottom up, the u values of eight
+// rows loaded ahead of the sums.
+template <class T>
+__global__ void __launch_bounds__(BD_THREADS) tail_matvec_kernel(const T *__restrict__ u, T *__restrict__ out,
+                                                                 const double *__restrict__ r,
+                                                                 const double *__restrict__ t,
+                                                                 const double *__restrict__ scale, int w,
+                                                                 int64_t outer, int64_t inner, int n_rows, int n_cols,
+                                                                 int n_u, int n_out, int accumulate) {
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= outer * inner) return;
+    const int64_t o = line / inner, c = line % inner;
+    const double s = scale ? scale[line] : 1.0;
+    const T *ul = u + (o * n_u) * inner + c;
+    T *ol = out + (o * n_out) * inner + c;
+    if (!(accumulate & 1))
+        for (int k = n_rows; k < n_out; ++k) ol[(int64_t)k * inner] = Num<T>::zero();
+    constexpr int U = 8;
+    T P[2] = {Num<T>::zero(), Num<T>::zero()};
+    for (int k0 = n_rows - 1; k0 >= 0; k0 -= U) {
+        T uu[U], old[U];
+        double tt[U], rr[U];
+#pragma unroll
+        for (int b = 0; b < U; ++b) {
+            const int k = k0 - b;
+            if (k >= 0) {
+                const int j = k + w;
+                const bool in = (j >= 0 && j < n_cols);
+                uu[b] = in ? ul[(int64_t)j * inner] : Num<T>::zero();
+                tt[b] = in ? __ldg(&t[j]) : 0.0;
+                rr[b] = __ldg(&r[k]);
+                if (accumulate & 1) old[b] = ol[(int64_t)k * inner];
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < U; ++b) {
+            const int k = k0 - b;
+            if (k >= 0) {
+                const int par = (k + w) & 1;
+                P[par] = Num<T>::fnma(-tt[b], uu[b], P[par]);
+                T acc = Num<T>::mul(s * rr[b], P[par]);
+                if (accumulate & 2) acc = times_i(acc);
+                ol[(int64_t)k * inner] = (accumulate & 1) ? Num<T>::add(old[b], acc) : acc;
+            }
+        }
+    }
+}
+
+
 // ---- Chebyshev Helmholtz ------------------------------------------------------------------
 // (alfa*A + beta*B) u = b,  A: diagonals 0,2,4 with A[i, i+2q] = A4[i] for q >= 2 (constant rows),
 // B: diagonals -2, 0, 2.  Per line: forward recurrence for L, d0, d1, d2 (la.pyx:744-756).
@@ -762,6 +815,24 @@ int shb_banded_matvec(const void *d_u, void *d_out, int nmat, int ndiag, const i
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (is_complex) banded_matvec_kernel<cplx><<<(unsigned)blocks, 256, 0, st>>>((const cplx *)d_u, (cplx *)d_out, d);
     else banded_matvec_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double *)d_u, (double *)d_out, d);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_tail_matvec(const void *d_u, void *d_out, const double *d_r, const double *d_t, const double *d_scale, int w,
+                    int64_t outer, int64_t inner, int n_rows, int n_cols, int n_u, int n_out, int accumulate,
+                    int is_complex, void *stream) {
+    SHB_REQUIRE(d_u && d_out && d_u != d_out && d_r && d_t && n_rows >= 1 && n_cols >= 1 && n_u >= n_cols &&
+                n_out >= n_rows, "bad arguments");
+    if (outer * inner == 0) return SHB_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (is_complex)
+        tail_matvec_kernel<cplx><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (const cplx *)d_u, (cplx *)d_out, d_r, d_t, d_scale, w, outer, inner, n_rows, n_cols, n_u, n_out, accumulate);
+    else
+        tail_matvec_kernel<double><<<bd_blocks(outer * inner), BD_THREADS, 0, st>>>(
+            (const double *)d_u, (double *)d_out, d_r, d_t, d_scale, w, outer, inner, n_rows, n_cols, n_u, n_out,
+            accumulate);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }

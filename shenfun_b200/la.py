@@ -349,7 +349,11 @@ class LinearFormOperator:
         sc = float(np.real(m1.scale))
         offs = sorted(m1.keys())
         if m1.shape[0] != m1.shape[1]:
-            # cross-basis matrices with a dense upper part (e.g. (phi_j', T_k)_w): tensor-core contraction
+            # cross-basis matrices with a dense upper part (e.g. (phi_j', T_k)_w): running sums when the
+            # tail is separable, else the tensor-core contraction
+            st = self._septail_part(m1, scd, imag)
+            if st is not None:
+                return st
             return ('dense', ops.as_device_tensor(np.ascontiguousarray(m1.diags())), scd, n, imag)
 
         def diag(off):
@@ -378,7 +382,23 @@ class LinearFormOperator:
                 tab = np.zeros((13, n))
                 tab[0], tab[1], tab[2], tab[3], tab[4] = diag(0), diag(2), diag(4), al, be
                 return ('bih', ops.as_device_tensor(tab), scd, zeros.new_zeros(scd.shape), n, imag)
+        st = self._septail_part(m1, scd, imag)
+        if st is not None:
+            return st
         return ('dense', ops.as_device_tensor(np.ascontiguousarray(m1.diags())), scd, n, imag)
+
+    def _septail_part(self, m1, scd, imag):
+        found = separable_tail(m1.diags())
+        if found is None:
+            return None
+        w, r, t, band = found
+        if len(band) > self.MAXDIAG:
+            return None
+        bpart = None
+        if band:
+            bpart = self._banded_part([(SparseMatrix(band, m1.shape, 1.0), scd)], imag)
+        return ('septail', bpart, int(w), ops.as_device_tensor(r), ops.as_device_tensor(t), scd,
+                m1.shape[0], m1.shape[1], imag)
 
     def matvec(self, u, out, accumulate=False):
         """out (+)= sum of the parts applied to u.  Without `accumulate` the first part overwrites
@@ -400,6 +420,15 @@ class LinearFormOperator:
                 _, offs, tabs, scales, n_rows, n_cols, imag = part
                 ops.banded_matvec(u, out, offs, tabs, scales, self.outer, self.inner, n_rows, n_cols,
                                   self.n_u, self.n_out, (1 if acc else 0) | (2 if imag else 0))
+            elif kind == 'septail':
+                _, bpart, w, r, t, sc, n_rows, n_cols, imag = part
+                if bpart is not None:
+                    _, offs, tabs, scales, _, _, _ = bpart
+                    ops.banded_matvec(u, out, offs, tabs, scales, self.outer, self.inner, n_rows, n_cols,
+                                      self.n_u, self.n_out, (1 if acc else 0) | (2 if imag else 0))
+                    acc = True
+                ops.tail_matvec(u, out, r, t, sc, w, self.outer, self.inner, n_rows, n_cols, self.n_u, self.n_out,
+                                (1 if acc else 0) | (2 if imag else 0))
             else:
                 tmp = torch.empty_like(out) if acc else out
                 if kind == 'helm':
@@ -426,6 +455,51 @@ class LinearFormOperator:
                     out.mul_(1j)
             acc = True
         return out
+
+
+
+def separable_tail(D, rtol=1e-12, min_tail=3):
+    """Structure of an upper-triangular derivative matrix: find the smallest offset w such that every
+    entry with j - k >= w on the parity class of w is r_k * t_j with r == 1 (column function) or
+    t == 1 (row function) and the other parity class is empty beyond w.  Returns (w, r, t, band) with
+    `band` = {offset: diagonal} for the offsets below w, or None when there is no such structure
+    (or the tail is shorter than `min_tail` diagonals and plain banded storage is just as good)."""
+    D = np.asarray(D, dtype=float)
+    n_rows, n_cols = D.shape
+    K, J = np.indices(D.shape)
+    off = J-K
+    amax = np.abs(D).max() if D.size else 0.0
+    if amax == 0:
+        return None
+    tol = rtol*amax
+    present = sorted(set(off[np.abs(D) > tol].tolist()))
+    for w in present:
+        if len([o for o in present if o >= w]) < min_tail:
+            break
+        other = (off > w) & ((off-w) % 2 == 1)
+        if np.any(np.abs(D[other]) > tol):
+            continue
+        tail = (off >= w) & ((off-w) % 2 == 0)
+        Dt = np.where(tail, D, np.nan)
+        r = t = None
+        with np.errstate(all='ignore'):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore', RuntimeWarning)
+                cmin, cmax = np.nanmin(Dt, axis=0), np.nanmax(Dt, axis=0)
+                rmin, rmax = np.nanmin(Dt, axis=1), np.nanmax(Dt, axis=1)
+        if np.all(np.isnan(cmax) | (cmax-cmin <= tol)):
+            t, r = np.nan_to_num(cmax), np.ones(n_rows)
+        elif np.all(np.isnan(rmax) | (rmax-rmin <= tol)):
+            r, t = np.nan_to_num(rmax), np.ones(n_cols)
+        if r is None:
+            continue
+        band = {}
+        for o in present:
+            if o < w:
+                band[o] = np.diagonal(D, o).copy()
+        return w, r, t, band
+    return None
 
 
 def _nondiagonal_axis(mats):

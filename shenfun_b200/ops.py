@@ -222,6 +222,14 @@ def gemm_axis(A, u, out, outer, inner):
           int(u.dtype.is_complex), _lib.stream_ptr())
 
 
+def tail_matvec(u, out, r, t, scale, w, outer, inner, n_rows, n_cols, n_u, n_out, accumulate):
+    """out_k (+)= scale * r_k * sum_{j >= k+w, same parity} t_j u_j (separable upper tail)."""
+    assert u.dtype == out.dtype
+    _call('shb_tail_matvec', _req(u, u.dtype, 'u'), _req(out, out.dtype, 'out'), _req(r, F64, 'r'), _req(t, F64, 't'),
+          None if scale is None else _req(scale, F64, 'scale'), int(w), outer, inner, n_rows, n_cols, n_u, n_out,
+          int(accumulate), int(u.dtype.is_complex), _lib.stream_ptr())
+
+
 def helmholtz_matvec(v, c, tabs, alfa, beta, outer, inner, n, n_u):
     assert v.dtype == c.dtype
     _call('shb_helmholtz_matvec', _req(v, v.dtype, 'v'), _req(c, c.dtype, 'c'), *[_req(t, F64, 'table') for t in tabs],

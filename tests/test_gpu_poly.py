@@ -259,3 +259,65 @@ def test_chebyshev_gauss_lobatto_in_a_tensor_product_space():
     u = T.backward(sf.Function(T, buffer=vh))
     back = T.forward(T.backward(T.forward(u)))
     assert rel_l2(back.get(), T.forward(u).get()) < TOL
+
+
+@pytest.mark.parametrize('name', ['CTSD', 'CTSB', 'CTT', 'CTSN', 'ASDSD'])
+@pytest.mark.parametrize('axis', [0, 1, 2])
+def test_separable_tail_matvec(name, axis):
+    """Upper-triangular Chebyshev derivative matrices applied as banded part + running sums
+    (`la.separable_tail`, `shb_tail_matvec`) == the dense product."""
+    from shenfun_b200 import ops
+    N = 40
+    TC = sf.FunctionSpace(N, 'C')
+    SD = sf.FunctionSpace(N, 'C', bc=(0, 0))
+    SB = sf.FunctionSpace(N, 'C', bc=(0, 0, 0, 0))
+    SN = sf.FunctionSpace(N, 'C', bc=BCS['neumann'])
+    test, trial, a, b = {'CTSD': (TC, SD, 0, 1), 'CTSB': (TC, SB, 0, 1), 'CTT': (TC, TC, 0, 1), 'CTSN': (TC, SN, 0, 1),
+                         'ASDSD': (SD, SD, 0, 2)}[name]
+    D = test.spectral_matrix(a, b, trial).diags()
+    w, r, t, band = la.separable_tail(D)
+    n_rows, n_cols = D.shape
+    rng = np.random.default_rng(4)
+    shape = [3, 4, 5]
+    shape[axis] = N
+    u = rng.standard_normal(shape)+1j*rng.standard_normal(shape)
+    sl = [slice(None)]*3
+    sl[axis] = slice(0, n_cols)
+    ref = np.zeros(shape, dtype=complex)
+    so = [slice(None)]*3
+    so[axis] = slice(0, n_rows)
+    ref[tuple(so)] = np.moveaxis(np.tensordot(D, np.moveaxis(u[tuple(sl)], axis, 0), axes=(1, 0)), 0, axis)
+    outer = int(np.prod(shape[:axis]))
+    inner = int(np.prod(shape[axis+1:]))
+    scale = rng.uniform(0.5, 2.0, outer*inner)
+    sshape = list(shape)
+    sshape[axis] = 1
+    ref = ref*scale.reshape(sshape)
+    ud = torch.from_numpy(u).cuda()
+    out = torch.full(shape, 7.0, dtype=torch.complex128, device='cuda')
+    sc = torch.from_numpy(scale).cuda()
+    acc = 0
+    if band:
+        offs = sorted(band)
+        tab = np.zeros((len(offs), n_rows))
+        for k, o in enumerate(offs):
+            v = band[o]
+            if o >= 0:
+                tab[k, :len(v)] = v
+            else:
+                tab[k, -o:-o+len(v)] = v
+        ops.banded_matvec(ud, out, offs, [torch.from_numpy(tab).cuda()], [sc], outer, inner, n_rows, n_cols, N, N, 0)
+        acc = 1
+    ops.tail_matvec(ud, out, torch.from_numpy(r).cuda(), torch.from_numpy(t).cuda(), sc, w, outer, inner, n_rows,
+                    n_cols, N, N, acc)
+    assert rel_l2(out.cpu().numpy(), ref) < TOL
+    # times-i flag on top of an existing array
+    out2 = torch.from_numpy(ref.copy()).cuda()
+    ops.tail_matvec(ud, out2, torch.from_numpy(r).cuda(), torch.from_numpy(t).cuda(), sc, w, outer, inner, n_rows,
+                    n_cols, N, N, 3)
+    tail_only = ref.copy()
+    if band:
+        tb = torch.zeros(shape, dtype=torch.complex128, device='cuda')
+        ops.banded_matvec(ud, tb, offs, [torch.from_numpy(tab).cuda()], [sc], outer, inner, n_rows, n_cols, N, N, 0)
+        tail_only = ref-tb.cpu().numpy()
+    assert rel_l2(out2.cpu().numpy(), ref+1j*tail_only) < TOL

@@ -115,3 +115,39 @@ def test_chebyshev_lobatto_operator_matrices_host(name, N):
     assert rel_l2(fw, g[f'fw_{tag}']) < 1e-12
     if N == 16:
         assert np.abs(M[:d, :d]-g[f'M00_{tag}'][:d, :d]).max() < 1e-13
+
+
+@pytest.mark.parametrize('name', ['CTSD', 'CTSB', 'CTT', 'CTSN', 'ASDSD', 'ATT', 'SSBSB'])
+def test_separable_tail_detection_host(name):
+    """Host logic behind `shb_tail_matvec`: the structure found in the Chebyshev derivative
+    matrices reproduces the dense product when applied as band + running sums per parity; matrices
+    without a rank-one tail are left to the other paths."""
+    import shenfun_b200 as sf
+    from shenfun_b200.la import separable_tail
+    N = 33
+    TC = sf.FunctionSpace(N, 'C')
+    SD = sf.FunctionSpace(N, 'C', bc=(0, 0))
+    SB = sf.FunctionSpace(N, 'C', bc=(0, 0, 0, 0))
+    SN = sf.FunctionSpace(N, 'C', bc=BCS['neumann'])
+    test, trial, a, b = {'CTSD': (TC, SD, 0, 1), 'CTSB': (TC, SB, 0, 1), 'CTT': (TC, TC, 0, 1), 'CTSN': (TC, SN, 0, 1),
+                         'ASDSD': (SD, SD, 0, 2), 'ATT': (TC, TC, 0, 2), 'SSBSB': (SB, SB, 0, 4)}[name]
+    D = test.spectral_matrix(a, b, trial).diags()
+    found = separable_tail(D)
+    if name in ('ATT', 'SSBSB'):
+        assert found is None
+        return
+    w, r, t, band = found
+    n_rows, n_cols = D.shape
+    u = np.random.default_rng(0).standard_normal(n_cols)
+    out = np.zeros(n_rows)
+    for o, v in band.items():
+        for i, val in enumerate(v):
+            k = i if o >= 0 else i-o
+            out[k] += val*u[k+o]
+    P = [0.0, 0.0]
+    for k in range(n_rows-1, -1, -1):
+        j = k+w
+        if 0 <= j < n_cols:
+            P[(k+w) & 1] += t[j]*u[j]
+        out[k] += r[k]*P[(k+w) & 1]
+    assert rel_l2(out, D @ u) < 1e-13
