@@ -48,7 +48,7 @@ class ShenfunBaseArray(torch.Tensor):
                 assert len(val) == shape[0]
                 for i, v in enumerate(val):
                     data[i] = v
-            else:
+            elif val is not None:           # val=None: left uninitialised (about to be overwritten)
                 data.fill_(val)
         elif isinstance(buffer, torch.Tensor):
             data = buffer.as_subclass(torch.Tensor)
@@ -177,7 +177,7 @@ class Array(ShenfunBaseArray):
         """arguments.py:1968-1983"""
         space = self.function_space()
         if output_array is None:
-            output_array = Function(space)
+            output_array = Function(space, val=None)
         return space.forward(self, output_array, kind=kind)
 
     def offset(self):
@@ -194,7 +194,7 @@ class Function(ShenfunBaseArray):
         if padding_factor is not None:
             space = space.get_dealiased(padding_factor)
         if output_array is None:
-            output_array = Array(space)
+            output_array = Array(space, val=None)
         return space.backward(self, output_array, kind=kind)
 
     def mask_nyquist(self, mask=None):

@@ -505,55 +505,45 @@ dct_strided_kernel(const __grid_constant__ DctFastDesc d) {
                 }
         }
         __syncthreads();
-        // 2. c = K^T u (+ boundary lift), kept in registers, then published
-        if (j < SC::NB0) {
-#pragma unroll
-            for (int q = 0; q < SC::B0; ++q)
-#pragma unroll
-                for (int m = 0; m < SC::R0; ++m) {
-                    const int pos = (j + q * P) + m * SC::NB0;
-                    cplx acc = make_double2(0.0, 0.0);
-                    for (int i = 0; i < d.nsten; ++i) {
-                        const int k = pos - d.soff[i];
-                        if (k >= 0 && k < d.dim) {
-                            const double a = d.sten[i] ? __ldg(&d.sten[i][k]) : 1.0;
-                            const cplx x = s(k);
-                            acc.x = fma(a, x.x, acc.x);
-                            acc.y = fma(a, x.y, acc.y);
-                        }
-                    }
-                    if (d.nbc > 0 && pos < 4) {
-                        for (int b = 0; b < d.nbc; ++b) {
-                            if (d.dim + b >= M) break;
-                            const double a = __ldg(&d.bc_lift[b * 4 + pos]);
-                            const cplx x = s(d.dim + b);
-                            acc.x = fma(a, x.x, acc.x);
-                            acc.y = fma(a, x.y, acc.y);
-                        }
-                    }
-                    v[q * SC::R0 + m] = acc;
+        // 2. c = K^T u (+ boundary lift) evaluated at pos AND at M - pos straight from the staged
+        //    coefficients (twice the stencil arithmetic, but no publish / re-read round trip), then
+        //    U_0 = c_0, U_k = 0.5 w_k (c_k + i c_{M-k})
+        auto coeff = [&](int pos) -> cplx {
+            cplx acc = make_double2(0.0, 0.0);
+            for (int i = 0; i < d.nsten; ++i) {
+                const int k = pos - d.soff[i];
+                if (k >= 0 && k < d.dim) {
+                    const double a = d.sten[i] ? __ldg(&d.sten[i][k]) : 1.0;
+                    const cplx x = s(k);
+                    acc.x = fma(a, x.x, acc.x);
+                    acc.y = fma(a, x.y, acc.y);
                 }
-        }
-        __syncthreads();
-        if (j < SC::NB0) {
-#pragma unroll
-            for (int q = 0; q < SC::B0; ++q)
-#pragma unroll
-                for (int m = 0; m < SC::R0; ++m) s((j + q * P) + m * SC::NB0) = v[q * SC::R0 + m];
-        }
-        __syncthreads();
-        // 3. U_0 = c_0, U_k = 0.5 w_k (c_k + i c_{M-k})
+            }
+            if (d.nbc > 0 && pos < 4) {
+                for (int b = 0; b < d.nbc; ++b) {
+                    if (d.dim + b >= M) break;
+                    const double a = __ldg(&d.bc_lift[b * 4 + pos]);
+                    const cplx x = s(d.dim + b);
+                    acc.x = fma(a, x.x, acc.x);
+                    acc.y = fma(a, x.y, acc.y);
+                }
+            }
+            return acc;
+        };
         if (j < SC::NB0) {
 #pragma unroll
             for (int q = 0; q < SC::B0; ++q)
 #pragma unroll
                 for (int m = 0; m < SC::R0; ++m) {
                     const int pos = (j + q * P) + m * SC::NB0;
+                    const cplx ck = coeff(pos);
                     if (pos > 0) {
-                        const cplx ck = v[q * SC::R0 + m], cm = s(M - pos);
+                        const cplx cm = coeff(M - pos);
                         const cplx w = __ldg(&d.tw3[pos]);
                         const cplx sum = make_double2(ck.x - cm.y, ck.y + cm.x);
                         v[q * SC::R0 + m] = cscale(cmul(w, sum), 0.5);
+                    } else {
+                        v[q * SC::R0 + m] = ck;
                     }
                 }
         }

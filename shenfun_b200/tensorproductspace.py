@@ -197,7 +197,7 @@ class _Transform:
         space = self.space
         fo = self.direction != 'backward'
         if output_array is None:
-            output_array = Function(space) if fo else Array(space)
+            output_array = Function(space, val=None) if fo else Array(space, val=None)
         u = ops.as_device_tensor(input_array)
         out = ops.plain(output_array)
         ncomp = 1
@@ -704,7 +704,7 @@ class _CompositeTransform:
         space = self.space
         fo = self.direction != 'backward'
         if output_array is None:
-            output_array = Function(space) if fo else Array(space)
+            output_array = Function(space, val=None) if fo else Array(space, val=None)
         flat = space.flatten()
         same = all(s is flat[0] for s in flat)
         if same:
