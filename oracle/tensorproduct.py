@@ -58,3 +58,24 @@ def backward(uh, descs, axes=None, lead=0):
     for ax in axes:
         out = _bwd_axis(out, ax+lead, descs[ax])
     return out
+
+
+def fourier_poisson3d(N):
+    """demo/fourier_poisson3D.py:19-45 restated: u = cos(4x) + sin(4y) + sin(6z) on (0, 2 pi)^3,
+    f = div grad u on the quadrature mesh x_j = 2 pi j / N (fourier/bases.py:76).  The Fourier
+    scalar product carries the 1/N normalisation (fourier/bases.py:157-162), so f_hat = (v, f) equals
+    forward(f) and A = (v, div grad u) = -|k|^2; u_hat = f_hat / A with the (0,0,0) mode pinned to 0
+    (matrixbase.py:1418-1424).  Returns (f_hat, u_hat)."""
+    import numpy as np
+    xs = [2*np.pi*np.arange(n)/n for n in N]
+    X, Y, Z = np.meshgrid(*xs, indexing='ij')
+    f = -16*np.cos(4*X)-16*np.sin(4*Y)-36*np.sin(6*Z)
+    d = [('C2C', N[0], N[0]), ('C2C', N[1], N[1]), ('R2C', N[2], N[2])]
+    f_hat = forward(f, d, scalar_product=True)
+    k0 = np.fft.fftfreq(N[0], 1./N[0])[:, None, None]
+    k1 = np.fft.fftfreq(N[1], 1./N[1])[None, :, None]
+    k2 = np.fft.rfftfreq(N[2], 1./N[2])[None, None, :]
+    A = -(k0**2+k1**2+k2**2)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        u_hat = np.where(A == 0, 0, f_hat/A)
+    return f_hat, u_hat

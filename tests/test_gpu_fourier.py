@@ -134,3 +134,16 @@ def test_full_size_512_properties(pf):
     a = 0.37
     v2 = Tp.backward(sf.Function(T, buffer=(vh.v*a)))
     assert (torch.linalg.vector_norm(v2.v-a*v.v)/torch.linalg.vector_norm(v.v)).item() < 1e-14
+
+
+@pytest.mark.parametrize('N', [(14, 15, 16), (64, 64, 64)])
+def test_fourier_poisson3d_demo(N):
+    """BASELINE config 0 (demo/fourier_poisson3D.py): solution coefficients against the reference's
+    own run of the demo, and the demo's own assertion on the L2 error (:49)."""
+    from shenfun_b200.demos import fourier_poisson3d
+    g = load_golden('fourier_poisson3d')
+    tag = 'x'.join(str(n) for n in N)
+    u_hat, err = fourier_poisson3d.solve(N)
+    assert err < 1e-6
+    assert abs(err-float(g[f'error_{tag}'])) < 1e-12
+    assert rel_l2(u_hat.get(), g[f'u_hat_{tag}']) < TOL

@@ -32,3 +32,14 @@ def test_padded_match_reference(name, pf):
     d = descs(g, pf)
     assert rel_l2(otp.backward(g['v_hat'], d), g[f'v_pad{tag}']) < TOL
     assert rel_l2(otp.forward(g[f'w_pad{tag}'], d), g[f'w_hat_pad{tag}']) < TOL
+
+
+@pytest.mark.parametrize('N', [(14, 15, 16), (64, 64, 64)])
+def test_fourier_poisson3d_matches_reference_demo(N):
+    """BASELINE config 0: the oracle's restatement of demo/fourier_poisson3D.py against the
+    reference's own run of it."""
+    g = load_golden('fourier_poisson3d')
+    tag = 'x'.join(str(n) for n in N)
+    f_hat, u_hat = otp.fourier_poisson3d(N)
+    assert rel_l2(f_hat, g[f'f_hat_{tag}']) < 1e-13
+    assert rel_l2(u_hat, g[f'u_hat_{tag}']) < 1e-13
