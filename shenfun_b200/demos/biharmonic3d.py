@@ -30,6 +30,10 @@ def build(N, family='L'):
     u = sf.TrialFunction(T)
     v = sf.TestFunction(T)
     matrices = sf.inner(v, sf.div(sf.grad(sf.div(sf.grad(u)))))
+    # Chebyshev: the dedicated solver for the upper-triangular fourth-derivative matrix
+    # (chebyshev/la.py:354-558); Legendre: banded per-wavenumber systems
+    if family.lower().startswith('c'):
+        return T, la.Biharmonic(matrices)
     return T, la.SolverGeneric1ND(matrices)
 
 
