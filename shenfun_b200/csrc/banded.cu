@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(BD_THREADS) helmholtz_factor_kernel(
 // Solve (la.pyx:871-947): y_i = b_i - L[i-2] y_{i-2};  u_i = (y_i - d1[i] u_{i+2} - d2[i] sum_{q>=2} u_{i+2q}) / d0[i]
 template <class T>
 __global__ void __launch_bounds__(BD_THREADS) helmholtz_solve_kernel(
-    const T *__restrict__ b, T *__restrict__ u, const double *__restrict__ fd0, const double *__restrict__ fd1,
+    const T *b, T *u /* may alias b: in-place solve */, const double *__restrict__ fd0, const double *__restrict__ fd1,
     const double *__restrict__ fd2, const double *__restrict__ fL, int64_t outer, int64_t inner,
     int n, int n_fac, int n_u, int flags) {
     const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(BD_THREADS) biharmonic_factor_kernel(
 
 template <class T>
 __global__ void __launch_bounds__(BD_THREADS) biharmonic_solve_kernel(
-    const T *__restrict__ b, T *__restrict__ u, const double *__restrict__ fac, int64_t outer, int64_t inner,
+    const T *b, T *u /* may alias b: in-place solve */, const double *__restrict__ fac, int64_t outer, int64_t inner,
     int n, int n_u) {
     const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= outer * inner) return;

@@ -353,7 +353,7 @@ def _integrate(arr):
         df *= float(b.domain_factor())
         shape = [1]*nd
         shape[ax] = len(w)
-        t = t*torch.as_tensor(np.ascontiguousarray(w), device=t.device).view(shape)
+        t = t*torch.as_tensor(np.array(w, dtype=float), device=t.device).view(shape)
     val = t.sum()
     val = space.comm.allreduce(val)
     val = val.item()/df

@@ -227,7 +227,7 @@ def Poisson_Solve_ADD(A, b, u, axis=0):
 # functions scatter to / gather from the reference arrays; a gathered table is cached against the
 # tensors' version counters so that repeated solves do not re-pack.
 
-_PACK_CACHE = {}
+_PACK_CACHE = []
 
 
 def _bih_tab(n, sii, siu, siuu, ail, aii, aiu, bill, bil, bii, biu, biuu):
@@ -330,12 +330,18 @@ def Biharmonic_factor_pr(ak, bk, l0, l1, axis=0):
     st.finish()
 
 
-def _bih_pack(f, a0, axis):
+def _bih_pack(f, a0, axis, originals):
+    """Packed factor table for the seven reference arrays.  Cached per caller tensor OBJECT (weak
+    references, so a recycled address can never alias) and invalidated by torch's in-place version
+    counters; host (numpy) arguments are staged afresh each call and always re-packed."""
+    import weakref
     u0, u1, u2, l0, l1, ak, bk = f
-    key = tuple((t.data_ptr(), t._version) for t in f)+(float(a0), axis)
-    hit = _PACK_CACHE.get(key[0][0])
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    cacheable = all(isinstance(t, torch.Tensor) for t in originals)
+    if cacheable:
+        for refs, vers, ca0, cax, fac in list(_PACK_CACHE):
+            if ca0 == float(a0) and cax == axis and all(r() is t for r, t in zip(refs, originals)) \
+                    and vers == tuple(t._version for t in originals):
+                return fac
     outer, M, inner = axis_view(tuple(u0.shape[1:]), axis)
     fac = torch.empty((7, outer, 2*M, inner), dtype=torch.float64, device=u0.device)
     fac[0] = _rows_from_split(l0, axis, 1)
@@ -345,9 +351,10 @@ def _bih_pack(f, a0, axis):
     fac[4] = _rows_from_split(u2, axis, 0)
     fac[5] = _rows_from_split(ak, axis, 0)*float(a0)
     fac[6] = _rows_from_split(bk, axis, 0)*float(a0)
-    if len(_PACK_CACHE) > 8:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key[0][0]] = (key, fac)
+    if cacheable:
+        _PACK_CACHE[:] = [e for e in _PACK_CACHE if all(r() is not None for r in e[0])][-3:]
+        _PACK_CACHE.append((tuple(weakref.ref(t) for t in originals), tuple(t._version for t in originals),
+                            float(a0), axis, fac))
     return fac
 
 
@@ -358,7 +365,7 @@ def Biharmonic_Solve(b, u, u0, u1, u2, l0, l1, ak, bk, a0, axis=0):
     bt = ut if b is u else st(b, dtype=ut.dtype)
     f = [st(x, dtype=torch.float64) for x in (u0, u1, u2, l0, l1, ak, bk)]
     a0 = float(np.atleast_1d(host(a0)).item())
-    fac = _bih_pack(f, a0, axis)
+    fac = _bih_pack(f, a0, axis, (u0, u1, u2, l0, l1, ak, bk))
     outer, n_u, inner = axis_view(ut.shape, axis)
     n = fac.shape[2]
     ops.biharmonic_solve(bt, ut, fac, outer, inner, n, n_u)
