@@ -327,6 +327,37 @@ def _time_launch(fn, reps=10):
     return e0.elapsed_time(e1)/reps
 
 
+# ncu kernel name of each stage of the forward plan (profiles/r1_ncu_full_summary_final.txt)
+_STAGE_KERNEL = {
+    'r2c_axis2': 'void fft_contig_kernel<Sched<256, 8, 8, 4, 32>, 2, 8>',
+    'c2c_axis1': 'void fft_strided_kernel<Sched<512, 8, 8, 8, 64>, 0, 8, 0>',
+    'c2c_axis0': 'void fft_strided_kernel<Sched<512, 8, 8, 8, 64>, 0, 8, 0>',
+}
+
+
+def ncu_traffic_bytes(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernel, per launch, from the
+    committed `ncu --set full` capture (profiles/); None when the summary is not there."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_full_summary_final.txt')
+    want = _STAGE_KERNEL.get(stage)
+    if want is None or not os.path.exists(path):
+        return None
+    hits = []
+    with open(path) as f:
+        for line in f:
+            cols = [c.strip() for c in line.split('|')]
+            if cols and cols[0] == want and len(cols) > 3:
+                try:
+                    hits.append((float(cols[2])+float(cols[3]))*1e9)
+                except ValueError:
+                    pass
+    if not hits:
+        return None
+    # c2c_axis1 / c2c_axis0 are the same kernel launched twice in plan order (axis 1 first)
+    idx = {'c2c_axis1': 0, 'c2c_axis0': 1}.get(stage, 0)
+    return int(hits[min(idx, len(hits)-1)])
+
+
 def dominant_kernel_roofline(T, u, uh, peak, peak_src):
     """Per-stage timing of the forward plan; the slowest axis pass is reported."""
     import torch
@@ -341,7 +372,9 @@ def dominant_kernel_roofline(T, u, uh, peak, peak_src):
     ms, nbytes = stages[name]
     ach = nbytes/(ms*1e-3)/1e9
     return {'bound': 'hbm', 'kernel': name, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach/peak,
-            'peak_source': peak_src, 'traffic': None, 'algorithmic_bytes_per_launch': nbytes,
+            'peak_source': peak_src, 'traffic': ncu_traffic_bytes(name),
+            'traffic_source': 'profiles/r1_ncu_full_summary_final.txt (ncu --set full, dram read + write per launch)',
+            'algorithmic_bytes_per_launch': nbytes,
             'avg_launch_ms': ms,
             'all_stages_gbs': {k: v[1]/(v[0]*1e-3)/1e9 for k, v in stages.items()}}
 
