@@ -112,6 +112,40 @@ SHB_API int shb_fft_c2r_backward(const void *d_in, void *d_out, int64_t outer, i
                          int n_fft, int N, double scale, int flags, void *stream);
 
 /* ------------------------------------------------------------------ */
+/* N-D Fourier transform plans (single device): the C-level counterpart of
+ * TensorProductSpace.__init__ / configure_backwards (shenfun/tensorproductspace.py:314-541) and of
+ * ForwardTransform / BackwardTransform.__call__ (:205-259, :46-96) for Fourier bases.
+ * Axis i has `shape[i]` modes (an R2C axis stores shape/2+1 of them) and `padded[i]` >= shape[i]
+ * quadrature points (3/2-rule padding when larger).  `axes` is the backward transform order; the
+ * forward transform runs it in reverse ("last item is transformed first", :274-276), so an R2C axis
+ * must be the last entry.  Forward is normalised by the padded lengths, backward is not
+ * (fourier/bases.py:138-142, 407).  Arrays are C-ordered, `ncomp` components stacked in front
+ * (VectorSpace / TensorSpace batches, :1786-1795).  The plan owns no device memory; the caller passes
+ * shb_plan_workspace_bytes(plan, ncomp) bytes of scratch.                                     */
+#define SHB_PLAN_MAXDIM 4
+enum shb_axis_kind { SHB_AXIS_C2C = 0, SHB_AXIS_R2C = 1 };
+typedef struct shb_plan_desc {
+    int ndim;
+    int64_t shape[SHB_PLAN_MAXDIM];
+    int64_t padded[SHB_PLAN_MAXDIM];
+    int kind[SHB_PLAN_MAXDIM];
+    int axes[SHB_PLAN_MAXDIM];
+    int dealias_direct;
+} shb_plan_desc;
+typedef struct shb_plan shb_plan;
+
+SHB_API int shb_plan_create(const shb_plan_desc *desc, shb_plan **plan);
+SHB_API int shb_plan_destroy(shb_plan *plan);
+SHB_API int64_t shb_plan_workspace_bytes(const shb_plan *plan, int ncomp);
+/* elements of the physical (spectral = 0: real when there is an R2C axis, else complex) or spectral
+ * (spectral = 1: complex) array of ONE component */
+SHB_API int64_t shb_plan_array_elems(const shb_plan *plan, int spectral);
+SHB_API int shb_plan_forward(const shb_plan *plan, const void *d_in, void *d_out, void *d_work, int ncomp,
+                             void *stream);
+SHB_API int shb_plan_backward(const shb_plan *plan, const void *d_in, void *d_out, void *d_work, int ncomp,
+                              void *stream);
+
+/* ------------------------------------------------------------------ */
 /* Point-wise kernels of the Navier-Stokes path.                        */
 
 /* c = a x b on [3][n] arrays (real fp64 or complex128).  Replaces

@@ -16,6 +16,12 @@ class ShenB200Error(RuntimeError):
     pass
 
 
+class PlanDesc(ctypes.Structure):
+    """`shb_plan_desc` of include/shenb200.h."""
+    _fields_ = [('ndim', ctypes.c_int), ('shape', ctypes.c_int64*4), ('padded', ctypes.c_int64*4),
+                ('kind', ctypes.c_int*4), ('axes', ctypes.c_int*4), ('dealias_direct', ctypes.c_int)]
+
+
 def _declare(lib):
     c = ctypes
     vp, i64, i32, f64 = c.c_void_p, c.c_int64, c.c_int, c.c_double
@@ -55,6 +61,19 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.restype = i32
         fn.argtypes = argtypes
+    # N-D plan API
+    lib.shb_plan_create.restype = i32
+    lib.shb_plan_create.argtypes = [c.POINTER(PlanDesc), c.POINTER(vp)]
+    lib.shb_plan_destroy.restype = i32
+    lib.shb_plan_destroy.argtypes = [vp]
+    lib.shb_plan_workspace_bytes.restype = i64
+    lib.shb_plan_workspace_bytes.argtypes = [vp, i32]
+    lib.shb_plan_array_elems.restype = i64
+    lib.shb_plan_array_elems.argtypes = [vp, i32]
+    for name in ('shb_plan_forward', 'shb_plan_backward'):
+        fn = getattr(lib, name)
+        fn.restype = i32
+        fn.argtypes = [vp, vp, vp, vp, i32, vp]
     return sig
 
 
