@@ -101,7 +101,7 @@ class Orthogonal(PolyBase):
         G = c[:, None]*self._deriv_ld(N, d_trial)
         if d_test > 0:
             G = self._deriv_ld(N, d_test).T @ G
-        return G, ld(np.pi)/2 if False else np.longdouble('1.5707963267948966192313216916397514')
+        return G, np.longdouble('1.5707963267948966192313216916397514')      # pi/2 to long-double precision
 
     def boundary_values(self, n, order, side):
         n = np.asarray(n, dtype=float)
@@ -154,26 +154,25 @@ class Orthogonal(PolyBase):
         return self._tables['gl_ops']
 
     def _gl_operators_host(self):
-        if True:
-            Np = self.physical_len()
-            ld = np.longdouble
-            pi = ld('3.14159265358979323846264338327950288')
-            jk = np.outer(np.arange(Np), np.arange(self.N)) % (2*(Np-1))       # exact integer phase
-            V = np.cos(pi*jk.astype(ld)/(Np-1))
-            w = np.full(Np, pi/(Np-1))
-            w[0] /= 2
-            w[-1] /= 2
-            K = self.stencil_matrix().diags().astype(ld)             # (dim, N)
-            dim = self.dim()
-            F = np.zeros((self.N, Np), dtype=ld)
-            F[:dim] = K @ (V.T*w[None, :])/ld(float(self.domain_factor()))
-            B = np.zeros((Np, self.N), dtype=ld)
-            B[:, :dim] = V @ K.T
-            nbc = self.bcs.num_bcs()
-            if nbc and self.N >= 4:
-                L = self.bc_basis()                                   # (nbc, 4)
-                B[:, dim:] = V[:, :4] @ L[:, :4].T.astype(ld)
-            return np.ascontiguousarray(F.astype(np.float64)), np.ascontiguousarray(B.astype(np.float64))
+        Np = self.physical_len()
+        ld = np.longdouble
+        pi = ld('3.14159265358979323846264338327950288')
+        jk = np.outer(np.arange(Np), np.arange(self.N)) % (2*(Np-1))       # exact integer phase
+        V = np.cos(pi*jk.astype(ld)/(Np-1))
+        w = np.full(Np, pi/(Np-1))
+        w[0] /= 2
+        w[-1] /= 2
+        K = self.stencil_matrix().diags().astype(ld)             # (dim, N)
+        dim = self.dim()
+        F = np.zeros((self.N, Np), dtype=ld)
+        F[:dim] = K @ (V.T*w[None, :])/ld(float(self.domain_factor()))
+        B = np.zeros((Np, self.N), dtype=ld)
+        B[:, :dim] = V @ K.T
+        nbc = self.bcs.num_bcs()
+        if nbc and self.N >= 4:
+            L = self.bc_basis()                                   # (nbc, 4)
+            B[:, dim:] = V[:, :4] @ L[:, :4].T.astype(ld)
+        return np.ascontiguousarray(F.astype(np.float64)), np.ascontiguousarray(B.astype(np.float64))
 
     def _scalar_product_axis(self, u, out, outer, inner):
         if self.quad == 'GL':

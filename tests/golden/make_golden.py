@@ -311,8 +311,7 @@ def solvers():
     SB = sf.FunctionSpace(16, 'L', bc=(0, 0, 0, 0))
     K1 = sf.FunctionSpace(12, 'F', dtype='D')
     K2 = sf.FunctionSpace(10, 'F', dtype='d')
-    T = sf.TensorProductSpace(sf.comm, (K1, K2.get_unplanned() if False else sf.FunctionSpace(10, 'F', dtype='D'), SB)) if False else \
-        sf.TensorProductSpace(sf.comm, (SB, K1, K2))
+    T = sf.TensorProductSpace(sf.comm, (SB, K1, K2))
     u = TrialFunction(T)
     v = TestFunction(T)
     f_hat = sf.Function(T)
