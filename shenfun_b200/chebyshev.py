@@ -71,6 +71,9 @@ class Orthogonal(PolyBase):
             points = self.map_true_domain(points)
         return points, weights
 
+    def orthogonal_vandermonde(self, X):
+        return np.polynomial.chebyshev.chebvander(X, self.N-1)
+
     def ortho_norm_sq(self, N=None):
         N = self.N if N is None else N
         h = np.full(N, np.pi/2)

@@ -28,4 +28,9 @@ def solve(N=(14, 15, 16), comm=None):
     uq = u_hat.backward()
     uj = sf.Array(T, buffer=ue)
     error = np.sqrt(sf.inner(1, (uj-uq)**2))
+    # evaluation at arbitrary points (demo :54-58)
+    point = np.array([[0.1, 0.5], [0.5, 0.6], [0.1, 0.2]])
+    p = T.eval(point, u_hat)
+    ul = sp.lambdify((x, y, z), ue)
+    assert np.allclose(p, ul(*point)), (p, ul(*point))
     return u_hat, float(abs(error))

@@ -70,6 +70,12 @@ class FourierBase(SpectralBase):
             val = np.ones(len(k))
         return SparseMatrix({0: val}, (len(k), len(k)))
 
+    def evaluate_basis_all(self, x):
+        """E[p, k] = exp(i k_k X_p) on the reference domain (fourier/bases.py:87-103)."""
+        X = np.atleast_1d(self.map_reference_domain(np.asarray(x, dtype=float)))
+        k = np.asarray(self.wavenumbers(bcast=False), dtype=float)
+        return np.exp(1j*np.outer(X, k))
+
 
 class R2C(FourierBase):
     """Real-to-complex Fourier space (fourier/bases.py:283-497)."""

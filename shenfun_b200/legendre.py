@@ -75,6 +75,9 @@ class Orthogonal(PolyBase):
             x = self.map_true_domain(x)
         return x, w
 
+    def orthogonal_vandermonde(self, X):
+        return np.polynomial.legendre.legvander(X, self.N-1)
+
     def ortho_norm_sq(self, N=None):
         N = self.N if N is None else N
         return 2.0/(2*np.arange(N)+1.0)

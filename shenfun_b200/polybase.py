@@ -246,6 +246,20 @@ class PolyBase(SpectralBase):
             out[b] /= df**order
         return out
 
+    def evaluate_basis_all(self, x):
+        """E[p, k] = phi_k(X_p) for the dofs k < dim and the boundary functions on the bc rows
+        (spectralbase.py:1000-1035 `evaluate_basis_all`; composite: spectralbase.py:1616-1634)."""
+        X = np.atleast_1d(self.map_reference_domain(np.asarray(x, dtype=float)))
+        V = self.orthogonal_vandermonde(X)                       # (npoints, N)
+        E = np.zeros((len(X), self.N))
+        dim = self.dim()
+        K = self.stencil_matrix().diags()                         # (dim, N)
+        E[:, :dim] = V @ K.T
+        nbc = self.bcs.num_bcs()
+        if nbc and self.N >= 4:
+            E[:, dim:dim+nbc] = V[:, :4] @ self.bc_basis()[:, :4].T
+        return E
+
     @property
     def has_nonhomogeneous_bcs(self):
         return not self.bcs.is_homogeneous()

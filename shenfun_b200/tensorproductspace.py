@@ -401,6 +401,48 @@ class TensorProductSpace:
         self.backward._run(ab[3:], bp, 3)
         return self.backward_cross(ab[:3], bp, out)
 
+    def eval(self, points, coefficients, output_array=None, method=1):
+        """Function values at arbitrary points from the expansion coefficients
+        (tensorproductspace.py:668-854).  points: (D, npoints).  Every axis contributes a basis
+        matrix E_a[p, k] evaluated on the host; the coefficients are contracted axis by axis on the
+        device (not a hot path: O(npoints * N^D)).  For a real-to-complex axis the conjugate half
+        of the spectrum is added as in the reference (:718-737): modes 1 .. N/2-1 (N even) or
+        1 .. (N-1)/2 (N odd).  Ranks hold their local block; the result is summed over ranks."""
+        pts = np.atleast_2d(np.asarray(points, dtype=float))
+        assert pts.shape[0] == self.dimensions, 'points must have shape (D, npoints)'
+        npts = pts.shape[1]
+        uh = ops.as_device_tensor(coefficients)
+        sl = self.local_slice(True)
+        dev = uh.device
+        letters = 'abcd'[:self.dimensions]
+        mats, r2c_axis, conj_mask = [], None, None
+        for ax, base in enumerate(self.bases):
+            E = np.asarray(base.evaluate_basis_all(pts[ax]))[:, sl[ax]]
+            if base.family() == 'fourier' and base.short_name() == 'R2C':
+                r2c_axis = ax
+                k = np.arange(base.spectral_len())[sl[ax]]
+                last = base.N//2 if base.N % 2 == 0 else base.N//2+1      # first index NOT conjugated
+                conj_mask = ((k >= 1) & (k < last)).astype(float)
+            mats.append(torch.as_tensor(np.ascontiguousarray(E), device=dev).to(torch.complex128))
+        u = uh.to(torch.complex128)
+        expr = ','.join('p'+c for c in letters)+','+letters+'->p'
+        val = torch.einsum(expr, *mats, u)
+        if r2c_axis is not None:
+            m2 = list(mats)
+            m2[r2c_axis] = mats[r2c_axis]*torch.as_tensor(conj_mask, device=dev)
+            val = val+torch.conj(torch.einsum(expr, *m2, u))
+        if self.comm.Get_size() > 1:
+            import torch.distributed as dist
+            buf = torch.view_as_real(val.contiguous())
+            dist.all_reduce(buf, group=self.comm.group)
+            val = torch.view_as_complex(buf)
+        real_out = not self.physical_dtype.is_complex
+        res = (val.real if real_out else val).cpu().numpy()
+        if output_array is not None:
+            output_array[...] = res
+            return output_array
+        return res
+
     # ---- bookkeeping API (mpi4py_fft.PFFT + tensorproductspace.py:580-1180) ------------
     @property
     def dimensions(self):

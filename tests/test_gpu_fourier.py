@@ -147,3 +147,30 @@ def test_fourier_poisson3d_demo(N):
     assert err < 1e-6
     assert abs(err-float(g[f'error_{tag}'])) < 1e-12
     assert rel_l2(u_hat.get(), g[f'u_hat_{tag}']) < TOL
+
+
+def test_eval_at_points_matches_backward_on_the_mesh():
+    """`TensorProductSpace.eval` (tensorproductspace.py:668-854) at mesh points == backward."""
+    import shenfun_b200 as sf
+    rng = np.random.default_rng(8)
+    N = (10, 9, 12)
+    T = sf.TensorProductSpace(sf.comm, [sf.FunctionSpace(N[0], 'F', dtype='D'), sf.FunctionSpace(N[1], 'F', dtype='D'),
+                                        sf.FunctionSpace(N[2], 'F', dtype='d')])
+    u = rng.standard_normal(N)
+    uh = T.forward(u)
+    xs = [2*np.pi*np.arange(n)/n for n in N]
+    idx = rng.integers(0, N, size=(25, 3))
+    pts = np.array([[xs[a][i[a]] for i in idx] for a in range(3)])
+    ref = np.array([u[tuple(i)] for i in idx])
+    assert np.abs(T.eval(pts, uh)-ref).max() < 1e-12
+    SD = sf.FunctionSpace(14, 'C', bc=(0, 0))
+    Tc = sf.TensorProductSpace(sf.comm, (SD, sf.FunctionSpace(8, 'F', dtype='D'), sf.FunctionSpace(6, 'F', dtype='d')))
+    vh = np.zeros(Tc.shape(True), dtype=complex)
+    vh[:SD.dim()] = rng.standard_normal((SD.dim(), 8, 4))+1j*rng.standard_normal((SD.dim(), 8, 4))
+    F = sf.Function(Tc, buffer=vh)
+    v = Tc.backward(F).get()
+    xs = [SD.points_and_weights(14)[0], 2*np.pi*np.arange(8)/8, 2*np.pi*np.arange(6)/6]
+    idx = rng.integers(0, [14, 8, 6], size=(25, 3))
+    pts = np.array([[xs[a][i[a]] for i in idx] for a in range(3)])
+    ref = np.array([v[tuple(i)] for i in idx])
+    assert np.abs(Tc.eval(pts, F)-ref).max() < 1e-12*max(1.0, np.abs(ref).max())
