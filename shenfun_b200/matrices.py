@@ -142,10 +142,19 @@ class TPMatrix:
         if u is None:
             u = b
         if self.is_diagonal():
-            d = self.diagonal_array()
-            inv = torch.where(d == 0, torch.zeros_like(d), 1.0/d)
+            inv = getattr(self, '_inv_diag', None)
+            if inv is None:
+                d = self.diagonal_array()
+                inv = torch.where(d == 0, torch.zeros_like(d), 1.0/d).contiguous()
+                self._inv_diag = inv                      # the reciprocal is formed once per matrix
             bt, ut = ops.plain(b), ops.plain(u)
-            torch.mul(bt, inv, out=ut)
+            if (inv.dtype == torch.float64 and ut.dtype == torch.complex128 and ut.is_contiguous()
+                    and ut.numel() % inv.numel() == 0 and tuple(ut.shape[ut.ndim-inv.ndim:]) == tuple(inv.shape)):
+                if ut.data_ptr() != bt.data_ptr():
+                    ut.copy_(bt)
+                ops.apply_mask(ut, inv)                   # u *= 1/d in the library's point-wise kernel
+            else:
+                torch.mul(bt, inv, out=ut)
             return u
         from .la import SolverGeneric1ND
         return SolverGeneric1ND([self])(b, u, constraints=constraints)
