@@ -179,6 +179,10 @@ SHB_API int shb_ns_rk_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d
  * operator L[n] (may be NULL): integrators.py:590-598.                      */
 SHB_API int shb_rk4_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, const double *d_L,
                           int64_t n, int ncomp, double a_dt, double b_dt, int last, void *stream);
+/* Same with a COMPLEX diagonal operator L[n] (complex128): odd-derivative / complex-coefficient
+ * linear terms such as KdV's -u_xxx (integrators.py:569-585 uses the complex scale array as is). */
+SHB_API int shb_rk4_stage_cplx(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, const void *d_L,
+                               int64_t n, int ncomp, double a_dt, double b_dt, int last, void *stream);
 
 /* u *= mask on [ncomp][n] complex (Nyquist masking): replaces
  * shenfun/optimization/cython/applymask.pyx:15-169 (`apply_mask`).          */

@@ -215,8 +215,19 @@ def ShenBiharmonic(N, bc=(0, 0, 0, 0), **kw):
     return Orthogonal(N, bc=bc, **kw)
 
 
+_BASIS_BCS = {'orthogonal': None, 'shendirichlet': (0, 0), 'shenneumann': {'left': {'N': 0}, 'right': {'N': 0}},
+              'shenbiharmonic': (0, 0, 0, 0)}
+
+
 def make_space(N, bc=None, quad=None, domain=None, dtype='d', scaled=None, basis=None, padding_factor=1,
                dealias_direct=False, **kw):
+    if basis is not None:
+        # forms/arguments.py:30-418: `basis` names a class; only the ones boundary conditions imply exist here
+        name = str(basis).lower()
+        if name not in _BASIS_BCS:
+            raise NotImplementedError(f'basis={basis!r}: only {sorted(_BASIS_BCS)} are on the device path')
+        if bc is None:
+            bc = _BASIS_BCS[name]
     par = dict(quad=quad or 'GC', padding_factor=padding_factor, dealias_direct=dealias_direct,
                dtype=np.dtype(dtype), scaled=bool(scaled))
     if domain is not None:

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(PW_THREADS) ns_rk_stage_kernel(
 // generic RK4 stage: dU += L*u_hat (L real, broadcast over ncomp); U1 += a_dt dU; u_hat = U0 + b_dt dU | U1
 __global__ void __launch_bounds__(PW_THREADS) rk4_stage_kernel(
     cplx *__restrict__ dU, cplx *__restrict__ u_hat, const cplx *__restrict__ U0, cplx *__restrict__ U1,
-    const double *__restrict__ L, int64_t n, int ncomp, double a_dt, double b_dt, int last) {
+    const double *__restrict__ L, const cplx *__restrict__ Lc, int64_t n, int ncomp, double a_dt, double b_dt,
+    int last) {
     const int64_t tot = n * ncomp;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
         cplx d = dU[i];
@@ -148,6 +149,12 @@ __global__ void __launch_bounds__(PW_THREADS) rk4_stage_kernel(
             const double l = L[i % n];
             d.x = fma(l, uh.x, d.x);
             d.y = fma(l, uh.y, d.y);
+            dU[i] = d;
+        } else if (Lc) {
+            // complex diagonal operator (odd derivatives: KdV's -u_xxx, Ginzburg-Landau)
+            const cplx l = Lc[i % n];
+            d.x = fma(l.x, uh.x, fma(-l.y, uh.y, d.x));
+            d.y = fma(l.x, uh.y, fma(l.y, uh.x, d.y));
             dU[i] = d;
         }
         cplx u1 = U1[i];
@@ -257,7 +264,18 @@ int shb_rk4_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, const
     SHB_REQUIRE(d_dU && d_u_hat && d_U0 && d_U1 && n >= 0 && ncomp >= 1, "bad arguments");
     if (n == 0) return SHB_OK;
     rk4_stage_kernel<<<pw_blocks(n * ncomp), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        (cplx *)d_dU, (cplx *)d_u_hat, (const cplx *)d_U0, (cplx *)d_U1, d_L, n, ncomp, a_dt, b_dt, last);
+        (cplx *)d_dU, (cplx *)d_u_hat, (const cplx *)d_U0, (cplx *)d_U1, d_L, nullptr, n, ncomp, a_dt, b_dt, last);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_rk4_stage_cplx(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, const void *d_L,
+                       int64_t n, int ncomp, double a_dt, double b_dt, int last, void *stream) {
+    SHB_REQUIRE(d_dU && d_u_hat && d_U0 && d_U1 && d_L && n >= 0 && ncomp >= 1, "bad arguments");
+    if (n == 0) return SHB_OK;
+    rk4_stage_kernel<<<pw_blocks(n * ncomp), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (cplx *)d_dU, (cplx *)d_u_hat, (const cplx *)d_U0, (cplx *)d_U1, nullptr, (const cplx *)d_L, n, ncomp,
+        a_dt, b_dt, last);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }

@@ -44,7 +44,7 @@ class IntegratorBase:
         pass
 
     def _linear_operator(self):
-        """Diagonal of the linear operator as a real device tensor, or None
+        """Diagonal of the linear operator as a real (or, for odd derivatives, complex) device tensor, or None
         (integrators.py:569-585)."""
         ut = TrialFunction(self.T)
         vt = TestFunction(self.T)
@@ -59,6 +59,8 @@ class IntegratorBase:
             d = L.diagonal_array()
             shape = self.T.flatten()[0].shape(True) if self.T.is_composite_space else self.T.shape(True)
             d = d.expand(shape).contiguous()
+            if d.is_complex() and bool((d.imag != 0).any()):
+                return d.contiguous()            # complex operator: shb_rk4_stage_cplx
             return d.real.contiguous() if d.is_complex() else d
         if isinstance(L, torch.Tensor):
             return L

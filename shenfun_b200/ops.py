@@ -14,6 +14,12 @@ def plain(t):
     return t.as_subclass(torch.Tensor) if isinstance(t, torch.Tensor) else t
 
 
+def device():
+    if not torch.cuda.is_available():
+        raise _lib.ShenB200Error('no CUDA device: shenfun_b200 has no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
 def as_device_tensor(x):
     if isinstance(x, torch.Tensor):
         t = plain(x)
@@ -131,6 +137,11 @@ def rk4_stage(dU, u_hat, U0, U1, L, a_dt, b_dt, last):
     if L is not None:
         n = L.numel()
         ncomp = u_hat.numel()//n
+    if L is not None and L.is_complex():
+        _call('shb_rk4_stage_cplx', _req(dU, C128, 'dU'), _req(u_hat, C128, 'u_hat'), _req(U0, C128, 'U0'),
+              _req(U1, C128, 'U1'), _req(L, C128, 'L'), n, ncomp, float(a_dt), float(b_dt), int(last),
+              _lib.stream_ptr())
+        return
     _call('shb_rk4_stage', _req(dU, C128, 'dU'), _req(u_hat, C128, 'u_hat'), _req(U0, C128, 'U0'),
           _req(U1, C128, 'U1'), None if L is None else _req(L, F64, 'L'), n, ncomp, float(a_dt),
           float(b_dt), int(last), _lib.stream_ptr())

@@ -313,7 +313,8 @@ def Biharmonic_factor_pr(ak, bk, l0, l1, axis=0):
     par = torch.arange(2, dtype=torch.float64, device=a.device).view(2, 1, 1)
     av.zero_()
     bv.zero_()
-    for m in sorted(set(range(min(2, M))) | set(range(2, M-3))):
+    # la.pyx:1221-1233 loops to l0.shape[0]+1-3, and l0 is as long as ak: rows 2 .. M-3 are filled
+    for m in sorted(set(range(min(2, M))) | set(range(2, M-2))):
         kk = 2.0*m+par
         pa = 8*kk*(kk+1)*(kk+2)*(kk+4)*np.pi
         pb = 24*(kk+1)*(kk+2)*np.pi

@@ -199,7 +199,10 @@ class PolyBase(SpectralBase):
         return out
 
     def _stencil_scaling(self, k):
-        return np.ones(len(k))
+        """Row scaling of the stencil for `scaled=True`; families implement the bases that have one
+        in the reference (Legendre ShenDirichlet: 1/sqrt(4k+6), legendre/bases.py:373-376)."""
+        raise NotImplementedError(f'scaled=True is not available for the {self.family()} '
+                                  f'{self.boundary_condition()} basis')
 
     def stencil_matrix(self, N=None):
         """K as a (dim x N) SparseMatrix (spectralbase.py:1504-1526)."""
@@ -366,21 +369,47 @@ class PolyBase(SpectralBase):
         """In-place B^-1 along the axis (spectralbase.py:560-577) on [outer][N][inner]."""
         self._mass_solver().solve(out, outer, inner, self.N)
 
+    def _line_bcs(self, outer, inner):
+        """Boundary values per line for the current axis pass: [nbc][outer1][inner] tensors from the
+        tensor-product space (functions of the other coordinates, already transformed along the axes
+        that ran before this one; tensorproductspace.py:1909-2032), or None for a 1-D space / lines
+        that all carry the same numbers."""
+        T = self.tensorproductspace
+        if T is None or getattr(T, 'dimensions', 1) < 2:
+            return None
+        return T._tensor_bcs(self)[0]
+
     def _set_bc_rows(self, out, outer, inner):
-        """Write the boundary values into rows dim.. of every line (set_boundary_dofs)."""
+        """Write the boundary values into rows dim.. of every line (set_boundary_dofs, not final)."""
         conds = self.bcs.conditions()
         dim = self.dim()
+        lb = self._line_bcs(outer, inner)
+        if lb is not None:
+            o1 = lb.shape[1]
+            v = out.view(outer//o1, o1, self.N, inner)
+            for b in range(len(conds)):
+                v[:, :, dim+b, :] = lb[b].to(out.dtype)
+            return
         v = out.view(outer, self.N, inner)
         for b, (_, _, val) in enumerate(conds):
             v[:, dim+b, :] = float(val)
 
     def _subtract_bc_mass(self, out, outer, inner):
+        """rhs -= (beta_b, phi_k)_w * bc value of the line (`_add_mass_rhs`, tensorproductspace.py:2091-2106)."""
         conds = self.bcs.conditions()
+        Mb = self.bc_mass()
+        rows = np.nonzero(np.abs(Mb).max(axis=1) > 0)[0]
+        lb = self._line_bcs(outer, inner)
+        if lb is not None:
+            o1 = lb.shape[1]
+            v = out.view(outer//o1, o1, self.N, inner)
+            for r in rows:
+                for b in range(len(conds)):
+                    if Mb[r, b] != 0:
+                        v[:, :, r, :] -= float(Mb[r, b])*lb[b].to(out.dtype)
+            return
         if all(float(v) == 0 for _, _, v in conds):
             return
-        Mb = self.bc_mass()
-        dim = self.dim()
-        rows = np.nonzero(np.abs(Mb).max(axis=1) > 0)[0]
         v = out.view(outer, self.N, inner)
         for r in rows:
             s = sum(Mb[r, b]*float(val) for b, (_, _, val) in enumerate(conds))

@@ -87,9 +87,12 @@ class _Transform:
     def output_shape(self):
         return self.steps[-1].out_shape
 
-    def _run(self, u, out, ncomp, last_override=None):
+    def _run(self, u, out, ncomp, last_override=None, overrides=None):
+        """`last_override` / `overrides` {step index: fn(cur, dst, outer, inner)} replace the axis
+        kernel of a step (fused C2R-cross; the do-nothing pass of `TensorProductSpace._tensor_bcs`)."""
         from ._lib import ShenB200Error
         self._last_override = last_override
+        self._overrides = overrides
         try:
             return self._run_impl(u, out, ncomp)
         except ShenB200Error as e:
@@ -181,6 +184,8 @@ class _Transform:
                         peer_done = None
                 if i == n-1 and getattr(self, '_last_override', None) is not None:
                     self._last_override(cur, dst, outer, inner)
+                elif getattr(self, '_overrides', None) and i in self._overrides:
+                    self._overrides[i](cur, dst, outer, inner)
                 elif bwd:
                     s.base._backward_axis(cur, dst, outer, inner, **kw)
                 else:
@@ -230,6 +235,21 @@ class TensorProductSpace:
     def __init__(self, comm, bases, axes=None, dtype=None, slab=True, collapse_fourier=False,
                  backward_from_pencil=False, coordinates=None, modify_spaces_inplace=False, **kw):
         self.comm = default_comm if comm is None else comm
+        # Only the slab decomposition of mpi4py-fft (`slab=True`, one exchange; :393-396) exists on the
+        # device path: a pencil request (slab=False with > 1 rank, an explicit `Subcomm` or a tuple /
+        # list process grid as in demo/poisson3D.py:67) must not silently run something else.
+        if isinstance(self.comm, (tuple, list)) or type(self.comm).__name__ == 'Subcomm':
+            dims = list(self.comm.dims) if hasattr(self.comm, 'dims') else list(self.comm)
+            if sum(1 for d in dims if d != 1) > 1:
+                raise NotImplementedError('pencil decompositions (process grid %r) are not built: the device '
+                                          'path is slab-distributed over <= 8 GPUs' % (dims,))
+            self.comm = getattr(self.comm, 'comm', default_comm) if not isinstance(self.comm, (tuple, list)) \
+                else default_comm
+        if not slab and self.comm.Get_size() > 1 and len(bases) > 2:
+            raise NotImplementedError('slab=False (pencil decomposition) is not built on the device path; '
+                                      'use slab=True (one all-to-all per transform)')
+        if collapse_fourier and self.comm.Get_size() > 1:
+            raise NotImplementedError('collapse_fourier=True is not built on the device path')
         if not modify_spaces_inplace:
             bases = [b.get_unplanned() for b in bases]
         self.bases = tuple(bases)
@@ -339,6 +359,96 @@ class TensorProductSpace:
         self.forward = _Transform(self, fsteps, 'forward')
         self.backward = _Transform(self, bsteps, 'backward')
         self.scalar_product = _Transform(self, fsteps, 'scalar_product')
+
+    # ---- inhomogeneous boundary conditions in a tensor-product space ----------------------------
+    def get_nonhomogeneous_axes(self):
+        """tensorproductspace.py:1085-1095"""
+        return [i for i, b in enumerate(self.bases) if getattr(b, 'has_nonhomogeneous_bcs', False)]
+
+    def _tensor_bcs(self, base):
+        """Boundary values of `base` as the plan sees them (`BoundaryValues.set_tensor_bcs`,
+        tensorproductspace.py:1909-2032): the boundary data, a function of the other coordinates, is
+        stored in the rows of the boundary dofs of a physical array and taken through the forward
+        plan with a do-nothing pass in place of this base's own transform.  Returns
+        (partial, final): `partial[b]` [outer][inner] are the values at the moment this base is
+        transformed (axes transformed earlier already spectral: what `_add_mass_rhs` needs, :2091-2106),
+        `final[b]` the fully transformed values (what `set_boundary_dofs(final=True)` writes, :2108-2128)."""
+        ax = base.axis
+        cache = self.__dict__.setdefault('_tbc_cache', {})
+        if ax in cache:
+            return cache[ax]
+        if len(self.get_nonhomogeneous_axes()) > 1:
+            raise NotImplementedError('inhomogeneous boundary conditions along more than one axis')
+        conds = base.bcs.conditions()
+        nbc = len(conds)
+        nd = self.dimensions
+        fw = self.forward
+        idx = [i for i, s in enumerate(fw.steps) if s.kind == 'axis' and s.axis == ax][0]
+        b = torch.zeros(self.shape(False), dtype=self.physical_dtype, device=ops.device())
+        # the boundary rows live at the tail of the (padded) physical axis; that axis is never the
+        # distributed one when its own transform runs, but it can be in physical space
+        sl_phys = self.local_slice(False)
+        n_phys = base.physical_len()
+        mesh = None
+        for j, (_, _, val) in enumerate(conds):
+            row = n_phys-nbc+j
+            if not (sl_phys[ax].start <= row < sl_phys[ax].stop):
+                continue
+            sel = [slice(None)]*nd
+            sel[ax] = row-sl_phys[ax].start
+            if isinstance(val, (int, float, complex, np.number)):
+                b[tuple(sel)] = val
+            else:
+                import sympy as sp
+                e = sp.sympify(val)
+                syms = sorted(e.free_symbols, key=str)
+                if mesh is None:
+                    mesh = self.local_mesh(bcast=True)
+                args = []
+                for sym in syms:
+                    k = 'xyzrs'.index(str(sym))
+                    assert k != ax and k < nd, 'boundary data may depend on the other coordinates only'
+                    take = [slice(None)]*nd
+                    take[ax] = 0
+                    args.append(np.asarray(mesh[k])[tuple(take)])
+                data = sp.lambdify(syms, e, 'numpy')(*args) if syms else complex(e)
+                b[tuple(sel)] = ops.as_device_tensor(np.ascontiguousarray(np.broadcast_to(
+                    data, tuple(n for i, n in enumerate(self.shape(False)) if i != ax)))).to(b.dtype)
+        dim = base.dim()
+        grabbed = {}
+
+        def do_nothing(cur, dst, outer, inner):
+            v = cur.view(outer, n_phys, inner)
+            o = dst.view(outer, base.N, inner)
+            o.zero_()
+            o[:, dim:dim+nbc, :] = v[:, n_phys-nbc:, :]
+            grabbed['partial'] = o[:, dim:dim+nbc, :].transpose(0, 1).contiguous()   # [nbc][outer][inner]
+        out = torch.empty(self.shape(True), dtype=self.spectral_dtype, device=b.device)
+        fw._run(b, out, 1, overrides={idx: do_nothing})
+        fw._overrides = None
+        sel = [slice(None)]*nd
+        sel[ax] = slice(dim, dim+nbc)
+        final = out[tuple(sel)].movedim(ax, 0).contiguous()                          # [nbc] + other axes
+        cache[ax] = (grabbed['partial'], final)
+        return cache[ax]
+
+    def _set_boundary_dofs(self, u):
+        """Function.set_boundary_dofs (forms/arguments.py:1525-1539; final values, :2108-2128)."""
+        t = ops.plain(u)
+        for base in self.bases:
+            nbc = base.bcs.num_bcs() if hasattr(base, 'bcs') else 0
+            if not nbc:
+                continue
+            ax, dim = base.axis, base.dim()
+            sel = [slice(None)]*self.dimensions
+            sel[ax] = slice(dim, dim+nbc)
+            lead = t.dim()-self.dimensions
+            tgt = t[(slice(None),)*lead+tuple(sel)]
+            if getattr(base, 'has_nonhomogeneous_bcs', False):
+                tgt.copy_(self._tensor_bcs(base)[1].movedim(0, ax))
+            else:
+                tgt.zero_()
+        return u
 
     def backward_cross(self, u_hat, b, out):
         """out = backward(u_hat) x b for three-component fields: the last (complex-to-real) axis

@@ -29,11 +29,12 @@ def apply_mask(u_hat, mask):
 
 
 def dx(u):
-    """Integral of an Array over the domain (utilities/__init__.py:26-61)."""
+    """Integral of an Array over the reference domain: sum(u*w) with the un-weighted quadrature
+    weights of every axis (utilities/__init__.py:26-61; "assumes a standard reference domain"), i.e.
+    the true-domain integral of `forms._integrate` times the domain factors."""
     from .forms import _integrate
     space = u.function_space()
-    L = 1.0
+    df = 1.0
     for b in (space.flatten()[0].bases if space.is_composite_space else space.bases):
-        if b.family() == 'fourier':
-            L *= b.domain_length()
-    return _integrate(u)*L
+        df *= float(b.domain_factor())
+    return _integrate(u)*df

@@ -25,7 +25,12 @@ def main():
     comm = sf.init_from_env('nccl')
     rank, world = comm.Get_rank(), comm.Get_size()
     worst = 0.0
-    for N, pf in (((32, 24, 20), 1.0), ((32, 24, 20), 1.5), ((30, 27, 16), 1.0), ((64, 64, 64), 1.5)):
+    # the last three cases put BASELINE line lengths on both exchanged axes: the 512-point producer is
+    # the 16-column peer-store kernel (`fft_strided_kernel<Sched<512,...>, ., 16, true>`), the 768-point
+    # ones the 3/2-padded passes of the NS step, 1024 x 256 the channel-flow planes
+    cases = [((32, 24, 20), 1.0), ((32, 24, 20), 1.5), ((30, 27, 16), 1.0), ((64, 64, 64), 1.5),
+             ((512, 512, 16), 1.0), ((512, 512, 16), 1.5), ((1024, 256, 16), 1.0)]
+    for N, pf in cases:
         bases = [sf.FunctionSpace(N[0], 'F', dtype='D'), sf.FunctionSpace(N[1], 'F', dtype='D'),
                  sf.FunctionSpace(N[2], 'F', dtype='d')]
         T = sf.TensorProductSpace(comm, bases)
@@ -90,7 +95,7 @@ def main():
     e6 = float(torch.sqrt(en[0]/en[1]))
     if rank == 0:
         print(f'MKM 3 steps vs reference {e6:.2e}', flush=True)
-    worst = max(worst, e4, e5, e6*1e-2)     # gate for e6: 1e-9 (ill-conditioned biharmonic solves)
+    worst = max(worst, e4, e5, e6*1e-1)     # gate for e6: 1e-11 as in tests/test_gpu_channelflow.py
     if max(e4, e5) > 1e-12:
         print(f'[rank {rank}] helmholtz {e4:.2e} NS {e5:.2e}', flush=True)
     w = torch.tensor([worst], dtype=torch.float64, device='cuda')
@@ -98,7 +103,7 @@ def main():
     if rank == 0:
         print(f'helmholtz solve/matvec {e4:.2e}  NS 5 steps {e5:.2e}  WORST {w.item():.3e} world={world}', flush=True)
     dist.destroy_process_group()
-    sys.exit(0 if w.item() < 1e-11 else 1)
+    sys.exit(0 if w.item() < 1e-12 else 1)
 
 
 if __name__ == '__main__':

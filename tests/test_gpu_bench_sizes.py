@@ -1,0 +1,352 @@
+"""Oracle parity for every register-resident kernel instantiation the BASELINE configs run
+(VERDICT r1, weak 1): line lengths 512 / 768 / 1024 / 1536 and the other `Sched<...>` sizes of
+csrc/fft_fast.cu, plain and 3/2-padded, strided and contiguous, the peer-chunked layouts of the
+slab exchange (including the 16-column peer-store variant, driven here with local "peer" buffers),
+the fused C2R-cross kernel, the Chebyshev DCT kernels and the line solvers at n = 512 / 1024.
+
+Each case compares the device result with the numpy oracle on the same seeded input; the batch is
+small (the oracle finishes in milliseconds) but never a multiple of the tile width, and large
+enough that persistent kernels walk several tiles per CTA.  Tolerance: relative L2 <= 1e-12
+(north_star) unless a line next to the assert says why not.
+Reference behaviour: tests/test_tensorproductspace.py:59-120, tests/test_matrices.py:559-591.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2, BCS, oracle_spec
+import shenfun_b200 as sf
+from shenfun_b200 import ops, la
+from oracle import fourier as of
+from oracle import tensorproduct as otp
+from oracle import polybases as opb
+from oracle import la as ola
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+STRIDED_M = [64, 128, 256, 512, 1024, 96, 192, 384, 768, 1536, 1152]
+CONTIG_M = [32, 64, 128, 256, 512, 1024, 96, 192, 384, 768, 576]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def crand(rng, shape):
+    return rng.standard_normal(shape)+1j*rng.standard_normal(shape)
+
+
+# ---- Fourier, strided axis (c2c along axis 0 / 1 of the 3-D arrays) ---------------------------
+@pytest.mark.parametrize('M', STRIDED_M)
+def test_strided_c2c_plain(M):
+    rng = np.random.default_rng(M)
+    outer, inner = 3, 150                       # 450 lines: ragged against tiles of 4, 8 and 16
+    u = crand(rng, (outer, M, inner))
+    ud = dev(u)
+    out = torch.empty_like(ud)
+    ops.fft_c2c_forward(ud, out, outer, inner, M, M, 1./M)
+    assert rel_l2(out.cpu().numpy(), of.c2c_forward(u, 1, M)) < TOL
+    ops.fft_c2c_backward(ud, out, outer, inner, M, M)
+    assert rel_l2(out.cpu().numpy(), of.c2c_backward(u, 1)) < TOL
+    # in place (the un-padded plan runs the complex axes in place)
+    w = ud.clone()
+    ops.fft_c2c_forward(w, w, outer, inner, M, M, 1./M)
+    assert rel_l2(w.cpu().numpy(), of.c2c_forward(u, 1, M)) < TOL
+    # dealias_direct (2/3 rule)
+    ops.fft_c2c_backward(ud, out, outer, inner, M, M, 1.0, True)
+    assert rel_l2(out.cpu().numpy(), of.c2c_backward(u, 1, dealias_direct=True)) < TOL
+
+
+@pytest.mark.parametrize('N', [64, 128, 256, 512, 768, 1024])
+def test_strided_c2c_padded(N):
+    """3/2 rule: zero-padded backward (residue-split `fft_strided_pad3x_kernel` / widest-radix-first
+    schedule) and truncating forward (`fft_strided_pipe_kernel` at 768 / 1536)."""
+    M = 3*N//2
+    rng = np.random.default_rng(N+1)
+    outer, inner = 2, 1300                      # 2600 lines = 325 tiles of 8: > 2 tiles per CTA of a persistent grid
+    if M >= 1152:
+        inner = 700
+    vh = crand(rng, (outer, N, inner))
+    out = torch.empty((outer, M, inner), dtype=torch.complex128, device='cuda')
+    ops.fft_c2c_backward(dev(vh), out, outer, inner, M, N)
+    assert rel_l2(out.cpu().numpy(), of.c2c_backward(vh, 1, M)) < TOL
+    u = crand(rng, (outer, M, inner))
+    outf = torch.empty((outer, N, inner), dtype=torch.complex128, device='cuda')
+    ops.fft_c2c_forward(dev(u), outf, outer, inner, M, N, 1./M)
+    assert rel_l2(outf.cpu().numpy(), of.c2c_forward(u, 1, N, M)) < TOL
+
+
+# ---- Fourier, contiguous axis (r2c / c2r / c2c along the last axis) --------------------------
+@pytest.mark.parametrize('M', CONTIG_M)
+def test_contig_plain(M):
+    rng = np.random.default_rng(M+2)
+    lines = 77
+    n = 2*M
+    u = rng.standard_normal((lines, n))
+    out = torch.empty((lines, M+1), dtype=torch.complex128, device='cuda')
+    ops.fft_r2c_forward(dev(u), out, lines, 1, n, n, 1./n)
+    assert rel_l2(out.cpu().numpy(), of.r2c_forward(u, 1, n)) < TOL
+    vh = crand(rng, (lines, M+1))
+    outr = torch.empty((lines, n), dtype=torch.float64, device='cuda')
+    ops.fft_c2r_backward(dev(vh), outr, lines, 1, n, n)
+    assert rel_l2(outr.cpu().numpy(), of.c2r_backward(vh, 1, n)) < TOL
+    ops.fft_c2r_backward(dev(vh), outr, lines, 1, n, n, 1.0, True)
+    assert rel_l2(outr.cpu().numpy(), of.c2r_backward(vh, 1, n, dealias_direct=True)) < TOL
+    c = crand(rng, (lines, M))
+    outc = torch.empty((lines, M), dtype=torch.complex128, device='cuda')
+    ops.fft_c2c_forward(dev(c), outc, lines, 1, M, M, 1./M)
+    assert rel_l2(outc.cpu().numpy(), of.c2c_forward(c, 1, M)) < TOL
+    ops.fft_c2c_backward(dev(c), outc, lines, 1, M, M)
+    assert rel_l2(outc.cpu().numpy(), of.c2c_backward(c, 1)) < TOL
+
+
+@pytest.mark.parametrize('N', [64, 128, 256, 512, 768, 1024])
+def test_contig_padded(N):
+    """Padded r2c / c2r of the last axis: 512 -> 768 is `fft_contig_kernel<Sched<384,...>>`."""
+    n = 3*N//2
+    rng = np.random.default_rng(N+3)
+    lines = 77
+    vh = crand(rng, (lines, N//2+1))
+    outr = torch.empty((lines, n), dtype=torch.float64, device='cuda')
+    ops.fft_c2r_backward(dev(vh), outr, lines, 1, n, N)
+    assert rel_l2(outr.cpu().numpy(), of.c2r_backward(vh, 1, N, n)) < TOL
+    u = rng.standard_normal((lines, n))
+    out = torch.empty((lines, N//2+1), dtype=torch.complex128, device='cuda')
+    ops.fft_r2c_forward(dev(u), out, lines, 1, n, N, 1./n)
+    assert rel_l2(out.cpu().numpy(), of.r2c_forward(u, 1, N, n)) < TOL
+
+
+# ---- the slab-exchange layouts -----------------------------------------------------------------
+def _chunked(a, P):
+    """[outer][n][inner] -> the peer-chunked layout [P][outer][n/P][inner] (shenb200.h, shb_fft_c2c_chunked)."""
+    outer, n, inner = a.shape
+    return np.ascontiguousarray(a.reshape(outer, P, n//P, inner).transpose(1, 0, 2, 3))
+
+
+@pytest.mark.parametrize('P', [2, 4, 8])
+@pytest.mark.parametrize('M,N', [(512, 512), (768, 512), (256, 256), (1024, 1024)])
+@pytest.mark.parametrize('backward', [False, True])
+def test_chunked_layouts(P, M, N, backward):
+    """The kernels either side of the all-to-all address the send / receive layout directly."""
+    rng = np.random.default_rng(P+M)
+    outer, inner = 3, 44
+    n_in, n_out = (N, M) if backward else (M, N)
+    u = crand(rng, (outer, n_in, inner))
+    ref = of.c2c_backward(u, 1, M) if backward else of.c2c_forward(u, 1, N, M)
+    scale = 1.0 if backward else 1./M
+    # producer side: plain input, chunked output
+    out = torch.empty((P, outer, n_out//P, inner), dtype=torch.complex128, device='cuda')
+    ops.fft_c2c_chunked(backward, dev(u), out, outer, inner, M, N, scale, False, 0, n_out//P)
+    assert rel_l2(out.cpu().numpy(), _chunked(ref, P)) < TOL
+    # consumer side: chunked input, plain output
+    out2 = torch.empty((outer, n_out, inner), dtype=torch.complex128, device='cuda')
+    ops.fft_c2c_chunked(backward, dev(_chunked(u, P)), out2, outer, inner, M, N, scale, False, n_in//P, 0)
+    assert rel_l2(out2.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize('P', [2, 4, 8])
+@pytest.mark.parametrize('M,N', [(512, 512), (768, 512), (256, 256)])
+@pytest.mark.parametrize('backward', [False, True])
+def test_peer_store_kernel_on_local_buffers(P, M, N, backward):
+    """`shb_fft_c2c_peer` (at 512 points: the 16-column `fft_strided_kernel<..., 16, true>` the
+    multi-GPU bench runs) with the P "peer" receive buffers all on this device: block p of the
+    output must land in buffer p exactly as the all-to-all would deliver it."""
+    rng = np.random.default_rng(3*P+M)
+    outer, inner = 3, 50
+    n_in, n_out = (N, M) if backward else (M, N)
+    u = crand(rng, (outer, n_in, inner))
+    ref = _chunked(of.c2c_backward(u, 1, M) if backward else of.c2c_forward(u, 1, N, M), P)
+    bufs = [torch.zeros((outer, n_out//P, inner), dtype=torch.complex128, device='cuda') for _ in range(P)]
+    ops.fft_c2c_peer(backward, dev(u), [b.data_ptr() for b in bufs], outer, inner, M, N,
+                     1.0 if backward else 1./M, False, 0, n_out//P)
+    for p in range(P):
+        assert rel_l2(bufs[p].cpu().numpy(), ref[p]) < TOL, p
+
+
+# ---- C2R fused with the cross product (NS nonlinear term) -----------------------------------
+@pytest.mark.parametrize('n_fft,N', [(768, 512), (512, 512), (384, 256), (64, 64), (1024, 1024), (1536, 1024)])
+def test_c2r_cross(n_fft, N):
+    rng = np.random.default_rng(n_fft)
+    lines = 203
+    ns = N//2+1
+    ah = crand(rng, (3, lines, ns))
+    bh = crand(rng, (3, lines, ns))
+    a = of.c2r_backward(ah, 2, N, n_fft)
+    b = of.c2r_backward(bh, 2, N, n_fft)
+    ref = np.cross(a, b, axis=0)
+    out = torch.empty((3, lines, n_fft), dtype=torch.float64, device='cuda')
+    ops.fft_c2r_cross(dev(ah), dev(b), out, lines, n_fft, N)             # one field already physical
+    assert rel_l2(out.cpu().numpy(), ref) < TOL
+    ops.fft_c2r_cross(dev(ah), dev(bh), out, lines, n_fft, N)            # both spectral (DUAL)
+    assert rel_l2(out.cpu().numpy(), ref) < TOL
+
+
+# ---- whole plans at the BASELINE line lengths -------------------------------------------------
+@pytest.mark.parametrize('N', [(512, 8, 6), (8, 512, 6), (6, 8, 512), (1024, 4, 6), (4, 1024, 6), (6, 4, 1024),
+                               (768, 8, 6), (8, 768, 6), (6, 8, 768)])
+@pytest.mark.parametrize('pf', [1.0, 1.5])
+@pytest.mark.parametrize('ncomp', [1, 3])
+def test_plans_with_one_long_axis(N, pf, ncomp):
+    """TensorProductSpace.forward / backward with one BASELINE-length axis (512, 768, 1024; padded:
+    768, 1152, 1536 points), scalar and three-component, against oracle.tensorproduct
+    (cf. tests/test_tensorproductspace.py:59-120)."""
+    rng = np.random.default_rng(sum(N)+ncomp)
+    dts = 'DDd'
+    T = sf.TensorProductSpace(sf.comm, [sf.FunctionSpace(n, 'F', dtype=dt) for n, dt in zip(N, dts)])
+    Tp = T.get_dealiased((pf,)*3)
+    d = [('C2C' if dt == 'D' else 'R2C', n, int(np.floor(pf*n))) for n, dt in zip(N, dts)]
+    S, Sp = (T, Tp) if ncomp == 1 else (sf.VectorSpace(T), sf.VectorSpace(Tp))
+    lead = 0 if ncomp == 1 else 1
+    u = rng.standard_normal(Sp.shape(False))
+    uh = Sp.forward(sf.Array(Sp, buffer=u))
+    assert rel_l2(uh.get(), otp.forward(u, d, lead=lead)) < TOL
+    vh = crand(rng, S.shape(True))
+    v = Sp.backward(sf.Function(S, buffer=vh))
+    assert rel_l2(v.get(), otp.backward(vh, d, lead=lead)) < TOL
+
+
+# ---- Chebyshev DCT kernels and forward transforms at n = 512 / 1024 ------------------------
+@pytest.mark.parametrize('N', [512, 1024, 768])
+@pytest.mark.parametrize('name', ['dirichlet', 'biharmonic', 'neumann', 'ortho'])
+@pytest.mark.parametrize('pf', [1.0, 1.5])
+def test_chebyshev_lines(N, name, pf):
+    rng = np.random.default_rng(N+int(10*pf))
+    S = sf.FunctionSpace(N, 'C', bc=BCS[name], padding_factor=pf)
+    spec = oracle_spec(S)
+    Np, d = S.physical_len(), S.dim()
+    outer, inner = 2, 37
+    u = crand(rng, (outer, Np, inner))
+    out = torch.empty((outer, N, inner), dtype=torch.complex128, device='cuda')
+    S._scalar_product_axis(dev(u), out, outer, inner)
+    o = out.cpu().numpy()
+    assert rel_l2(o[:, :d], opb.scalar_product_axis(u, 1, spec)[:, :d]) < TOL
+    assert np.all(o[:, d:] == 0)
+    vh = crand(rng, (outer, N, inner))
+    vh[:, d:] = 0
+    outp = torch.empty((outer, Np, inner), dtype=torch.complex128, device='cuda')
+    S._backward_axis(dev(vh), outp, outer, inner)
+    assert rel_l2(outp.cpu().numpy(), opb.backward_axis(vh, 1, spec)) < TOL
+    # real data (the non-periodic axis transformed first)
+    ur = np.ascontiguousarray(u.real)
+    outr = torch.empty((outer, N, inner), dtype=torch.float64, device='cuda')
+    S._scalar_product_axis(dev(ur), outr, outer, inner)
+    assert rel_l2(outr.cpu().numpy()[:, :d], opb.scalar_product_axis(ur, 1, spec)[:, :d]) < TOL
+
+
+def _cond_tol(A):
+    """Two LU solves of the same system agree to cond(A)*eps, not to eps: the bar for a banded solve
+    compared with another elimination (LAPACK in the oracle, the reference's own order in a golden
+    file) is max(1e-12, 20*eps*cond_2(A))."""
+    return max(TOL, 20*np.finfo(float).eps*np.linalg.cond(A))
+
+
+@pytest.mark.parametrize('N', [512, 1024])
+@pytest.mark.parametrize('fam,name', [('C', 'dirichlet'), ('C', 'biharmonic'), ('C', 'neumann')])
+def test_forward_with_inverse_mass_long_lines(N, fam, name):
+    """Forward transform = scalar product + banded inverse-mass solve (TDMA / PDMA, shared table) at
+    the solver line lengths of configs 2 and 5."""
+    rng = np.random.default_rng(N)
+    S = sf.FunctionSpace(N, fam, bc=BCS[name])
+    spec = oracle_spec(S)
+    outer, inner = 2, 37
+    u = crand(rng, (outer, N, inner))
+    out = torch.empty((outer, N, inner), dtype=torch.complex128, device='cuda')
+    S._forward_axis(dev(u), out, outer, inner)
+    assert rel_l2(out.cpu().numpy(), opb.forward_axis(u, 1, spec)) < _cond_tol(spec['mass'])
+
+
+@pytest.mark.parametrize('n', [512, 1024])
+@pytest.mark.parametrize('axis', [0, 1])
+def test_chebyshev_helmholtz_long_lines(n, axis):
+    """chebyshev.la.Helmholtz at the line length of config 2 (512) and config 5 (1024), against the
+    line-by-line restatement of la.pyx:744-756, 896-905."""
+    rng = np.random.default_rng(n+axis)
+    SD = sf.FunctionSpace(n, 'C', bc=(0, 0))
+    K1 = sf.FunctionSpace(12, 'F', dtype='D')
+    K2 = sf.FunctionSpace(10, 'F', dtype='d')
+    if axis == 0:
+        T = sf.TensorProductSpace(sf.comm, (SD, K1, K2))
+        k1 = np.fft.fftfreq(12, 1./12)[None, :, None]
+    else:
+        T = sf.TensorProductSpace(sf.comm, (K1, SD, K2), axes=(1, 0, 2))
+        k1 = np.fft.fftfreq(12, 1./12)[:, None, None]
+    k2 = np.fft.rfftfreq(10, 1./10)[None, None, :]
+    u, v = sf.TrialFunction(T), sf.TestFunction(T)
+    H = la.Helmholtz(sf.inner(v, sf.div(sf.grad(u))-2.5*u))
+    f = crand(rng, T.shape(True))
+    sl = [slice(None)]*3
+    sl[axis] = slice(SD.dim(), None)
+    f[tuple(sl)] = 0
+    x = H(sf.Function(T, buffer=f), sf.Function(T)).get()
+    ref = ola.helmholtz_solve(SD.spectral_matrix(0, 2).diags(), SD.mass_matrix().diags(), np.ones((1, 1, 1)),
+                              -(k1**2+k2**2)-2.5, f, axis)
+    assert rel_l2(x, ref) < TOL
+    # solve o matvec round trip (tests/test_matrices.py:559-591)
+    c = H.matvec(sf.Function(T, buffer=x), sf.Function(T)).get()
+    sd = [slice(None)]*3
+    sd[axis] = slice(0, SD.dim())
+    assert rel_l2(c[tuple(sd)], f[tuple(sd)]) < 1e-11   # residual of a matrix with entries ~ n^2: eps * ||A|| ||x|| / ||b||
+
+
+@pytest.mark.parametrize('n', [256, 512])
+@pytest.mark.parametrize('fam,bc,kind', [('L', (0, 0), 'poisson'), ('L', (0, 0, 0, 0), 'biharmonic'),
+                                          ('C', (0, 0), 'poisson')])
+def test_solver_generic_1nd_long_lines(n, fam, bc, kind):
+    """SolverGeneric1ND (per-line LU from the O(N) diagonals) at n = 256 (config 3) and 512."""
+    rng = np.random.default_rng(n)
+    S = sf.FunctionSpace(n, fam, bc=bc)
+    K1 = sf.FunctionSpace(6, 'F', dtype='D')
+    K2 = sf.FunctionSpace(6, 'F', dtype='d')
+    T = sf.TensorProductSpace(sf.comm, (S, K1, K2))
+    u, v = sf.TrialFunction(T), sf.TestFunction(T)
+    k1 = np.fft.fftfreq(6, 1./6)[None, :, None]
+    k2 = np.fft.rfftfreq(6, 1./6)[None, None, :]
+    k = k1**2+k2**2
+    B = S.mass_matrix().diags()
+    A2 = S.spectral_matrix(0, 2).diags()
+    if kind == 'poisson':
+        H = la.SolverGeneric1ND(sf.inner(v, sf.div(sf.grad(u))-1.5*u))
+        mats, scales = [A2, B], [np.ones_like(k), -k-1.5]
+    else:
+        A4 = S.spectral_matrix(0, 4).diags()
+        H = la.SolverGeneric1ND(sf.inner(v, sf.div(sf.grad(sf.div(sf.grad(u))))))
+        mats, scales = [A4, A2, B], [np.ones_like(k), -2*k, k**2]
+    f = crand(rng, T.shape(True))
+    f[S.dim():] = 0
+    x = H(sf.Function(T, buffer=f), sf.Function(T)).get()
+    d = S.dim()
+    ref = ola.solve_generic_1nd([m[:d, :d] for m in mats], scales, f, 0)
+    worst = max(np.linalg.cond(sum(s.ravel()[i]*m[:d, :d] for s, m in zip(scales, mats)))
+                for i in (0, k.size-1))
+    assert rel_l2(x[:d], ref[:d]) < max(TOL, 20*np.finfo(float).eps*worst)
+
+
+@pytest.mark.parametrize('n', [64, 256])
+def test_chebyshev_biharmonic_long_lines(n):
+    """chebyshev.la.Biharmonic against dense LU per line; bar = cond * eps (see _cond_tol)."""
+    rng = np.random.default_rng(n)
+    SB = sf.FunctionSpace(n, 'C', bc=(0, 0, 0, 0))
+    K1 = sf.FunctionSpace(4, 'F', dtype='D')
+    K2 = sf.FunctionSpace(4, 'F', dtype='d')
+    T = sf.TensorProductSpace(sf.comm, (SB, K1, K2))
+    u, v = sf.TrialFunction(T), sf.TestFunction(T)
+    H = la.Biharmonic(sf.inner(v, sf.div(sf.grad(sf.div(sf.grad(u))))))
+    f = crand(rng, T.shape(True))
+    d = SB.dim()
+    f[d:] = 0
+    x = H(sf.Function(T, buffer=f), sf.Function(T)).get()
+    k1 = np.fft.fftfreq(4, 1./4)[None, :, None]
+    k2 = np.fft.rfftfreq(4, 1./4)[None, None, :]
+    k = k1**2+k2**2
+    S4 = SB.spectral_matrix(0, 4).diags()[:d, :d]
+    A2 = SB.spectral_matrix(0, 2).diags()[:d, :d]
+    B = SB.mass_matrix().diags()[:d, :d]
+    ref = np.zeros_like(f)
+    worst = 0.0
+    for j in range(4):
+        for l in range(3):
+            Hm = S4-2*k[0, j, l]*A2+k[0, j, l]**2*B
+            ref[:d, j, l] = np.linalg.solve(Hm, f[:d, j, l])
+            worst = max(worst, np.linalg.cond(Hm))
+    assert rel_l2(x[:d], ref[:d]) < max(TOL, 20*np.finfo(float).eps*worst)
