@@ -255,6 +255,43 @@ def poly_3d():
     save('poly3d', **out)
 
 
+def poly_3d_inhom():
+    """Inhomogeneous boundary values in a tensor-product space (BoundaryValues.set_tensor_bcs,
+    tensorproductspace.py:1909-2032): constants and functions of the other coordinates; the
+    polynomial axis first and in the middle; forward, backward of the result, set_boundary_dofs."""
+    import sympy as sp
+    x, y, z = sp.symbols('x,y,z', real=True)
+    out = {}
+    for fam in ('C', 'L'):
+        for layout in ('first', 'middle'):
+            other = (y, z) if layout == 'first' else (x, z)
+            kinds = {
+                'const': {'left': {'D': 1.5}, 'right': {'D': -0.5}},
+                'func': {'left': {'D': sp.cos(2*other[0])*sp.sin(other[1])}, 'right': {'D': 0.25+sp.sin(other[0])}},
+                'neumann': {'left': {'N': 0.75}, 'right': {'N': sp.cos(other[1])}},
+            }
+            for kind, bc in kinds.items():
+                SD = sf.FunctionSpace(14, fam, bc=bc)
+                K1 = sf.FunctionSpace(12, 'F', dtype='D')
+                K2 = sf.FunctionSpace(10, 'F', dtype='d')
+                if layout == 'first':
+                    T = sf.TensorProductSpace(sf.comm, (SD, K1, K2))
+                else:
+                    T = sf.TensorProductSpace(sf.comm, (K1, SD, K2), axes=(1, 0, 2))
+                tag = f'{fam}_{kind}_{layout}'
+                u = rng.standard_normal(T.shape(False))
+                ua = sf.Array(T)
+                ua[:] = u
+                out[f'u_{tag}'] = u
+                uh = T.forward(ua, sf.Function(T))
+                out[f'fw_{tag}'] = np.array(uh)
+                out[f'bw_{tag}'] = np.array(T.backward(uh, sf.Array(T)))
+                f0 = sf.Function(T)
+                f0.set_boundary_dofs()
+                out[f'bdofs_{tag}'] = np.array(f0)
+    save('poly3d_inhom', **out)
+
+
 def solvers():
     """la.TDMA/PDMA/... along axes; SolverGeneric1ND Poisson / biharmonic; Chebyshev Helmholtz."""
     from shenfun import la, inner, div, grad, TestFunction, TrialFunction, Dx

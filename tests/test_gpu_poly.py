@@ -338,3 +338,34 @@ def test_biharmonic3d_demo_manufactured_solution(fam):
     from shenfun_b200.demos import biharmonic3d
     err, _ = biharmonic3d.main((32, 32, 32), fam)
     assert err < 1e-8, err
+
+
+@pytest.mark.parametrize('fam', ['C', 'L'])
+@pytest.mark.parametrize('layout', ['first', 'middle'])
+@pytest.mark.parametrize('kind', ['const', 'func', 'neumann'])
+def test_3d_inhomogeneous_boundary_values_golden(fam, layout, kind):
+    """Inhomogeneous boundary values in a tensor-product space: the boundary data
+    is a function of the other coordinates and is transformed along them
+    (`BoundaryValues.set_tensor_bcs`, tensorproductspace.py:1909-2032); forward, backward and
+    `Function.set_boundary_dofs` against the reference's own run (tests/golden/make_golden.py::poly_3d_inhom)."""
+    import sympy as sp
+    x, y, z = sp.symbols('x,y,z', real=True)
+    g = load_golden('poly3d_inhom')
+    other = (y, z) if layout == 'first' else (x, z)
+    bc = {
+        'const': {'left': {'D': 1.5}, 'right': {'D': -0.5}},
+        'func': {'left': {'D': sp.cos(2*other[0])*sp.sin(other[1])}, 'right': {'D': 0.25+sp.sin(other[0])}},
+        'neumann': {'left': {'N': 0.75}, 'right': {'N': sp.cos(other[1])}},
+    }[kind]
+    SD = sf.FunctionSpace(14, fam, bc=bc)
+    K1 = sf.FunctionSpace(12, 'F', dtype='D')
+    K2 = sf.FunctionSpace(10, 'F', dtype='d')
+    T = sf.TensorProductSpace(sf.comm, (SD, K1, K2)) if layout == 'first' else \
+        sf.TensorProductSpace(sf.comm, (K1, SD, K2), axes=(1, 0, 2))
+    tag = f'{fam}_{kind}_{layout}'
+    uh = T.forward(g[f'u_{tag}'])
+    assert rel_l2(uh.get(), g[f'fw_{tag}']) < TOL
+    assert rel_l2(T.backward(sf.Function(T, buffer=g[f'fw_{tag}'])).get(), g[f'bw_{tag}']) < TOL
+    f0 = sf.Function(T)
+    f0.set_boundary_dofs()
+    assert rel_l2(f0.get(), g[f'bdofs_{tag}']) < TOL
