@@ -249,6 +249,24 @@ SHB_API int shb_helmholtz_factor(const double *d_A0, const double *d_A2, const d
 SHB_API int shb_helmholtz_solve(const void *d_b, void *d_u, const double *d_d0, const double *d_d1,
                                 const double *d_d2, const double *d_L, int64_t outer, int64_t inner, int n,
                                 int n_fac, int n_u, int is_complex, int flags, void *stream);
+/* The same solver from ONE stored array per line: d_invd0[outer][n][inner] = 1/d0 (written by
+ * shb_helmholtz_factor_lean); d1, d2 and L are regenerated from the O(N) diagonals and the per-line
+ * (alfa, beta) inside the solve (d2 obeys the recurrence of the forward substitution and rides along
+ * as a third right-hand side).  Every line is cut into chunks of rows solved by different threads
+ * (chunk maps + scan), the line stays in registers between the sweeps: b is read once, u written
+ * once (1.25x the algorithmic bytes with the 1/d0 read).  Dirichlet variant only.
+ * SHB_ERR_UNSUPPORTED when n is too long for one CTA (callers use the four-array form).           */
+SHB_API int shb_helmholtz_factor_lean(const double *d_A0, const double *d_A2, const double *d_A4,
+                                      const double *d_Bm2, const double *d_B0, const double *d_B2,
+                                      const double *d_alfa, const double *d_beta, double *d_invd0,
+                                      int64_t outer, int64_t inner, int n, void *stream);
+/* The solve takes the four diagonals it needs as two interleaved tables of
+ * shb_helmholtz_lean_table_rows(n) rows, zero beyond row n:
+ *   d_tabF[i] = { Bm2[i-2] (0 for i < 2), A4[i] },   d_tabB[i] = { A2[i], B2[i] }.               */
+SHB_API int shb_helmholtz_lean_table_rows(int n);
+SHB_API int shb_helmholtz_solve_lean(const void *d_b, void *d_u, const double *d_tabF, const double *d_tabB,
+                                     const double *d_alfa, const double *d_beta, const double *d_invd0,
+                                     int64_t outer, int64_t inner, int n, int n_u, int is_complex, void *stream);
 /* c = (alfa*A + beta*B) v with running sums over the constant rows of A; replaces
  * Helmholtz_matvec (optimization/cython/Matvec.pyx:656-712).                    */
 SHB_API int shb_helmholtz_matvec(const void *d_v, void *d_c, const double *d_A0, const double *d_A2,

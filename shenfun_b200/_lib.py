@@ -50,6 +50,9 @@ def _declare(lib):
         'shb_dot_grad3d': [vp, vp, vp, i64, vp],
         'shb_helmholtz_factor': [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp],
         'shb_helmholtz_solve': [vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, vp],
+        'shb_helmholtz_factor_lean': [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, vp],
+        'shb_helmholtz_solve_lean': [vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp],
+        'shb_helmholtz_lean_table_rows': [i32],
         'shb_cheb_scalar_product': [vp, vp, i64, i64, i32, i32, f64, i32, i32, i32, vp, vp, vp],
         'shb_helmholtz_matvec': [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp],
         'shb_biharmonic_factor': [vp, vp, vp, vp, vp, i64, i64, i32, vp],

@@ -10,6 +10,7 @@ per-line factors of `SolverGeneric1ND` / `Helmholtz` are computed on the device
 straight from the O(N) diagonals and the per-line scales -- the reference's
 O(N0*N1) Python assembly loop (la.py:1248-1263) has no counterpart.
 """
+import os
 import numpy as np
 import torch
 
@@ -668,8 +669,18 @@ class Helmholtz:
             if off > 4:
                 assert np.allclose(A[off], A[4][:len(A[off])], rtol=1e-12, atol=0), 'A must have constant rows'
         self._tabs = [diag(A, 0, n), diag(A, 2, n-2), diag(A, 4, n-4), diag(B, -2, n-2), diag(B, 0, n), diag(B, 2, n-2)]
-        self.fac = torch.empty((4, op.outer, n, op.inner), dtype=torch.float64, device=self.alfa.device)
-        ops.helmholtz_factor(*self._tabs, self.alfa, self.beta, self.fac, op.outer, op.inner, n)
+        # one stored array per line (1/d0); d1, d2, L are regenerated inside the chunk-parallel solve
+        # (csrc/linesolve.cu).  Lines too long for one CTA keep the reference's four arrays.
+        self.lean = n <= Helmholtz.LEAN_MAX_N and os.environ.get('SHB_HELMHOLTZ_LEAN', '0') == '1'
+        if self.lean:
+            self.fac = torch.empty((op.outer, n, op.inner), dtype=torch.float64, device=self.alfa.device)
+            ops.helmholtz_factor_lean(self._tabs, self.alfa, self.beta, self.fac, op.outer, op.inner, n)
+            self._lean_tabs = ops.helmholtz_lean_tables(self._tabs, n)
+        else:
+            self.fac = torch.empty((4, op.outer, n, op.inner), dtype=torch.float64, device=self.alfa.device)
+            ops.helmholtz_factor(*self._tabs, self.alfa, self.beta, self.fac, op.outer, op.inner, n)
+
+    LEAN_MAX_N = 1024
 
     def matvec(self, v, c):
         op = self.op
@@ -683,7 +694,11 @@ class Helmholtz:
         if u is None:
             u = b
         ut = ops.plain(u)
-        ops.helmholtz_solve(bt, ut, self.fac, op.outer, op.inner, op.n_rows, op.n_u)
+        if self.lean:
+            ops.helmholtz_solve_lean(bt, ut, self._lean_tabs, self.alfa, self.beta, self.fac, op.outer, op.inner,
+                                     op.n_rows, op.n_u)
+        else:
+            ops.helmholtz_solve(bt, ut, self.fac, op.outer, op.inner, op.n_rows, op.n_u)
         if hasattr(u, 'set_boundary_dofs'):
             u.set_boundary_dofs()
         return u

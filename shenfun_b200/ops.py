@@ -204,6 +204,34 @@ def helmholtz_solve(b, u, fac, outer, inner, n, n_u, n_fac=None, neumann=False, 
           _lib.stream_ptr())
 
 
+def helmholtz_factor_lean(tabs, alfa, beta, invd0, outer, inner, n):
+    """invd0[outer][n][inner] = 1/d0 of every line (tabs = A0, A2, A4, Bm2, B0, B2)."""
+    _call('shb_helmholtz_factor_lean', *[_req(t, F64, 'table') for t in tabs], _req(alfa, F64, 'alfa'),
+          _req(beta, F64, 'beta'), _req(invd0, F64, 'invd0'), outer, inner, n, _lib.stream_ptr())
+
+
+def helmholtz_lean_tables(tabs, n):
+    """The two interleaved diagonal tables of shb_helmholtz_solve_lean (see shenb200.h)."""
+    A0, A2, A4, Bm2, B0, B2 = tabs
+    rows = int(_lib.load().shb_helmholtz_lean_table_rows(n))
+    tF = torch.zeros((rows, 2), dtype=F64, device=A0.device)
+    tB = torch.zeros((rows, 2), dtype=F64, device=A0.device)
+    tF[2:n, 0] = Bm2[:n-2]
+    tF[:n, 1] = A4[:n]
+    tB[:n, 0] = A2[:n]
+    tB[:n, 1] = B2[:n]
+    return tF, tB
+
+
+def helmholtz_solve_lean(b, u, lean_tabs, alfa, beta, invd0, outer, inner, n, n_u):
+    """Chunk-parallel Helmholtz solve from the single stored factor array."""
+    assert b.dtype == u.dtype
+    tF, tB = lean_tabs
+    _call('shb_helmholtz_solve_lean', _req(b, b.dtype, 'b'), _req(u, u.dtype, 'u'), _req(tF, F64, 'tabF'),
+          _req(tB, F64, 'tabB'), _req(alfa, F64, 'alfa'), _req(beta, F64, 'beta'), _req(invd0, F64, 'invd0'),
+          outer, inner, n, n_u, int(u.dtype.is_complex), _lib.stream_ptr())
+
+
 def _stencil_args(soff, sten):
     import ctypes
     offs = (ctypes.c_int*len(soff))(*[int(o) for o in soff])
