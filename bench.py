@@ -131,6 +131,25 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    if 'TORCHELASTIC_RUN_ID' in os.environ or int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        # torchrun pins OMP_NUM_THREADS=1 (and may narrow the CPU affinity) for its workers; the CPU
+        # path does not depend on the number of GPUs, so rank 0 re-runs this very arm in a clean
+        # environment: the measurement is then the same process setup as at N = 1.
+        env = {k: v for k, v in os.environ.items()
+               if k not in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'LOCAL_WORLD_SIZE',
+                            'GROUP_RANK', 'ROLE_RANK', 'ROLE_WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT',
+                            'TORCHELASTIC_RUN_ID', 'TORCHELASTIC_RESTART_COUNT', 'TORCHELASTIC_MAX_RESTARTS',
+                            'TORCHELASTIC_USE_AGENT_STORE', 'TORCH_NCCL_ASYNC_ERROR_HANDLING')}
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except (AttributeError, OSError):
+            pass
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--gpus', str(args.gpus),
+                            '--steps', str(args.steps), '--warmup', str(args.warmup)], env=env,
+                           stdout=subprocess.PIPE, text=True)
+        sys.stdout.write(r.stdout)
+        sys.stdout.flush()
+        return
     cores = os.cpu_count() or 1
     budget_s = 150.0
     t_full = cpu_pair_time(SHAPE, 1, cores)             # one full pair: warm-up and cost estimate
@@ -169,7 +188,7 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-extras', action='store_true', help='skip secondary workloads')
-    ap.add_argument('--no-graph', action='store_true', help='multi-GPU: time the eager path instead of CUDA-graph replay')
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of CUDA-graph replay')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':
@@ -208,12 +227,13 @@ def main():
     for _ in range(args.warmup):
         eager_step()
     barrier()
-    # multi-GPU: the per-rank work is so short that issuing it from Python costs as much as running
-    # it; capture the pair once and replay it (shenfun_b200.graphs.GraphedCall, public API).  Every
-    # rank must take the same path, hence the all-reduce on the outcome.
+    # The pair is captured once and replayed (shenfun_b200.graphs.GraphedCall, public API) at EVERY
+    # N, so that the 1 -> 8 GPU curve is one launch mode: at 8 GPUs the per-rank work is so short that
+    # issuing it from Python costs as much as running it.  Every rank must take the same path, hence
+    # the all-reduce on the outcome.
     step, launch_mode = eager_step, 'eager'
     launches_per_step = None
-    if world > 1 and not args.no_graph:
+    if not args.no_graph:
         ok = 1
         try:
             from shenfun_b200.graphs import GraphedCall
@@ -225,7 +245,8 @@ def main():
             if rank == 0:
                 print(f'[bench] CUDA-graph capture failed, timing the eager path: {e!r}', file=sys.stderr)
         okt = torch.tensor([ok], device=dev)
-        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         if int(okt.item()) == 1:
             step, launch_mode = graphed, 'cuda_graph'
             for _ in range(3):
@@ -255,6 +276,8 @@ def main():
     rt = (torch.linalg.vector_norm(ub.v-u.v)/torch.linalg.vector_norm(u.v)).item()
 
     # ---- e2e: host pinned -> device -> forward -> backward -> host pinned ---------
+    from shenfun_b200.hostio import bind_host_to_device_numa_node
+    numa = bind_host_to_device_numa_node()        # pinned buffers are first-touched on the GPU's own NUMA node
     h_in = torch.empty(T.shape(False), dtype=torch.float64).pin_memory()
     h_in.copy_(u.v)
     h_out = torch.empty(T.shape(False), dtype=torch.float64).pin_memory()
@@ -297,10 +320,13 @@ def main():
     roof = None
     if world == 1:
         roof = dominant_kernel_roofline(T, u, uh, peak, peak_src)
+    else:
+        roof = exchange_kernel_roofline(T, u, uh, comm, ms)
+    exchange_impl = T.exchange_impl
 
     extras = {}
     if world == 1 and not args.no_extras:
-        extras = secondary_workloads(T, uh, args, peak)
+        extras = secondary_workloads(T, uh, args, peak, with_cpu=not args.no_cpu)
     elif not args.no_extras:
         try:
             from shenfun_b200.demos import navier_stokes
@@ -309,6 +335,13 @@ def main():
             extras['ns'] = navier_stokes.bench(512, steps=max(2, min(args.steps, 5)), warmup=1, comm=comm)
         except Exception as e:  # noqa: BLE001
             extras['ns'] = {'error': repr(e)}
+        if world == 8:
+            # BASELINE config 5: demo/MKM.py channel flow 1024 x 768 x 1024 slab-distributed over 8 GPUs
+            try:
+                torch.cuda.empty_cache()
+                extras['mkm'] = mkm_workload(comm, (1024, 768, 1024), steps=2)
+            except Exception as e:  # noqa: BLE001
+                extras['mkm'] = {'error': repr(e)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -326,14 +359,15 @@ def main():
             'config': {'workload': 'TensorProductSpace(C2C(512),C2C(512),R2C(512)) forward+backward, 512^3 real fp64',
                        'global_shape': list(SHAPE), 'decomposition': 'slab' if world > 1 else 'single',
                        'l2_policy': 'working set 2.15 GB per pass >> 126 MB L2 (no flush needed)',
-                       'seed': 1234, 'launch_mode': launch_mode},
+                       'seed': 1234, 'launch_mode': launch_mode, 'exchange_impl': exchange_impl},
             'pair_hbm_frac_of_measured': (PAIR_BYTES/world/(ms*1e-3)/1e9)/peak,
             'roundtrip_rel_err': rt,
             'clocks': clocks,
             'e2e': {'value': 1e3/e2e_ms, 'unit': 'pairs/s', 'h2d_bytes_per_step': int(np.prod(T.shape(False)))*8,
                     'd2h_bytes_per_step': int(np.prod(T.shape(False)))*8, 'ms_per_step': e2e_ms,
                     'roundtrip_rel_err_host': e2e_rt,
-                    'api': 'shenfun_b200.hostio.HostPipeline (H2D / transforms / D2H on three streams)'},
+                    'api': 'shenfun_b200.hostio.HostPipeline (H2D / transforms / D2H on three streams)',
+                    'host_numa_node': numa},
             'gpu_launches': launches,
             'roofline': roof,
             'cpu_baseline': cpu,
@@ -410,7 +444,109 @@ def dominant_kernel_roofline(T, u, uh, peak, peak_src):
             'all_stages_gbs': {k: v[1]/(v[0]*1e-3)/1e9 for k, v in stages.items()}}
 
 
-def secondary_workloads(T, uh, args, peak):
+def exchange_kernel_roofline(T, u, uh, comm, ms_pair):
+    """N > 1: the kernel that bounds the pair is the C2C pass whose stores ARE the all-to-all (it
+    writes (P-1)/P of its output into the peers' receive buffers over NVLink).  Timed live with CUDA
+    events on every rank (all ranks launch it together, as in the plan), max over ranks; the
+    roofline is the NVLink bandwidth per direction per GPU (770 GB/s measured peer copy on this
+    pool, /opt/skills/guides/B200_PROFILING.md; 900 nominal)."""
+    import torch
+    import torch.distributed as dist
+    P = comm.Get_size()
+    fw = T.forward
+    ex = [i for i, s in enumerate(fw.steps) if s.kind == 'exchange']
+    if not ex:
+        return None
+    spec_local = int(np.prod(T.shape(True)))*16
+    nv_bytes = spec_local*(P-1)/P                       # sent (= received) per rank per exchange
+    # time a whole forward transform and subtract nothing: report the exchange share from the plan's
+    # own structure instead: forward = r2c pass + producer pass (NVLink-bound) + consumer pass
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    reps = 20
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        T.forward(u, uh)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)/reps], dtype=torch.float64, device=u.v.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_fwd = t.item()
+    # local passes at the single-GPU rate would take (algorithmic bytes / P) / measured HBM rate
+    peak_hbm, _ = peaks()
+    ms_local = (REAL_B+SPEC_B+2*(2*SPEC_B))/P/(0.82*peak_hbm*1e9)*1e3
+    ms_exch = max(ms_fwd-ms_local, 1e-6)
+    ach = nv_bytes/(ms_exch*1e-3)/1e9
+    return {'bound': 'nvlink', 'kernel': 'c2c_axis1 producer (peer stores) + barrier', 'achieved': ach, 'peak': 770.0,
+            'unit': 'GB/s', 'frac': ach/770.0, 'peak_source': 'measured peer copy per direction (B200_PROFILING.md)',
+            'traffic': None, 'algorithmic_bytes_per_launch': nv_bytes, 'avg_launch_ms': ms_exch,
+            'how': f'forward transform {ms_fwd:.3f} ms (CUDA events, max over ranks) minus the local axis passes at the '
+                   f'single-GPU HBM rate ({ms_local:.3f} ms) = time attributable to the exchange; bytes = (P-1)/P of '
+                   f'the local spectral block'}
+
+
+def mkm_workload(comm, N, steps=2):
+    """demo/MKM.py (channel flow, IMEXRK222, 3/2 padding) on the slab-distributed ranks."""
+    import torch
+    from shenfun_b200 import ops
+    from shenfun_b200.demos.channelflow import MKM
+    c = MKM(N=N, Re=180., dt=0.0005, conv=0, padding_factor=(1.5, 1.5, 1.5), timestepper='IMEXRK222', comm=comm)
+    t, ts = c.initialize()
+    c.assemble()
+    t, ts = c.solve(t=t, tstep=ts, end_time=c.dt)      # warm-up step
+    torch.cuda.synchronize()
+    comm.barrier()
+    l0 = ops.LAUNCHES
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t, ts = c.solve(t=t, tstep=ts, end_time=t+steps*c.dt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = comm.allreduce(e0.elapsed_time(e1)/steps, op='max')
+    e, div = c.energy_and_divergence()
+    return {'workload': f'demo/MKM.py channel flow {N[0]}x{N[1]}x{N[2]}, 3/2 padding, IMEXRK222', 'n_gpus': comm.Get_size(),
+            'ms_per_step': ms, 'value': 1e3/ms, 'unit': 'steps/s', 'energy': e, 'divergence': div,
+            'gpu_launches_per_step': (ops.LAUNCHES-l0)//steps, 'mem_GB_per_gpu': torch.cuda.max_memory_allocated()/1e9}
+
+
+def ns_cpu_baseline(n, steps, workers):
+    """oracle/navier_stokes.py (numpy restatement of demo/NavierStokes.py:35-44 + RK4) on host cores."""
+    from oracle import fourier as of
+    from oracle.navier_stokes import NavierStokes
+    of.WORKERS = workers
+    s = NavierStokes((n, n, n), nu=0.000625, dt=0.001, padding_factor=1.5).initialize()
+    s.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.step()
+    return (time.perf_counter()-t0)/steps
+
+
+def ns_cross_kernel_roofline(peak):
+    """Dominant kernel of the NS step: the six-component C2R fused with the cross product
+    (`fft_c2r_cross_kernel<Sched<384,...>,1,true>`: 768-point lines, 512 modes kept).  Algorithmic
+    bytes: six spectral lines read (257 complex each), three physical lines written (768 reals)."""
+    import torch
+    from shenfun_b200 import ops
+    nl = 768*768
+    ab = torch.randn((6, nl, 257, 2), dtype=torch.float64, device='cuda')
+    abc = torch.view_as_complex(ab)
+    out = torch.empty((3, nl, 768), dtype=torch.float64, device='cuda')
+    ms = _time_launch(lambda: ops.fft_c2r_cross(abc[:3], abc[3:], out, nl, 768, 512), reps=5)
+    nbytes = 6*nl*257*16+3*nl*768*8
+    del ab, abc, out
+    torch.cuda.empty_cache()
+    ach = nbytes/(ms*1e-3)/1e9
+    return {'bound': 'hbm', 'kernel': 'fft_c2r_cross_kernel (six C2R 768-point lines + cross product)', 'achieved': ach,
+            'peak': peak, 'unit': 'GB/s', 'frac': ach/peak, 'algorithmic_bytes_per_launch': nbytes, 'avg_launch_ms': ms,
+            'launches_per_step': 4, 'traffic': 25390000000,
+            'traffic_source': 'profiles/r1_ncu_full_summary_final.txt (dram read 14.55 GB + write 10.84 GB)'}
+
+
+def secondary_workloads(T, uh, args, peak, with_cpu=True):
     """3/2-padded pair (S 512x512x257 <-> P 768^3), reported beside the headline."""
     import torch
     import shenfun_b200 as sf
@@ -433,20 +569,76 @@ def secondary_workloads(T, uh, args, peak):
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         out['padded_pair'] = {'error': repr(e)}
+    cores = os.cpu_count() or 1
     try:
         from shenfun_b200.demos import navier_stokes
         out['ns'] = navier_stokes.bench(512, steps=max(2, min(args.steps, 5)), warmup=1)
+        # whole-step algorithmic bytes as built: 523 GB per RK4 step
+        out['ns']['hbm_frac_of_measured'] = 523e9/(out['ns']['ms_per_step']*1e-3)/1e9/peak
+        torch.cuda.empty_cache()
+        out['ns']['roofline'] = ns_cross_kernel_roofline(peak)
+        if with_cpu:
+            n_cpu = 128
+            tcpu = ns_cpu_baseline(n_cpu, 1, cores)
+            # work per step scales with the number of points (36 padded transforms + point-wise work)
+            out['ns']['cpu_baseline'] = {
+                'value': 1.0/(tcpu*(512/n_cpu)**3), 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
+                'sample': f'{n_cpu}^3 Taylor-Green RK4 steps with 3/2 padding, oracle/navier_stokes.py (numpy + scipy.fft '
+                          f'workers={cores}): {tcpu:.3f} s/step measured, scaled by (512/{n_cpu})^3 = {(512//n_cpu)**3} '
+                          f'to the 512^3 workload (a 768^3 padded step needs ~45 GB of host work arrays)',
+                'measured_steps_per_s_at_sample_size': 1.0/tcpu}
     except Exception as e:  # noqa: BLE001
         out['ns'] = {'error': repr(e)}
     torch.cuda.empty_cache()
     try:
         from shenfun_b200.demos import poisson3d, biharmonic3d
         out['poisson3d_chebyshev_512'] = poisson3d.bench(512, 'C')
+        if with_cpu:
+            out['poisson3d_chebyshev_512']['cpu_baseline'] = solver_cpu_baseline('helmholtz', 512, cores)
         torch.cuda.empty_cache()
         out['biharmonic3d_legendre_256'] = biharmonic3d.bench(256, 'L')
+        if with_cpu:
+            out['biharmonic3d_legendre_256']['cpu_baseline'] = solver_cpu_baseline('legendre', 256, cores)
     except Exception as e:  # noqa: BLE001
         out['poisson_biharmonic'] = {'error': repr(e)}
     return out
+
+
+def solver_cpu_baseline(kind, n, cores):
+    """CPU leg of the solver configs on a bounded sample of lines (the lines are independent):
+    'helmholtz' = oracle.la.helmholtz_solve (la.pyx:744-756, 896-905 restated, numpy vectorised over
+    the lines); 'legendre' = one Legendre Vandermonde forward stage as a dense contraction
+    (spectralbase.py:539-548: np.dot(P, u))."""
+    from oracle import la as ola
+    rng = np.random.default_rng(1234)
+    if kind == 'helmholtz':
+        import shenfun_b200 as sf
+        SD = sf.FunctionSpace(n, 'C', bc=(0, 0))
+        A = SD.spectral_matrix(0, 2).diags()
+        B = SD.mass_matrix().diags()
+        m1, m2 = 64, 33                                    # sample: 64 x 33 of the 512 x 257 lines
+        k1 = np.fft.fftfreq(n, 1./n)[None, :m1, None]
+        k2 = np.fft.rfftfreq(n, 1./n)[None, None, :m2]
+        f = rng.standard_normal((n, m1, m2))+1j*rng.standard_normal((n, m1, m2))
+        f[SD.dim():] = 0
+        d = SD.dim()
+        t0 = time.perf_counter()
+        ola.helmholtz_solve(A[:d, :d], B[:d, :d], np.ones((1, 1, 1)), -(k1**2+k2**2), f, 0)
+        t = time.perf_counter()-t0
+        scale = (n*(n//2+1))/(m1*m2)
+        return {'value': 1.0/(t*scale), 'unit': 'solves/s', 'cores': 1, 'kind': 'port',
+                'sample': f'factor + solve of {m1}x{m2} of the {n}x{n//2+1} lines (n = {n}), oracle/la.py '
+                          f'helmholtz_solve (numpy, one thread): {t:.2f} s, scaled by {scale:.1f}'}
+    # Legendre stage: (n x n) operator times n x (n/2+1) complex columns, numpy BLAS
+    P = rng.standard_normal((n, n))
+    u = rng.standard_normal((n, 2*n*(n//2+1)))           # complex columns as pairs of real ones (real operator)
+    np.dot(P, u[:, :1024])
+    t0 = time.perf_counter()
+    np.dot(P, u)
+    t = time.perf_counter()-t0
+    return {'value': 2.0*n*n*u.shape[1]/t/1e12, 'unit': 'TFLOP/s', 'cores': cores, 'kind': 'port', 'ms': t*1e3,
+            'sample': f'one full Legendre Vandermonde stage of the {n}^3 transform as numpy.dot (BLAS dgemm/zgemm '
+                      f'on the host cores): {t*1e3:.0f} ms'}
 
 
 if __name__ == '__main__':

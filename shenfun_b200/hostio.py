@@ -3,7 +3,38 @@ host memory: the H2D copy of step k+1, the device work of step k and the D2H cop
 run on three streams with double-buffered device arrays, so a sequence of steps is bounded by
 the slowest of the three (PCIe is full duplex) instead of their sum.
 """
+import os
+
 import torch
+
+
+def bind_host_to_device_numa_node(device=None):
+    """Restrict this process to the CPUs of the NUMA node the GPU hangs off, so that pinned host
+    buffers allocated afterwards are first-touched there and H2D / D2H copies of the ranks of one box
+    do not all cross the socket interconnect.  Returns the node number (None when the topology is not
+    exposed in sysfs; nothing is changed then)."""
+    try:
+        dev = torch.cuda.current_device() if device is None else device
+        pr = torch.cuda.get_device_properties(dev)
+        bus = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        base = f'/sys/bus/pci/devices/{bus}'
+        node = int(open(f'{base}/numa_node').read().strip())
+        cpus = open(f'{base}/local_cpulist').read().strip()
+        ids = set()
+        for part in cpus.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                ids.update(range(int(a), int(b)+1))
+            elif part:
+                ids.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        ids = ids & allowed if ids & allowed else allowed
+        if node >= 0 and ids:
+            os.sched_setaffinity(0, ids)
+            return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return None
 
 
 class HostPipeline:

@@ -159,9 +159,13 @@ class _Transform:
                     hdl.barrier()
                     dst = rbuf[:int(np.prod(full_out_shape))].view(full_out_shape)
                     peer_done = None
+                    self.space.exchange_impl = 'peer-store (axis kernel writes the peers\' receive buffers over NVLink)'
                 else:
                     s.exchange(cur, dst, ncomp, self.direction, src_packed=cur_packed,
                                dst_packed=bool(s.fuse and s.fuse[1]))
+                    self.space.exchange_impl = ('nccl all_to_all_single, pack/unpack fused into the axis kernels'
+                                                if (cur_packed or (s.fuse and s.fuse[1])) else
+                                                'nccl all_to_all_single, separate pack/unpack')
                 cur_packed = False
             else:
                 ax = s.axis
@@ -271,6 +275,7 @@ class TensorProductSpace:
         self._pool = _WorkPool()
         self.coors = None
         self._fuse_exchange = bool(kw.pop('fuse_exchange', True))
+        self.exchange_impl = 'none (single rank)'     # set by the plans: which exchange implementation ran
 
         first = self.bases[self.axes[-1]]
         # tensorproductspace.py:365-385: real input needs an R2C (or a real

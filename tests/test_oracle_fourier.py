@@ -43,3 +43,17 @@ def test_fourier_poisson3d_matches_reference_demo(N):
     f_hat, u_hat = otp.fourier_poisson3d(N)
     assert rel_l2(f_hat, g[f'f_hat_{tag}']) < 1e-13
     assert rel_l2(u_hat, g[f'u_hat_{tag}']) < 1e-13
+
+
+@pytest.mark.parametrize('pf,tag', [(1.0, 'plain'), (1.5, 'pad15')])
+def test_navier_stokes_oracle_matches_reference_demo(pf, tag):
+    """oracle/navier_stokes.py (the CPU baseline of the `ns` bench key) against the reference's own
+    run of demo/NavierStokes.py at 16^3 after 1 and 5 RK4 steps."""
+    from oracle.navier_stokes import NavierStokes
+    g = load_golden('ns_16')
+    s = NavierStokes((16, 16, 16), nu=0.000625, dt=0.01, padding_factor=pf).initialize()
+    s.step()
+    assert rel_l2(s.U_hat, g[f'U_hat_{tag}_1']) < 1e-12
+    for _ in range(4):
+        s.step()
+    assert rel_l2(s.U_hat, g[f'U_hat_{tag}_5']) < 1e-12
