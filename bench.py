@@ -277,10 +277,13 @@ def main():
 
     # ---- e2e: host pinned -> device -> forward -> backward -> host pinned ---------
     from shenfun_b200.hostio import bind_host_to_device_numa_node
+    aff0 = os.sched_getaffinity(0)
     numa = bind_host_to_device_numa_node()        # pinned buffers are first-touched on the GPU's own NUMA node
     h_in = torch.empty(T.shape(False), dtype=torch.float64).pin_memory()
     h_in.copy_(u.v)
     h_out = torch.empty(T.shape(False), dtype=torch.float64).pin_memory()
+    h_out.zero_()
+    os.sched_setaffinity(0, aff0)                 # the CPU legs below use every core again
     from shenfun_b200.hostio import HostPipeline
     uh2 = [sf.Function(T), sf.Function(T)]
     cnt = [0]

@@ -99,6 +99,20 @@ SHB_API int shb_fft_c2c_peer(int backward, const void *d_in, void *const *d_peer
                              int64_t outer, int64_t inner, int n_fft, int N, double scale, int flags,
                              int in_chunk_rows, int out_chunk_rows, void *stream);
 
+/* The same transform on an arbitrary family of lines, for exchanges that are cut into pieces and
+ * overlapped with the neighbouring passes: line (a, b), a < na, b < ncols, has element r at
+ *     a*as + r*rs + b + c0                                   (plain side)
+ *     (r / cr)*chunk_stride + a*as + (r % cr)*rs + b + c0     (peer-chunked side, cr = chunk_rows)
+ * with separate (as, rs) for input and output.  The [outer][n][inner] array of the entry points
+ * above is na = outer, ncols = inner, c0 = 0, rs = inner, as = n*inner (chunked: cr*inner); a column
+ * sub-range, or the lines of a flattened (j, c) inner index for one range of c, are other settings.
+ * d_peer_out (may be NULL): nranks peer receive buffers as in shb_fft_c2c_peer; else d_out.
+ * SHB_ERR_UNSUPPORTED for line lengths without a register-resident kernel.                        */
+SHB_API int shb_fft_c2c_lines(int backward, const void *d_in, void *d_out, void *const *d_peer_out, int nranks,
+                              int64_t na, int64_t ncols, int64_t c0, int64_t in_as, int64_t in_rs, int64_t out_as,
+                              int64_t out_rs, int n_fft, int N, double scale, int flags, int in_chunk_rows,
+                              int64_t in_chunk_stride, int out_chunk_rows, int64_t out_chunk_stride, void *stream);
+
 /* Real-to-complex forward DFT of length n_fft, truncation to N//2+1 modes
  * (Nyquist -> 2*Re when N even and N < n_fft), scaling.
  * in : real [outer][n_fft][inner];  out : complex [outer][N/2+1][inner].  */

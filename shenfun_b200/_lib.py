@@ -34,6 +34,8 @@ def _declare(lib):
         'shb_fft_c2c_backward': [vp, vp, i64, i64, i32, i32, f64, i32, vp],
         'shb_fft_r2c_forward': [vp, vp, i64, i64, i32, i32, f64, vp],
         'shb_fft_c2r_backward': [vp, vp, i64, i64, i32, i32, f64, i32, vp],
+        'shb_fft_c2c_lines': [i32, vp, vp, vp, i32, i64, i64, i64, i64, i64, i64, i64, i32, i32, f64, i32, i32, i64, i32,
+                              i64, vp],
         'shb_fft_c2c_chunked': [i32, vp, vp, i64, i64, i32, i32, f64, i32, i32, i32, vp],
         'shb_fft_c2c_peer': [i32, vp, vp, i32, i64, i64, i32, i32, f64, i32, i32, i32, vp],
         'shb_fft_c2r_cross': [vp, vp, vp, i64, i32, i32, f64, i32, vp],

@@ -59,6 +59,29 @@ int shb_fft_c2c_peer(int backward, const void *d_in, void *const *d_peer_out, in
     return rc;
 }
 
+int shb_fft_c2c_lines(int backward, const void *d_in, void *d_out, void *const *d_peer_out, int nranks, int64_t na,
+                      int64_t ncols, int64_t c0, int64_t in_as, int64_t in_rs, int64_t out_as, int64_t out_rs,
+                      int n_fft, int N, double scale, int flags, int in_chunk_rows, int64_t in_chunk_stride,
+                      int out_chunk_rows, int64_t out_chunk_stride, void *stream) {
+    if (!d_in || (!d_out && !d_peer_out) || na < 0 || ncols < 0 || c0 < 0 || n_fft < 1 || N < 1 || N > n_fft ||
+        in_chunk_rows < 0 || out_chunk_rows < 0 || nranks < 0 || nranks > 8 || (d_peer_out && out_chunk_rows <= 0)) {
+        set_error("fft_c2c_lines: bad arguments");
+        return SHB_ERR_ARG;
+    }
+    const int n_in = backward ? N : n_fft, n_out = backward ? n_fft : N;
+    if ((in_chunk_rows && n_in % in_chunk_rows) || (out_chunk_rows && n_out % out_chunk_rows) ||
+        (d_peer_out && n_out / out_chunk_rows != nranks)) {
+        set_error("fft_c2c_lines: chunk rows must split the axis into equal blocks (one per rank for peer stores)");
+        return SHB_ERR_ARG;
+    }
+    int rc = fft_fast_launch_general(backward ? FFT_C2C_BWD : FFT_C2C_FWD, d_in, d_peer_out ? d_peer_out[0] : d_out, na,
+                                     ncols, c0, in_as, in_rs, out_as, out_rs, n_fft, N, scale, flags,
+                                     reinterpret_cast<cudaStream_t>(stream), in_chunk_rows, in_chunk_stride,
+                                     out_chunk_rows, out_chunk_stride, d_peer_out, d_peer_out ? nranks : 0);
+    if (rc == SHB_ERR_UNSUPPORTED) set_error("fft_c2c_lines: no register-resident kernel for n_fft=%d", n_fft);
+    return rc;
+}
+
 int shb_fft_c2c_chunked(int backward, const void *d_in, void *d_out, int64_t outer, int64_t inner, int n_fft,
                         int N, double scale, int flags, int in_chunk_rows, int out_chunk_rows, void *stream) {
     if (!d_in || !d_out || d_in == d_out || outer < 0 || inner < 0 || n_fft < 1 || N < 1 || N > n_fft ||

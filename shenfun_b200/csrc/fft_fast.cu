@@ -180,6 +180,13 @@ struct FastDesc {
     // buffer of rank p, already offset to the slot of this rank) instead of out + p*out_cs
     cplx *out_peer[8];
     int use_peer;
+    // generalised line addressing of the CH variants of fft_strided_kernel: line -> (a, b) = (line / cw,
+    // line % cw); element r of the line at a*as + r*rs + b + c0 (chunked: p*cs + a*as + (r - p*cr)*rs
+    // + b + c0).  The standard [outer][n][inner] array is cw = inner, c0 = 0, rs = inner,
+    // as = n*inner (chunked: cr*inner); a column sub-range [c0, c0+cw) of it, or lines picked out of
+    // a flattened (j, c) inner index, are other settings of the same five numbers -- what the
+    // column-chunked (overlapped) slab exchange launches.
+    int64_t cw, c0, in_as, in_rs, out_as, out_rs;
 };
 
 // zero-padding rule of the C2C backward transform as a branch-free gather:
@@ -214,22 +221,30 @@ fft_strided_kernel(const __grid_constant__ FastDesc d) {
     const int j = threadIdx.x / T;
     const int64_t line = (int64_t)blockIdx.x * T + c;
     const bool valid = line < d.nlines;
-    const int64_t o = valid ? line / d.inner : 0, cc = valid ? line % d.inner : 0;
+    const int64_t dv = CH ? d.cw : d.inner;
+    const int64_t o = valid ? line / dv : 0, cc = valid ? line % dv : 0;
     const cplx *__restrict__ inb = reinterpret_cast<const cplx *>(d.in);
     cplx *__restrict__ outb = reinterpret_cast<cplx *>(d.out);
+    const int64_t ib = CH ? o * d.in_as + cc + d.c0 : 0, ob = CH ? o * d.out_as + cc + d.c0 : 0;
     auto in_at = [&](int r) -> const cplx & {
-        if (CH && d.in_cr) {
-            const int p = r / d.in_cr;
-            return inb[p * d.in_cs + ((o * d.in_cr + (r - p * d.in_cr)) * d.inner + cc)];
+        if (CH) {
+            if (d.in_cr) {
+                const int p = r / d.in_cr;
+                return inb[p * d.in_cs + ib + (r - p * d.in_cr) * d.in_rs];
+            }
+            return inb[ib + r * d.in_rs];
         }
         return inb[(o * d.n_in + r) * d.inner + cc];
     };
     auto out_at = [&](int r) -> cplx & {
-        if (CH && d.out_cr) {
-            const int p = r / d.out_cr;
-            const int64_t off = (o * d.out_cr + (r - p * d.out_cr)) * d.inner + cc;
-            if (d.use_peer) return d.out_peer[p][off];
-            return outb[p * d.out_cs + off];
+        if (CH) {
+            if (d.out_cr) {
+                const int p = r / d.out_cr;
+                const int64_t off = ob + (r - p * d.out_cr) * d.out_rs;
+                if (d.use_peer) return d.out_peer[p][off];
+                return outb[p * d.out_cs + off];
+            }
+            return outb[ob + r * d.out_rs];
         }
         return outb[(o * d.n_out + r) * d.inner + cc];
     };
@@ -1424,6 +1439,12 @@ int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t 
     d.in = in; d.out = out; d.outer = outer; d.inner = inner; d.nlines = outer * inner;
     d.n_fft = n_fft; d.N = N; d.flags = flags; d.scale = scale;
     if (d.nlines == 0) return SHB_OK;
+    {
+        const int n_in = (mode == FFT_C2C_BWD) ? N : n_fft, n_out = (mode == FFT_C2C_BWD) ? n_fft : N;
+        d.cw = inner; d.c0 = 0; d.in_rs = inner; d.out_rs = inner;
+        d.in_as = (int64_t)(in_cr ? in_cr : n_in) * inner;
+        d.out_as = (int64_t)(out_cr ? out_cr : n_out) * inner;
+    }
     const int ns = N / 2 + 1;
     int M;
     switch (mode) {
@@ -1463,6 +1484,51 @@ int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t 
     case FFT_R2C: return contig_r2c(M, d, st);
     default: return contig_c2r(M, d, st);
     }
+}
+
+// C2C along a strided axis with fully general line addressing (FastDesc::cw ... out_rs): the
+// column-chunked slab exchange.  Only the sizes served by fft_strided_kernel (not its persistent
+// pipelined variant) are covered.
+int fft_fast_launch_general(int mode, const void *in, void *out, int64_t na, int64_t ncols, int64_t c0, int64_t in_as,
+                            int64_t in_rs, int64_t out_as, int64_t out_rs, int n_fft, int N, double scale, int flags,
+                            cudaStream_t st, int in_cr, int64_t in_cs, int out_cr, int64_t out_cs,
+                            void *const *peer_out, int npeer) {
+    if (mode != FFT_C2C_FWD && mode != FFT_C2C_BWD) return SHB_ERR_UNSUPPORTED;
+    FastDesc d;
+    d.in_cr = in_cr; d.out_cr = out_cr; d.in_cs = in_cs; d.out_cs = out_cs;
+    d.use_peer = (peer_out != nullptr && npeer > 0);
+    for (int p = 0; p < 8; ++p) d.out_peer[p] = (d.use_peer && p < npeer) ? reinterpret_cast<cplx *>(peer_out[p]) : nullptr;
+    d.in = in; d.out = out; d.outer = na; d.inner = ncols; d.nlines = na * ncols;
+    d.n_fft = n_fft; d.N = N; d.flags = flags; d.scale = scale;
+    d.cw = ncols; d.c0 = c0; d.in_as = in_as; d.in_rs = in_rs; d.out_as = out_as; d.out_rs = out_rs;
+    if (d.nlines == 0) return SHB_OK;
+    const int M = n_fft;
+    d.n_in = (mode == FFT_C2C_BWD) ? N : n_fft; d.n_out = (mode == FFT_C2C_BWD) ? n_fft : N;
+    d.tw = twiddle_table(0, M);
+    d.tw2 = nullptr;
+    if (!d.tw) { set_error("fft: twiddle table allocation failed"); return SHB_ERR_NOMEM; }
+    using S64 = Sched<64, 8, 8, 1, 8>;
+    using S128 = Sched<128, 8, 4, 4, 32>;
+    using S256 = Sched<256, 8, 8, 4, 32>;
+    using S512 = Sched<512, 8, 8, 8, 64>;
+    using S1024 = Sched<1024, 16, 8, 8, 128>;
+#define SHB_GEN_CASE(MM, SCHED, TT)                                                                       \
+    case MM: return mode == FFT_C2C_FWD ? launch_strided_ch<SCHED, FFT_C2C_FWD, TT, true>(d, st)          \
+                                        : launch_strided_ch<SCHED, FFT_C2C_BWD, TT, true>(d, st);
+    switch (M) {
+        SHB_GEN_CASE(64, S64, 8)
+        SHB_GEN_CASE(128, S128, 8)
+        SHB_GEN_CASE(256, S256, 8)
+        case 512:
+            if (d.use_peer && g_peer_t16)
+                return mode == FFT_C2C_FWD ? launch_strided_ch<S512, FFT_C2C_FWD, 16, true>(d, st)
+                                           : launch_strided_ch<S512, FFT_C2C_BWD, 16, true>(d, st);
+            return mode == FFT_C2C_FWD ? launch_strided_ch<S512, FFT_C2C_FWD, 8, true>(d, st)
+                                       : launch_strided_ch<S512, FFT_C2C_BWD, 8, true>(d, st);
+        SHB_GEN_CASE(1024, S1024, 4)
+    default: return SHB_ERR_UNSUPPORTED;
+    }
+#undef SHB_GEN_CASE
 }
 
 }  // namespace shb

@@ -79,6 +79,21 @@ def fft_c2c_peer(backward, u, peer_ptrs, outer, inner, n_fft, N, scale, dealias_
           scale, int(dealias_direct), int(in_chunk), int(out_chunk), _lib.stream_ptr())
 
 
+def fft_c2c_lines(backward, u, out, peer_ptrs, na, ncols, c0, in_as, in_rs, out_as, out_rs, n_fft, N, scale,
+                  dealias_direct=False, in_chunk=0, in_chunk_stride=0, out_chunk=0, out_chunk_stride=0):
+    """C2C transform of the lines (a, b), a < na, b < ncols, with explicit strides (shenb200.h:
+    shb_fft_c2c_lines); output to `out` or, when `peer_ptrs` is given, into the peers' buffers."""
+    import ctypes
+    arr = None
+    nr = 0
+    if peer_ptrs is not None:
+        arr = (ctypes.c_void_p*len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        nr = len(peer_ptrs)
+    _call('shb_fft_c2c_lines', int(backward), _req(u, C128, 'in'), None if out is None else _req(out, C128, 'out'), arr,
+          nr, na, ncols, c0, in_as, in_rs, out_as, out_rs, n_fft, N, scale, int(dealias_direct), int(in_chunk),
+          int(in_chunk_stride), int(out_chunk), int(out_chunk_stride), _lib.stream_ptr())
+
+
 def fft_c2r_cross(uh, b, out, nlines, n_fft, N, scale=1.0, dealias_direct=False):
     """out = irfft(uh) x b for (3, nlines, .) arrays (C2R fused with the cross product).  A complex
     `b` is a second spectral field, transformed in the same kernel: out = irfft(uh) x irfft(b)."""

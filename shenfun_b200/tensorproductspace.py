@@ -125,7 +125,19 @@ class _Transform:
         bwd = self.direction == 'backward'
         cur_packed = False
         peer_done = None
+        skip_to = 0
         for i, s in enumerate(steps):
+            if i < skip_to:
+                continue
+            # producer pass + exchange + consumer pass cut into column pieces and overlapped
+            if ncomp == 1 and i+2 < n:
+                res = self._overlapped_exchange(i, cur, out, dest_is_out, which)
+                if res is not None:
+                    cur, which = res
+                    cur_is_user_input = False
+                    cur_packed = False
+                    skip_to = i+3
+                    continue
             full_out_shape = lead + s.out_shape
             # fused all-to-all: the axis kernel before an exchange writes the send layout, the one
             # after it reads the receive layout (see transfer.SlabExchange / shb_fft_c2c_chunked)
@@ -201,6 +213,112 @@ class _Transform:
         if cur.data_ptr() != out.data_ptr():
             out.copy_(cur)
         return out
+
+    # ---- overlapped slab exchange ----------------------------------------------------------------
+    def _overlapped_exchange(self, i, cur, out, dest_is_out, which):
+        """Steps i, i+1, i+2 = [C2C pass whose stores are the all-to-all] [exchange] [C2C pass that
+        reads the receive buffers], for a 3-D space exchanged between axes 0 and 1: the last axis is
+        cut into K column ranges; the producer of range k+1 (NVLink-bound: it stores (P-1)/P of its
+        output into the peers' memory) runs while the barrier and the HBM-bound consumer of range k
+        run on a second, higher-priority stream.  Every piece is a set of complete lines for both
+        passes, so no pass ever waits for more than its own piece.  Returns (result tensor, work-pool
+        toggle) or None when the pattern / sizes are not covered (the caller then runs the steps one
+        by one).  Replaces one `Alltoallw` per re-alignment (tensorproductspace.py:89,183,252)."""
+        import os
+        from ._lib import ShenB200Error
+        steps = self.steps
+        sp, se, sc = steps[i], steps[i+1], steps[i+2]
+        K = int(os.environ.get('SHB_EXCHANGE_CHUNKS', '4'))
+        if K <= 1 or getattr(self.space, '_no_overlap', False):
+            return None
+        if not (sp.kind == 'axis' and se.kind == 'exchange' and sc.kind == 'axis' and se.fuse and all(se.fuse)):
+            return None
+        ex = se.exchange
+        if len(sp.in_shape) != 3 or {sp.axis, sc.axis} != {0, 1} or not ex.peer_available():
+            return None
+        for st in (sp, sc):
+            b = st.base
+            if not (b.family() == 'fourier' and b.short_name() == 'C2C' and b.physical_len() in (64, 128, 256, 512, 1024)):
+                return None
+        bwd = self.direction == 'backward'
+        P_, rank = ex.P, ex.rank
+        n2 = sp.in_shape[2]
+        if n2 < 2*K:
+            return None
+        dev = cur.device
+        try:
+            numel = int(np.prod(se.out_shape))
+            rbuf, hdl = ex.peer_buffers(numel, dev)
+        except Exception:  # noqa: BLE001  (no P2P / symmetric memory on this box)
+            ex._peer_broken = True
+            return None
+        slot = (numel//P_)*16*rank
+        peers = [int(p)+slot for p in hdl.buffer_ptrs]
+        # destination of the consumer pass
+        if dest_is_out[i+2] and out.data_ptr() != cur.data_ptr():
+            dst = out
+        else:
+            dst = self._pool.get(which, sc.out_shape, sc.out_dtype, dev)
+            if dst.data_ptr() == cur.data_ptr():
+                which ^= 1
+                dst = self._pool.get(which, sc.out_shape, sc.out_dtype, dev)
+            which ^= 1
+        bp, bc = sp.base, sc.base
+        npf, Np = bp.physical_len(), bp.N
+        ncf, Nc = bc.physical_len(), bc.N
+        if bwd:
+            # producer: along axis 0 of (n0, s1, n2), lines (j, c); consumer: along axis 1 of (g0, n1, n2)
+            s1 = sp.in_shape[1]
+            g0 = sc.out_shape[0]
+            p_in, p_out = (Np, npf)
+            c_in, c_out = (Nc, ncf)
+            prod = dict(na=s1, in_as=n2, in_rs=s1*n2, out_as=n2, out_rs=s1*n2, out_cr=p_out//P_)
+            cons = dict(na=g0, in_as=(c_in//P_)*n2, in_rs=n2, out_as=c_out*n2, out_rs=n2, in_cr=c_in//P_,
+                        in_cs=g0*(c_in//P_)*n2)
+            pscale, cscale = 1.0, 1.0
+            pdd, cdd = bp.dealias_direct, bc.dealias_direct
+        else:
+            # producer: along axis 1 of (g0, n1, n2), lines (i0, c); consumer: along axis 0 of (n0, s1, n2)
+            g0 = sp.in_shape[0]
+            s1 = sc.out_shape[1]
+            p_in, p_out = (npf, Np)
+            c_in, c_out = (ncf, Nc)
+            prod = dict(na=g0, in_as=p_in*n2, in_rs=n2, out_as=(p_out//P_)*n2, out_rs=n2, out_cr=p_out//P_)
+            cons = dict(na=s1, in_as=n2, in_rs=s1*n2, out_as=n2, out_rs=s1*n2, in_cr=c_in//P_,
+                        in_cs=(c_in//P_)*s1*n2)
+            pscale, cscale = 1./npf, 1./ncf
+            pdd = cdd = False
+        st = self.space.__dict__.setdefault('_ovl_streams', None)
+        if st is None:
+            st = self.space._ovl_streams = (torch.cuda.Stream(device=dev, priority=-1),
+                                            [torch.cuda.Event() for _ in range(16)])
+        side, events = st
+        main = torch.cuda.current_stream()
+        bounds = [round(k*n2/K) for k in range(K+1)]
+        try:
+            for k in range(K):
+                c0, cw = bounds[k], bounds[k+1]-bounds[k]
+                ops.fft_c2c_lines(bwd, cur, None, peers, prod['na'], cw, c0, prod['in_as'], prod['in_rs'], prod['out_as'],
+                                  prod['out_rs'], npf, Np, pscale, pdd, 0, 0, prod['out_cr'], 0)
+                ev = events[k % len(events)]
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    hdl.barrier(channel=k % 8)
+                    ops.fft_c2c_lines(bwd, rbuf, dst, None, cons['na'], cw, c0, cons['in_as'], cons['in_rs'],
+                                      cons['out_as'], cons['out_rs'], ncf, Nc, cscale, cdd, cons['in_cr'],
+                                      cons['in_cs'], 0, 0)
+            done = events[K % len(events)]
+            done.record(side)
+            main.wait_event(done)
+        except ShenB200Error as e:
+            if 'fft_c2c_lines' not in str(e):
+                raise
+            self.space._no_overlap = True
+            return None
+        self.space.exchange_impl = (f'peer-store, {K} column pieces: producer pass (NVLink stores) of piece k+1 overlaps '
+                                    f'barrier + consumer pass of piece k on a second stream')
+        return dst, which
 
     def __call__(self, input_array, output_array=None, kind=None, **kw):
         space = self.space

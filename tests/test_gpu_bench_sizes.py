@@ -349,3 +349,46 @@ def test_chebyshev_biharmonic_long_lines(n):
             ref[:d, j, l] = np.linalg.solve(Hm, f[:d, j, l])
             worst = max(worst, np.linalg.cond(Hm))
     assert rel_l2(x[:d], ref[:d]) < max(TOL, 20*np.finfo(float).eps*worst)
+
+
+# ---- arbitrary line families (the column pieces of the overlapped exchange) ---------------------
+@pytest.mark.parametrize('n', [512, 256, 1024])
+@pytest.mark.parametrize('backward', [False, True])
+def test_c2c_lines_column_pieces(n, backward):
+    """`shb_fft_c2c_lines`: a column range of an [a][n][n2] array (lines (a, c)) and of an [n][s1][n2]
+    array (lines (j, c)), plain and through the peer-chunked layouts; untouched columns stay put."""
+    rng = np.random.default_rng(n+backward)
+    na, n2, P = 5, 21, 4
+    c0, cw = 6, 9
+    scale = 1.0 if backward else 1./n
+    tr = (lambda a, ax: of.c2c_backward(a, ax)) if backward else (lambda a, ax: of.c2c_forward(a, ax, n))
+    # (1) standard view, plain in / plain out
+    u = crand(rng, (na, n, n2))
+    out = torch.full((na, n, n2), 7.0, dtype=torch.complex128, device='cuda')
+    ops.fft_c2c_lines(backward, dev(u), out, None, na, cw, c0, n*n2, n2, n*n2, n2, n, n, scale)
+    o = out.cpu().numpy()
+    assert rel_l2(o[:, :, c0:c0+cw], tr(u, 1)[:, :, c0:c0+cw]) < TOL
+    assert np.all(o[:, :, :c0] == 7.0) and np.all(o[:, :, c0+cw:] == 7.0)
+    # (2) split-inner view: lines (j, c) of [n][s1][n2] along axis 0
+    s1 = 6
+    v = crand(rng, (n, s1, n2))
+    out = torch.full((n, s1, n2), 7.0, dtype=torch.complex128, device='cuda')
+    ops.fft_c2c_lines(backward, dev(v), out, None, s1, cw, c0, n2, s1*n2, n2, s1*n2, n, n, scale)
+    o = out.cpu().numpy()
+    assert rel_l2(o[:, :, c0:c0+cw], tr(v, 0)[:, :, c0:c0+cw]) < TOL
+    assert np.all(o[:, :, :c0] == 7.0)
+    # (3) standard view writing P peer buffers, then the split-inner view reading them back:
+    #     exactly the producer / consumer pair of one piece of the exchange on "rank" 0 of P
+    cr = n//P
+    bufs = [torch.zeros((na, cr, n2), dtype=torch.complex128, device='cuda') for _ in range(P)]
+    ops.fft_c2c_lines(backward, dev(u), None, [b.data_ptr() for b in bufs], na, cw, c0, n*n2, n2, cr*n2, n2, n, n, scale,
+                      False, 0, 0, cr, 0)
+    ref = tr(u, 1)
+    for p in range(P):
+        assert rel_l2(bufs[p].cpu().numpy()[:, :, c0:c0+cw], ref[:, p*cr:(p+1)*cr, c0:c0+cw]) < TOL
+    # consumer: receive buffer [P][cr][s1][n2] (chunk p = rows p*cr.. of the transform axis)
+    w = crand(rng, (n, s1, n2))
+    recv = dev(w.reshape(P, cr, s1, n2))
+    out = torch.full((n, s1, n2), 7.0, dtype=torch.complex128, device='cuda')
+    ops.fft_c2c_lines(backward, recv, out, None, s1, cw, c0, n2, s1*n2, n2, s1*n2, n, n, scale, False, cr, cr*s1*n2, 0, 0)
+    assert rel_l2(out.cpu().numpy()[:, :, c0:c0+cw], tr(w, 0)[:, :, c0:c0+cw]) < TOL
