@@ -233,7 +233,7 @@ def main():
     # the all-reduce on the outcome.
     step, launch_mode = eager_step, 'eager'
     launches_per_step = None
-    if not args.no_graph:
+    if not args.no_graph and not os.environ.get('SHB_NO_GRAPH'):
         ok = 1
         try:
             from shenfun_b200.graphs import GraphedCall

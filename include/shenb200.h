@@ -106,10 +106,12 @@ SHB_API int shb_fft_c2c_peer(int backward, const void *d_in, void *const *d_peer
  * with separate (as, rs) for input and output.  The [outer][n][inner] array of the entry points
  * above is na = outer, ncols = inner, c0 = 0, rs = inner, as = n*inner (chunked: cr*inner); a column
  * sub-range, or the lines of a flattened (j, c) inner index for one range of c, are other settings.
+ * Only columns b < ncols_valid are transformed (ncols may be rounded up so that the column tiles
+ * of the kernel line up with a padded row pitch: aligned 128 / 256 B stores into peer memory).
  * d_peer_out (may be NULL): nranks peer receive buffers as in shb_fft_c2c_peer; else d_out.
  * SHB_ERR_UNSUPPORTED for line lengths without a register-resident kernel.                        */
 SHB_API int shb_fft_c2c_lines(int backward, const void *d_in, void *d_out, void *const *d_peer_out, int nranks,
-                              int64_t na, int64_t ncols, int64_t c0, int64_t in_as, int64_t in_rs, int64_t out_as,
+                              int64_t na, int64_t ncols, int64_t ncols_valid, int64_t c0, int64_t in_as, int64_t in_rs, int64_t out_as,
                               int64_t out_rs, int n_fft, int N, double scale, int flags, int in_chunk_rows,
                               int64_t in_chunk_stride, int out_chunk_rows, int64_t out_chunk_stride, void *stream);
 
@@ -197,6 +199,15 @@ SHB_API int shb_rk4_stage(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U
  * linear terms such as KdV's -u_xxx (integrators.py:569-585 uses the complex scale array as is). */
 SHB_API int shb_rk4_stage_cplx(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, const void *d_L,
                                int64_t n, int ncomp, double a_dt, double b_dt, int last, void *stream);
+
+/* out = mask * sum_j coefs[j] * T_j on n real or complex entries (d_terms: HOST array of nterms <= 10
+ * device pointers, coefs: HOST array; mask real [n_mask], applied per entry modulo n_mask, may be NULL);
+ * up to two terms are also copied out unchanged (d_save_dst[k] = T_{save_idx[k]}).  One pass for the
+ * right-hand side of an IMEX Runge-Kutta stage, rhs = (u0, v) + dt sum_j b_j N_j + dt sum_j a_j L_j with
+ * the newest N and L kept for the later stages (shenfun/utilities/integrators.py:692-696, 803-812).  */
+SHB_API int shb_lincomb(void *d_out, int nterms, const void *const *d_terms, const double *coefs,
+                        const double *d_mask, int64_t n_mask, int64_t n, int is_complex, int nsave,
+                        const int *save_idx, void *const *d_save_dst, void *stream);
 
 /* u *= mask on [ncomp][n] complex (Nyquist masking): replaces
  * shenfun/optimization/cython/applymask.pyx:15-169 (`apply_mask`).          */

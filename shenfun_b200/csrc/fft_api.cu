@@ -60,10 +60,10 @@ int shb_fft_c2c_peer(int backward, const void *d_in, void *const *d_peer_out, in
 }
 
 int shb_fft_c2c_lines(int backward, const void *d_in, void *d_out, void *const *d_peer_out, int nranks, int64_t na,
-                      int64_t ncols, int64_t c0, int64_t in_as, int64_t in_rs, int64_t out_as, int64_t out_rs,
+                      int64_t ncols, int64_t ncols_valid, int64_t c0, int64_t in_as, int64_t in_rs, int64_t out_as, int64_t out_rs,
                       int n_fft, int N, double scale, int flags, int in_chunk_rows, int64_t in_chunk_stride,
                       int out_chunk_rows, int64_t out_chunk_stride, void *stream) {
-    if (!d_in || (!d_out && !d_peer_out) || na < 0 || ncols < 0 || c0 < 0 || n_fft < 1 || N < 1 || N > n_fft ||
+    if (!d_in || (!d_out && !d_peer_out) || na < 0 || ncols < 0 || ncols_valid < 0 || ncols_valid > ncols || c0 < 0 || n_fft < 1 || N < 1 || N > n_fft ||
         in_chunk_rows < 0 || out_chunk_rows < 0 || nranks < 0 || nranks > 8 || (d_peer_out && out_chunk_rows <= 0)) {
         set_error("fft_c2c_lines: bad arguments");
         return SHB_ERR_ARG;
@@ -75,7 +75,7 @@ int shb_fft_c2c_lines(int backward, const void *d_in, void *d_out, void *const *
         return SHB_ERR_ARG;
     }
     int rc = fft_fast_launch_general(backward ? FFT_C2C_BWD : FFT_C2C_FWD, d_in, d_peer_out ? d_peer_out[0] : d_out, na,
-                                     ncols, c0, in_as, in_rs, out_as, out_rs, n_fft, N, scale, flags,
+                                     ncols, ncols_valid, c0, in_as, in_rs, out_as, out_rs, n_fft, N, scale, flags,
                                      reinterpret_cast<cudaStream_t>(stream), in_chunk_rows, in_chunk_stride,
                                      out_chunk_rows, out_chunk_stride, d_peer_out, d_peer_out ? nranks : 0);
     if (rc == SHB_ERR_UNSUPPORTED) set_error("fft_c2c_lines: no register-resident kernel for n_fft=%d", n_fft);

@@ -73,7 +73,8 @@ int fft_generic_launch(int mode, const void *in, void *out, int64_t outer, int64
 int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner,
                     int n_fft, int N, double scale, int flags, cudaStream_t st, int in_cr = 0, int out_cr = 0,
                     void *const *peer_out = nullptr, int npeer = 0);
-int fft_fast_launch_general(int mode, const void *in, void *out, int64_t na, int64_t ncols, int64_t c0, int64_t in_as,
+int fft_fast_launch_general(int mode, const void *in, void *out, int64_t na, int64_t ncols, int64_t ncols_valid, int64_t c0,
+                            int64_t in_as,
                             int64_t in_rs, int64_t out_as, int64_t out_rs, int n_fft, int N, double scale, int flags,
                             cudaStream_t st, int in_cr, int64_t in_cs, int out_cr, int64_t out_cs,
                             void *const *peer_out, int npeer);

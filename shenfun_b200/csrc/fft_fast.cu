@@ -187,6 +187,7 @@ struct FastDesc {
     // a flattened (j, c) inner index, are other settings of the same five numbers -- what the
     // column-chunked (overlapped) slab exchange launches.
     int64_t cw, c0, in_as, in_rs, out_as, out_rs;
+    int64_t cvalid;   // columns b >= cvalid of a line family are padding (tiles aligned to a padded pitch)
 };
 
 // zero-padding rule of the C2C backward transform as a branch-free gather:
@@ -220,9 +221,11 @@ fft_strided_kernel(const __grid_constant__ FastDesc d) {
     const int c = threadIdx.x % T;
     const int j = threadIdx.x / T;
     const int64_t line = (int64_t)blockIdx.x * T + c;
-    const bool valid = line < d.nlines;
     const int64_t dv = CH ? d.cw : d.inner;
-    const int64_t o = valid ? line / dv : 0, cc = valid ? line % dv : 0;
+    bool valid_ = line < d.nlines;
+    const int64_t o = valid_ ? line / dv : 0, cc = valid_ ? line % dv : 0;
+    if (CH) valid_ = valid_ && cc < d.cvalid;
+    const bool valid = valid_;
     const cplx *__restrict__ inb = reinterpret_cast<const cplx *>(d.in);
     cplx *__restrict__ outb = reinterpret_cast<cplx *>(d.out);
     const int64_t ib = CH ? o * d.in_as + cc + d.c0 : 0, ob = CH ? o * d.out_as + cc + d.c0 : 0;
@@ -256,19 +259,33 @@ fft_strided_kernel(const __grid_constant__ FastDesc d) {
 
     cplx v[SC::EMAX];
     if (j < SC::NB0) {
-        // branch-free operand fetch: all loads are issued back to back
+        // branch-free operand fetch: all loads are issued back to back.  The un-padded backward
+        // transform (no 3/2-rule gather, no 2/3-rule zeroing) takes the forward transform's plain
+        // path: the row mapping below costs the chunked-input variant 50 % (latency-bound loads)
+        if (MODE != FFT_C2C_BWD || (!pm.padded && !pm.dd)) {
 #pragma unroll
-        for (int q = 0; q < SC::B0; ++q) {
+            for (int q = 0; q < SC::B0; ++q) {
 #pragma unroll
-            for (int m = 0; m < SC::R0; ++m) {
-                const int r = (j + q * P) + m * SC::NB0;
-                bool ok = valid;
-                int src = r;
-                double f = 1.0;
-                if (MODE == FFT_C2C_BWD) ok = pm.map(r, src, f) && valid;
-                cplx x = make_double2(0.0, 0.0);
-                if (ok) x = in_at(src);
-                v[q * SC::R0 + m] = (MODE == FFT_C2C_BWD) ? make_double2(x.x * f, x.y * f) : x;
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int r = (j + q * P) + m * SC::NB0;
+                    cplx x = make_double2(0.0, 0.0);
+                    if (valid) x = in_at(r);
+                    v[q * SC::R0 + m] = x;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q) {
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int r = (j + q * P) + m * SC::NB0;
+                    int src = r;
+                    double f = 1.0;
+                    const bool ok = pm.map(r, src, f) && valid;
+                    cplx x = make_double2(0.0, 0.0);
+                    if (ok) x = in_at(src);
+                    v[q * SC::R0 + m] = make_double2(x.x * f, x.y * f);
+                }
             }
         }
     }
@@ -1441,7 +1458,7 @@ int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t 
     if (d.nlines == 0) return SHB_OK;
     {
         const int n_in = (mode == FFT_C2C_BWD) ? N : n_fft, n_out = (mode == FFT_C2C_BWD) ? n_fft : N;
-        d.cw = inner; d.c0 = 0; d.in_rs = inner; d.out_rs = inner;
+        d.cw = inner; d.cvalid = inner; d.c0 = 0; d.in_rs = inner; d.out_rs = inner;
         d.in_as = (int64_t)(in_cr ? in_cr : n_in) * inner;
         d.out_as = (int64_t)(out_cr ? out_cr : n_out) * inner;
     }
@@ -1489,7 +1506,7 @@ int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t 
 // C2C along a strided axis with fully general line addressing (FastDesc::cw ... out_rs): the
 // column-chunked slab exchange.  Only the sizes served by fft_strided_kernel (not its persistent
 // pipelined variant) are covered.
-int fft_fast_launch_general(int mode, const void *in, void *out, int64_t na, int64_t ncols, int64_t c0, int64_t in_as,
+int fft_fast_launch_general(int mode, const void *in, void *out, int64_t na, int64_t ncols, int64_t ncols_valid, int64_t c0, int64_t in_as,
                             int64_t in_rs, int64_t out_as, int64_t out_rs, int n_fft, int N, double scale, int flags,
                             cudaStream_t st, int in_cr, int64_t in_cs, int out_cr, int64_t out_cs,
                             void *const *peer_out, int npeer) {
@@ -1500,7 +1517,7 @@ int fft_fast_launch_general(int mode, const void *in, void *out, int64_t na, int
     for (int p = 0; p < 8; ++p) d.out_peer[p] = (d.use_peer && p < npeer) ? reinterpret_cast<cplx *>(peer_out[p]) : nullptr;
     d.in = in; d.out = out; d.outer = na; d.inner = ncols; d.nlines = na * ncols;
     d.n_fft = n_fft; d.N = N; d.flags = flags; d.scale = scale;
-    d.cw = ncols; d.c0 = c0; d.in_as = in_as; d.in_rs = in_rs; d.out_as = out_as; d.out_rs = out_rs;
+    d.cw = ncols; d.cvalid = ncols_valid; d.c0 = c0; d.in_as = in_as; d.in_rs = in_rs; d.out_as = out_as; d.out_rs = out_rs;
     if (d.nlines == 0) return SHB_OK;
     const int M = n_fft;
     d.n_in = (mode == FFT_C2C_BWD) ? N : n_fft; d.n_out = (mode == FFT_C2C_BWD) ? n_fft : N;

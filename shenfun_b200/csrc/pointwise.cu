@@ -180,6 +180,40 @@ __global__ void __launch_bounds__(PW_THREADS) apply_mask_kernel(cplx *__restrict
     }
 }
 
+// out = mask * sum_j coef_j T_j  (+ up to two plain copies save_dst = T_idx riding along): the
+// right-hand-side accumulation of one implicit-explicit Runge-Kutta stage
+// (shenfun/utilities/integrators.py:692-696, 803-812: rhs = (u0, v) + dt sum_j b_j N_j + dt sum_j a_j L_j,
+// then the Nyquist mask), one pass over the arrays instead of a copy and an axpy per term.
+// Arrays are addressed as doubles (a complex array is 2n doubles; the mask is per complex entry).
+constexpr int LC_MAXT = 10;
+struct LinComb {
+    const double *t[LC_MAXT];
+    double c[LC_MAXT];
+    int nterms;
+    const double *mask;       // [n_mask] or NULL
+    int64_t n_mask;
+    int cplx_shift;           // 1: two doubles per mask entry
+    double *save_dst[2];
+    int save_idx[2];
+    int nsave;
+};
+__global__ void __launch_bounds__(PW_THREADS) lincomb_kernel(double *__restrict__ out, const LinComb p, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < LC_MAXT; ++j) {
+            if (j < p.nterms) {
+                const double v = p.t[j][i];
+                acc = fma(p.c[j], v, acc);
+                if (p.nsave > 0 && p.save_idx[0] == j) p.save_dst[0][i] = v;
+                if (p.nsave > 1 && p.save_idx[1] == j) p.save_dst[1][i] = v;
+            }
+        }
+        if (p.mask) acc *= p.mask[(i >> p.cplx_shift) % p.n_mask];
+        out[i] = acc;
+    }
+}
+
 // H_i = sum_j u_j g[3 i + j]: the convective term u . grad u in physical space from the nine
 // gradient components (demo/ChannelFlow.py:213-215: three products and two sums per component
 // with numpy temporaries; here twelve arrays are read once and three written once).
@@ -276,6 +310,33 @@ int shb_rk4_stage_cplx(void *d_dU, void *d_u_hat, const void *d_U0, void *d_U1, 
     rk4_stage_kernel<<<pw_blocks(n * ncomp), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         (cplx *)d_dU, (cplx *)d_u_hat, (const cplx *)d_U0, (cplx *)d_U1, nullptr, (const cplx *)d_L, n, ncomp,
         a_dt, b_dt, last);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+int shb_lincomb(void *d_out, int nterms, const void *const *d_terms, const double *coefs, const double *d_mask,
+                int64_t n_mask, int64_t n, int is_complex, int nsave, const int *save_idx, void *const *d_save_dst,
+                void *stream) {
+    SHB_REQUIRE(d_out && d_terms && coefs && nterms >= 1 && nterms <= LC_MAXT && n >= 0 && nsave >= 0 && nsave <= 2 &&
+                (nsave == 0 || (save_idx && d_save_dst)) && (!d_mask || n_mask > 0), "bad arguments");
+    if (n == 0) return SHB_OK;
+    LinComb p;
+    p.nterms = nterms;
+    for (int j = 0; j < LC_MAXT; ++j) {
+        p.t[j] = j < nterms ? reinterpret_cast<const double *>(d_terms[j]) : nullptr;
+        p.c[j] = j < nterms ? coefs[j] : 0.0;
+        SHB_REQUIRE(j >= nterms || p.t[j], "null term");
+    }
+    p.mask = d_mask; p.n_mask = d_mask ? n_mask : 1; p.cplx_shift = is_complex ? 1 : 0;
+    p.nsave = nsave;
+    for (int k = 0; k < 2; ++k) {
+        p.save_idx[k] = k < nsave ? save_idx[k] : -1;
+        p.save_dst[k] = k < nsave ? reinterpret_cast<double *>(d_save_dst[k]) : nullptr;
+        SHB_REQUIRE(k >= nsave || (p.save_dst[k] && p.save_idx[k] >= 0 && p.save_idx[k] < nterms), "bad save slot");
+    }
+    const int64_t nd = is_complex ? 2 * n : n;
+    lincomb_kernel<<<pw_blocks(nd), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<double *>(d_out), p, nd);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }

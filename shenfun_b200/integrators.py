@@ -154,20 +154,34 @@ class PDEIMEXRK:
             self.nonlinear_rhs = Inner(self.v, self.N)
 
     def compute_rhs(self, rk=0):
+        """rhs = (u0, v) + dt sum_j b[rk+1, j] N_j + dt sum_j a[rk+1, j+1] L_j, masked
+        (integrators.py:692-696, 803-812) in ONE pass (`shb_lincomb`); the newest N / L evaluations are
+        written to their slots in the same pass when a later stage needs them."""
         a, b = self.stages()[:2]
-        self.Krhs[rk].copy_(ops.plain(self.nonlinear_rhs()))
+        nsteps = self.steps()
+        n_new = ops.plain(self.nonlinear_rhs())
         if rk == 0:
             self.u0_rhs()        # only at the start of a step
-        rhs = ops.plain(self.rhs)
-        rhs.copy_(ops.plain(self.u0_rhs.output_array))
-        for j in range(0, rk+1):
-            rhs.add_(self.Krhs[j], alpha=self.dt*b[rk+1, j])
+        terms, coefs, saves = [ops.plain(self.u0_rhs.output_array)], [1.0], []
+        for j in range(0, rk):
+            if b[rk+1, j] != 0:
+                terms.append(self.Krhs[j])
+                coefs.append(self.dt*b[rk+1, j])
+        terms.append(n_new)
+        coefs.append(self.dt*b[rk+1, rk])
+        if rk+1 < nsteps:
+            saves.append((len(terms)-1, self.Krhs[rk]))
         if rk > 0:
-            self.Lrhs[rk-1].copy_(ops.plain(self.linear_rhs()))
-            for j in range(0, rk):
-                rhs.add_(self.Lrhs[j], alpha=self.dt*a[rk+1, j+1])
-        if self.mask is not None:
-            ops.apply_mask(rhs, self.mask)
+            l_new = ops.plain(self.linear_rhs())
+            for j in range(0, rk-1):
+                if a[rk+1, j+1] != 0:
+                    terms.append(self.Lrhs[j])
+                    coefs.append(self.dt*a[rk+1, j+1])
+            terms.append(l_new)
+            coefs.append(self.dt*a[rk+1, rk])
+            if rk+1 < nsteps:
+                saves.append((len(terms)-1, self.Lrhs[rk-1]))
+        ops.lincomb(ops.plain(self.rhs), terms, coefs, self.mask, saves)
         return self.rhs
 
     def solve_step(self, rk=0):

@@ -80,7 +80,7 @@ def fft_c2c_peer(backward, u, peer_ptrs, outer, inner, n_fft, N, scale, dealias_
 
 
 def fft_c2c_lines(backward, u, out, peer_ptrs, na, ncols, c0, in_as, in_rs, out_as, out_rs, n_fft, N, scale,
-                  dealias_direct=False, in_chunk=0, in_chunk_stride=0, out_chunk=0, out_chunk_stride=0):
+                  dealias_direct=False, in_chunk=0, in_chunk_stride=0, out_chunk=0, out_chunk_stride=0, ncols_valid=None):
     """C2C transform of the lines (a, b), a < na, b < ncols, with explicit strides (shenb200.h:
     shb_fft_c2c_lines); output to `out` or, when `peer_ptrs` is given, into the peers' buffers."""
     import ctypes
@@ -90,7 +90,8 @@ def fft_c2c_lines(backward, u, out, peer_ptrs, na, ncols, c0, in_as, in_rs, out_
         arr = (ctypes.c_void_p*len(peer_ptrs))(*[int(p) for p in peer_ptrs])
         nr = len(peer_ptrs)
     _call('shb_fft_c2c_lines', int(backward), _req(u, C128, 'in'), None if out is None else _req(out, C128, 'out'), arr,
-          nr, na, ncols, c0, in_as, in_rs, out_as, out_rs, n_fft, N, scale, int(dealias_direct), int(in_chunk),
+          nr, na, ncols, ncols if ncols_valid is None else ncols_valid, c0, in_as, in_rs, out_as, out_rs, n_fft, N, scale,
+          int(dealias_direct), int(in_chunk),
           int(in_chunk_stride), int(out_chunk), int(out_chunk_stride), _lib.stream_ptr())
 
 
@@ -160,6 +161,23 @@ def rk4_stage(dU, u_hat, U0, U1, L, a_dt, b_dt, last):
     _call('shb_rk4_stage', _req(dU, C128, 'dU'), _req(u_hat, C128, 'u_hat'), _req(U0, C128, 'U0'),
           _req(U1, C128, 'U1'), None if L is None else _req(L, F64, 'L'), n, ncomp, float(a_dt),
           float(b_dt), int(last), _lib.stream_ptr())
+
+
+def lincomb(out, terms, coefs, mask=None, saves=()):
+    """out = mask * sum_j coefs[j]*terms[j] in one pass; `saves` = [(term index, destination)] also
+    copies up to two terms out unchanged (the IMEX-RK stage right-hand side)."""
+    import ctypes
+    dt = out.dtype
+    n = out.numel()
+    tp = (ctypes.c_void_p*len(terms))(*[_req(t, dt, 'term') for t in terms])
+    for t in terms:
+        assert t.numel() == n
+    cf = (ctypes.c_double*len(terms))(*[float(c) for c in coefs])
+    si = (ctypes.c_int*max(len(saves), 1))(*[int(i) for i, _ in saves])
+    sd = (ctypes.c_void_p*max(len(saves), 1))(*[_req(d, dt, 'save') for _, d in saves])
+    _call('shb_lincomb', _req(out, dt, 'out'), len(terms), tp, cf, None if mask is None else _req(mask, F64, 'mask'),
+          0 if mask is None else mask.numel(), n, int(dt.is_complex), len(saves), si, sd, _lib.stream_ptr())
+    return out
 
 
 def apply_mask(u_hat, mask):

@@ -130,8 +130,8 @@ class _Transform:
             if i < skip_to:
                 continue
             # producer pass + exchange + consumer pass cut into column pieces and overlapped
-            if ncomp == 1 and i+2 < n:
-                res = self._overlapped_exchange(i, cur, out, dest_is_out, which)
+            if i+2 < n:
+                res = self._overlapped_exchange(i, cur, out, dest_is_out, which, ncomp)
                 if res is not None:
                     cur, which = res
                     cur_is_user_input = False
@@ -214,22 +214,30 @@ class _Transform:
             out.copy_(cur)
         return out
 
-    # ---- overlapped slab exchange ----------------------------------------------------------------
-    def _overlapped_exchange(self, i, cur, out, dest_is_out, which):
-        """Steps i, i+1, i+2 = [C2C pass whose stores are the all-to-all] [exchange] [C2C pass that
-        reads the receive buffers], for a 3-D space exchanged between axes 0 and 1: the last axis is
-        cut into K column ranges; the producer of range k+1 (NVLink-bound: it stores (P-1)/P of its
-        output into the peers' memory) runs while the barrier and the HBM-bound consumer of range k
-        run on a second, higher-priority stream.  Every piece is a set of complete lines for both
-        passes, so no pass ever waits for more than its own piece.  Returns (result tensor, work-pool
-        toggle) or None when the pattern / sizes are not covered (the caller then runs the steps one
-        by one).  Replaces one `Alltoallw` per re-alignment (tensorproductspace.py:89,183,252)."""
+    # ---- slab exchange through pitched peer buffers ---------------------------------------------
+    def _overlapped_exchange(self, i, cur, out, dest_is_out, which, ncomp=1):
+        """Steps i, i+1, i+2 = [C2C pass whose stores ARE the all-to-all] [exchange] [C2C pass that
+        reads the receive buffers] of a 3-D space exchanged between axes 0 and 1, through
+        `shb_fft_c2c_lines`.  Two things differ from the step-by-step path:
+
+        * the receive buffers have a row pitch rounded up to 16 complex (256 B): with the odd R2C
+          extent (257) the rows of the natural layout start 16 B-aligned only, every 256 B store of
+          the producer then straddles 128 B lines and the NVLink write rate drops to ~530 GB/s;
+        * optionally (SHB_EXCHANGE_CHUNKS = K > 1) the last axis is cut into K column ranges, each a
+          set of complete lines for both passes, and barrier + consumer of range k run on a second
+          stream while the producer of range k+1 runs.  Measured on 2 B200 (profiles/): every extra
+          piece costs ~50 us (one more symmetric-memory barrier, shorter grids) and the two kernels
+          time-share the SMs instead of overlapping, so K = 1 is the default.
+
+        Returns (result tensor, work-pool toggle) or None when the pattern / sizes are not covered
+        (the caller then runs the steps one by one).  Replaces one `Alltoallw` per re-alignment
+        (tensorproductspace.py:89,183,252)."""
         import os
         from ._lib import ShenB200Error
         steps = self.steps
         sp, se, sc = steps[i], steps[i+1], steps[i+2]
-        K = int(os.environ.get('SHB_EXCHANGE_CHUNKS', '4'))
-        if K <= 1 or getattr(self.space, '_no_overlap', False):
+        K = int(os.environ.get('SHB_EXCHANGE_CHUNKS', '1'))
+        if os.environ.get('SHB_EXCHANGE_LINES', '1') == '0' or getattr(self.space, '_no_overlap', False):
             return None
         if not (sp.kind == 'axis' and se.kind == 'exchange' and sc.kind == 'axis' and se.fuse and all(se.fuse)):
             return None
@@ -243,81 +251,112 @@ class _Transform:
         bwd = self.direction == 'backward'
         P_, rank = ex.P, ex.rank
         n2 = sp.in_shape[2]
-        if n2 < 2*K:
-            return None
+        pitch = ((n2+15)//16)*16
+        K = max(1, min(K, pitch//16))
         dev = cur.device
+        block = int(np.prod(se.out_shape))//n2*pitch          # pitched receive buffer of ONE component
         try:
-            numel = int(np.prod(se.out_shape))
-            rbuf, hdl = ex.peer_buffers(numel, dev)
+            rbuf, hdl = ex.peer_buffers(ncomp*block, dev)
         except Exception:  # noqa: BLE001  (no P2P / symmetric memory on this box)
             ex._peer_broken = True
             return None
-        slot = (numel//P_)*16*rank
+        chunk = block//P_                                      # one peer's block, one component
+        slot = ncomp*chunk*16*rank
         peers = [int(p)+slot for p in hdl.buffer_ptrs]
+        lead = (ncomp,) if ncomp > 1 else ()
         # destination of the consumer pass
         if dest_is_out[i+2] and out.data_ptr() != cur.data_ptr():
             dst = out
         else:
-            dst = self._pool.get(which, sc.out_shape, sc.out_dtype, dev)
+            dst = self._pool.get(which, lead+sc.out_shape, sc.out_dtype, dev)
             if dst.data_ptr() == cur.data_ptr():
                 which ^= 1
-                dst = self._pool.get(which, sc.out_shape, sc.out_dtype, dev)
+                dst = self._pool.get(which, lead+sc.out_shape, sc.out_dtype, dev)
             which ^= 1
         bp, bc = sp.base, sc.base
         npf, Np = bp.physical_len(), bp.N
         ncf, Nc = bc.physical_len(), bc.N
+        curf, dstf, rflat = cur.reshape(-1), dst.reshape(-1), rbuf.reshape(-1)
         if bwd:
-            # producer: along axis 0 of (n0, s1, n2), lines (j, c); consumer: along axis 1 of (g0, n1, n2)
-            s1 = sp.in_shape[1]
-            g0 = sc.out_shape[0]
-            p_in, p_out = (Np, npf)
-            c_in, c_out = (Nc, ncf)
-            prod = dict(na=s1, in_as=n2, in_rs=s1*n2, out_as=n2, out_rs=s1*n2, out_cr=p_out//P_)
-            cons = dict(na=g0, in_as=(c_in//P_)*n2, in_rs=n2, out_as=c_out*n2, out_rs=n2, in_cr=c_in//P_,
-                        in_cs=g0*(c_in//P_)*n2)
+            # producer: along axis 0 of (n0, s1, n2), lines (j, c) of ONE component per launch;
+            # consumer: along axis 1 of (ncomp*g0, n1, n2), lines (a, c)
+            s1, g0 = sp.in_shape[1], sc.out_shape[0]
+            cr_p, cr_c = npf//P_, Nc//P_
+            comp_in, comp_out = Np*s1*n2, 0
+            prod = dict(na=s1, in_as=n2, in_rs=s1*n2, out_as=pitch, out_rs=s1*pitch, out_cr=cr_p, per_comp=True,
+                        in_comp=Np*s1*n2, peer_comp=cr_p*s1*pitch)
+            cons = dict(na=ncomp*g0, in_as=cr_c*pitch, in_rs=pitch, out_as=ncf*n2, out_rs=n2, in_cr=cr_c,
+                        in_cs=ncomp*g0*cr_c*pitch, per_comp=False)
             pscale, cscale = 1.0, 1.0
             pdd, cdd = bp.dealias_direct, bc.dealias_direct
         else:
-            # producer: along axis 1 of (g0, n1, n2), lines (i0, c); consumer: along axis 0 of (n0, s1, n2)
-            g0 = sp.in_shape[0]
-            s1 = sc.out_shape[1]
-            p_in, p_out = (npf, Np)
-            c_in, c_out = (ncf, Nc)
-            prod = dict(na=g0, in_as=p_in*n2, in_rs=n2, out_as=(p_out//P_)*n2, out_rs=n2, out_cr=p_out//P_)
-            cons = dict(na=s1, in_as=n2, in_rs=s1*n2, out_as=n2, out_rs=s1*n2, in_cr=c_in//P_,
-                        in_cs=(c_in//P_)*s1*n2)
+            # producer: along axis 1 of (ncomp*g0, n1, n2), lines (a, c);
+            # consumer: along axis 0 of (n0, s1, n2), lines (j, c) of ONE component per launch
+            g0, s1 = sp.in_shape[0], sc.out_shape[1]
+            cr_p, cr_c = Np//P_, ncf//P_
+            prod = dict(na=ncomp*g0, in_as=npf*n2, in_rs=n2, out_as=cr_p*pitch, out_rs=pitch, out_cr=cr_p, per_comp=False)
+            cons = dict(na=s1, in_as=pitch, in_rs=s1*pitch, out_as=n2, out_rs=s1*n2, in_cr=cr_c,
+                        in_cs=ncomp*cr_c*s1*pitch, per_comp=True, in_comp=cr_c*s1*pitch, out_comp=Nc*s1*n2)
             pscale, cscale = 1./npf, 1./ncf
             pdd = cdd = False
-        st = self.space.__dict__.setdefault('_ovl_streams', None)
-        if st is None:
-            st = self.space._ovl_streams = (torch.cuda.Stream(device=dev, priority=-1),
-                                            [torch.cuda.Event() for _ in range(16)])
-        side, events = st
-        main = torch.cuda.current_stream()
-        bounds = [round(k*n2/K) for k in range(K+1)]
+
+        def producer(c0, cw, cv):
+            if prod['per_comp']:
+                for q in range(ncomp):
+                    pq = [p+16*q*prod['peer_comp'] for p in peers]
+                    ops.fft_c2c_lines(bwd, curf[q*prod['in_comp']:], None, pq, prod['na'], cw, c0, prod['in_as'],
+                                      prod['in_rs'], prod['out_as'], prod['out_rs'], npf, Np, pscale, pdd, 0, 0,
+                                      prod['out_cr'], 0, ncols_valid=cv)
+            else:
+                ops.fft_c2c_lines(bwd, curf, None, peers, prod['na'], cw, c0, prod['in_as'], prod['in_rs'], prod['out_as'],
+                                  prod['out_rs'], npf, Np, pscale, pdd, 0, 0, prod['out_cr'], 0, ncols_valid=cv)
+
+        def consumer(c0, cw, cv):
+            if cons['per_comp']:
+                for q in range(ncomp):
+                    ops.fft_c2c_lines(bwd, rflat[q*cons['in_comp']:], dstf[q*cons['out_comp']:], None, cons['na'], cw, c0,
+                                      cons['in_as'], cons['in_rs'], cons['out_as'], cons['out_rs'], ncf, Nc, cscale, cdd,
+                                      cons['in_cr'], cons['in_cs'], 0, 0, ncols_valid=cv)
+            else:
+                ops.fft_c2c_lines(bwd, rflat, dstf, None, cons['na'], cw, c0, cons['in_as'], cons['in_rs'], cons['out_as'],
+                                  cons['out_rs'], ncf, Nc, cscale, cdd, cons['in_cr'], cons['in_cs'], 0, 0, ncols_valid=cv)
+
+        # column pieces: boundaries on multiples of 16 columns, the last piece carries the padding
+        nt = pitch//16
+        bounds = [16*round(k*nt/K) for k in range(K+1)]
         try:
-            for k in range(K):
-                c0, cw = bounds[k], bounds[k+1]-bounds[k]
-                ops.fft_c2c_lines(bwd, cur, None, peers, prod['na'], cw, c0, prod['in_as'], prod['in_rs'], prod['out_as'],
-                                  prod['out_rs'], npf, Np, pscale, pdd, 0, 0, prod['out_cr'], 0)
-                ev = events[k % len(events)]
-                ev.record(main)
-                side.wait_event(ev)
-                with torch.cuda.stream(side):
-                    hdl.barrier(channel=k % 8)
-                    ops.fft_c2c_lines(bwd, rbuf, dst, None, cons['na'], cw, c0, cons['in_as'], cons['in_rs'],
-                                      cons['out_as'], cons['out_rs'], ncf, Nc, cscale, cdd, cons['in_cr'],
-                                      cons['in_cs'], 0, 0)
-            done = events[K % len(events)]
-            done.record(side)
-            main.wait_event(done)
+            if K == 1:
+                producer(0, pitch, n2)
+                hdl.barrier()
+                consumer(0, n2, n2)
+            else:
+                st = self.space.__dict__.get('_ovl_streams')
+                if st is None:
+                    prio = {'cons': -1, 'prod': 0, 'none': 0}[os.environ.get('SHB_OVL_PRIO', 'cons')]
+                    st = self.space._ovl_streams = (torch.cuda.Stream(device=dev, priority=prio),
+                                                    [torch.cuda.Event() for _ in range(16)])
+                side, events = st
+                main = torch.cuda.current_stream()
+                for k in range(K):
+                    c0, cw = bounds[k], bounds[k+1]-bounds[k]
+                    cv = min(cw, n2-c0)
+                    producer(c0, cw, cv)
+                    ev = events[k % len(events)]
+                    ev.record(main)
+                    side.wait_event(ev)
+                    with torch.cuda.stream(side):
+                        hdl.barrier(channel=k % 8)
+                        consumer(c0, cv, cv)
+                done = events[K % len(events)]
+                done.record(side)
+                main.wait_event(done)
         except ShenB200Error as e:
             if 'fft_c2c_lines' not in str(e):
                 raise
             self.space._no_overlap = True
             return None
-        self.space.exchange_impl = (f'peer-store, {K} column pieces: producer pass (NVLink stores) of piece k+1 overlaps '
-                                    f'barrier + consumer pass of piece k on a second stream')
+        self.space.exchange_impl = ('peer-store into 256 B-pitched receive buffers (axis kernel writes the peers\' memory '
+                                    'over NVLink)' + (f', {K} overlapped column pieces' if K > 1 else ''))
         return dst, which
 
     def __call__(self, input_array, output_array=None, kind=None, **kw):
@@ -816,8 +855,12 @@ class TensorProductSpace:
         if mask is not None:
             t = ops.plain(u_hat)
             if not isinstance(mask, torch.Tensor):
-                mask = ops.as_device_tensor(np.ascontiguousarray(mask, dtype=float))
-            t.mul_(mask)
+                mask = ops.as_device_tensor(np.ascontiguousarray(np.broadcast_to(mask, self.shape(True)), dtype=float))
+            if t.is_complex() and t.is_contiguous() and mask.dtype == torch.float64 and mask.is_contiguous() \
+                    and t.numel() % mask.numel() == 0 and tuple(t.shape[t.dim()-mask.dim():]) == tuple(mask.shape):
+                ops.apply_mask(t, mask)               # shb_apply_mask (applymask.pyx:15-169)
+            else:
+                t.mul_(mask)
         return u_hat
 
     def _device_mask(self):
