@@ -130,6 +130,15 @@ class _Transform:
             if i < skip_to:
                 continue
             # producer pass + exchange + consumer pass cut into column pieces and overlapped
+            if i+3 < n and not bwd and s.kind == 'axis' and steps[i+1].kind == 'axis':
+                # [local pass] [producer] [exchange] [consumer]: the local pass is pipelined under the producer
+                res = self._overlapped_exchange(i+1, cur, out, dest_is_out, which, ncomp, pre=i)
+                if res is not None:
+                    cur, which = res
+                    cur_is_user_input = False
+                    cur_packed = False
+                    skip_to = i+4
+                    continue
             if i+2 < n:
                 res = self._overlapped_exchange(i, cur, out, dest_is_out, which, ncomp)
                 if res is not None:
@@ -215,7 +224,7 @@ class _Transform:
         return out
 
     # ---- slab exchange through pitched peer buffers ---------------------------------------------
-    def _overlapped_exchange(self, i, cur, out, dest_is_out, which, ncomp=1):
+    def _overlapped_exchange(self, i, cur, out, dest_is_out, which, ncomp=1, pre=None):
         """Steps i, i+1, i+2 = [C2C pass whose stores ARE the all-to-all] [exchange] [C2C pass that
         reads the receive buffers] of a 3-D space exchanged between axes 0 and 1, through
         `shb_fft_c2c_lines`.  Two things differ from the step-by-step path:
@@ -238,6 +247,11 @@ class _Transform:
         sp, se, sc = steps[i], steps[i+1], steps[i+2]
         K = int(os.environ.get('SHB_EXCHANGE_CHUNKS', '1'))
         if os.environ.get('SHB_EXCHANGE_LINES', '1') == '0' or getattr(self.space, '_no_overlap', False):
+            return None
+        # row pieces of the preceding local pass run under the producer: measured on 2 B200 (1.62 -> 1.64 ms per
+        # pair): the producer needs every SM to keep enough remote stores in flight, sharing them gains nothing
+        KO = int(os.environ.get('SHB_PRE_OVERLAP', '1'))
+        if pre is not None and (KO <= 1 or ncomp != 1 or steps[pre].axis != 2 or sp.axis != 1 or K != 1):
             return None
         if not (sp.kind == 'axis' and se.kind == 'exchange' and sc.kind == 'axis' and se.fuse and all(se.fuse)):
             return None
@@ -276,6 +290,17 @@ class _Transform:
         bp, bc = sp.base, sc.base
         npf, Np = bp.physical_len(), bp.N
         ncf, Nc = bc.physical_len(), bc.N
+        if pre is not None:
+            # intermediate of the local pass (never the user's output: the producer reads it)
+            spre = steps[pre]
+            mid = self._pool.get(which, lead+spre.out_shape, spre.out_dtype, dev)
+            if mid.data_ptr() in (cur.data_ptr(), dst.data_ptr()):
+                which ^= 1
+                mid = self._pool.get(which, lead+spre.out_shape, spre.out_dtype, dev)
+                if mid.data_ptr() in (cur.data_ptr(), dst.data_ptr()):
+                    return None
+            which ^= 1
+            pre_in, cur = cur, mid
         curf, dstf, rflat = cur.reshape(-1), dst.reshape(-1), rbuf.reshape(-1)
         if bwd:
             # producer: along axis 0 of (n0, s1, n2), lines (j, c) of ONE component per launch;
@@ -325,7 +350,37 @@ class _Transform:
         nt = pitch//16
         bounds = [16*round(k*nt/K) for k in range(K+1)]
         try:
-            if K == 1:
+            if pre is not None:
+                # forward only: rows [a0, a1) of the leading axis go through the local pass (HBM-bound) on
+                # the main stream and then through the producer (NVLink-bound) on a second stream
+                st = self.space.__dict__.get('_ovl_streams')
+                if st is None:
+                    st = self.space._ovl_streams = (torch.cuda.Stream(device=dev), [torch.cuda.Event() for _ in range(16)])
+                side, events = st
+                main = torch.cuda.current_stream()
+                g0_ = spre.in_shape[0]
+                KO = max(1, min(KO, g0_))
+                rb = [round(k*g0_/KO) for k in range(KO+1)]
+                pin, pmid = pre_in.reshape(spre.in_shape), cur.reshape(spre.out_shape)
+                inner_rows = int(np.prod(spre.in_shape[1:2]))
+                for k in range(KO):
+                    a0, a1 = rb[k], rb[k+1]
+                    spre.base._forward_axis(pin[a0:a1], pmid[a0:a1], (a1-a0)*inner_rows, 1,
+                                            scalar_product=(self.direction == 'scalar_product'))
+                    ev = events[k % len(events)]
+                    ev.record(main)
+                    side.wait_event(ev)
+                    with torch.cuda.stream(side):
+                        pk = [p+16*a0*prod['out_as'] for p in peers]
+                        ops.fft_c2c_lines(bwd, curf[a0*prod['in_as']:], None, pk, a1-a0, pitch, 0, prod['in_as'],
+                                          prod['in_rs'], prod['out_as'], prod['out_rs'], npf, Np, pscale, pdd, 0, 0,
+                                          prod['out_cr'], 0, ncols_valid=n2)
+                done = events[KO % len(events)]
+                done.record(side)
+                main.wait_event(done)
+                hdl.barrier()
+                consumer(0, n2, n2)
+            elif K == 1:
                 producer(0, pitch, n2)
                 hdl.barrier()
                 consumer(0, n2, n2)
@@ -356,7 +411,9 @@ class _Transform:
             self.space._no_overlap = True
             return None
         self.space.exchange_impl = ('peer-store into 256 B-pitched receive buffers (axis kernel writes the peers\' memory '
-                                    'over NVLink)' + (f', {K} overlapped column pieces' if K > 1 else ''))
+                                    'over NVLink)' + (f', {K} overlapped column pieces' if K > 1 else '')
+                                    + (f'; forward: preceding local pass pipelined under it in {KO} row pieces' if pre is not None
+                                       else ''))
         return dst, which
 
     def __call__(self, input_array, output_array=None, kind=None, **kw):
