@@ -450,44 +450,42 @@ def dominant_kernel_roofline(T, u, uh, peak, peak_src):
 def exchange_kernel_roofline(T, u, uh, comm, ms_pair):
     """N > 1: the kernel that bounds the pair is the C2C pass whose stores ARE the all-to-all (it
     writes (P-1)/P of its output into the peers' receive buffers over NVLink).  Timed live with CUDA
-    events on every rank (all ranks launch it together, as in the plan), max over ranks; the
-    roofline is the NVLink bandwidth per direction per GPU (770 GB/s measured peer copy on this
-    pool, /opt/skills/guides/B200_PROFILING.md; 900 nominal)."""
+    events around that one launch inside the forward plan (all ranks run it together, as in the
+    plan), average over launches, max over ranks; the roofline is the NVLink bandwidth per direction
+    per GPU (770 GB/s measured peer copy on this pool, /opt/skills/guides/B200_PROFILING.md; 900
+    nominal; a copy-engine peer copy on the bench box itself: scripts/exchange_breakdown.py)."""
     import torch
     import torch.distributed as dist
     P = comm.Get_size()
-    fw = T.forward
-    ex = [i for i, s in enumerate(fw.steps) if s.kind == 'exchange']
-    if not ex:
+    if not any(s.kind == 'exchange' for s in T.forward.steps):
         return None
     spec_local = int(np.prod(T.shape(True)))*16
     nv_bytes = spec_local*(P-1)/P                       # sent (= received) per rank per exchange
-    # time a whole forward transform and subtract nothing: report the exchange share from the plan's
-    # own structure instead: forward = r2c pass + producer pass (NVLink-bound) + consumer pass
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    reps = 20
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(reps):
-        T.forward(u, uh)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)/reps], dtype=torch.float64, device=u.v.device)
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    T._time_producer = ev
+    tot, reps = 0.0, 20
+    try:
+        for it in range(reps+2):
+            dist.barrier()
+            T.forward(u, uh)
+            torch.cuda.synchronize()
+            if it >= 2:
+                tot += ev[0].elapsed_time(ev[1])
+    except Exception:  # noqa: BLE001  (the plan did not take the timed path)
+        T._time_producer = None
+        return None
+    T._time_producer = None
+    t = torch.tensor([tot/reps], dtype=torch.float64, device=u.v.device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_fwd = t.item()
-    # local passes at the single-GPU rate would take (algorithmic bytes / P) / measured HBM rate
-    peak_hbm, _ = peaks()
-    ms_local = (REAL_B+SPEC_B+2*(2*SPEC_B))/P/(0.82*peak_hbm*1e9)*1e3
-    ms_exch = max(ms_fwd-ms_local, 1e-6)
-    ach = nv_bytes/(ms_exch*1e-3)/1e9
-    return {'bound': 'nvlink', 'kernel': 'c2c_axis1 producer (peer stores) + barrier', 'achieved': ach, 'peak': 770.0,
-            'unit': 'GB/s', 'frac': ach/770.0, 'peak_source': 'measured peer copy per direction (B200_PROFILING.md)',
-            'traffic': None, 'algorithmic_bytes_per_launch': nv_bytes, 'avg_launch_ms': ms_exch,
-            'how': f'forward transform {ms_fwd:.3f} ms (CUDA events, max over ranks) minus the local axis passes at the '
-                   f'single-GPU HBM rate ({ms_local:.3f} ms) = time attributable to the exchange; bytes = (P-1)/P of '
-                   f'the local spectral block'}
+    ms = t.item()
+    ach = nv_bytes/(ms*1e-3)/1e9
+    return {'bound': 'nvlink', 'kernel': 'fft_strided_kernel<Sched<512,8,8,8,64>, fwd, 16 columns, peer stores> (c2c along axis 1)',
+            'achieved': ach, 'peak': 770.0, 'unit': 'GB/s', 'frac': ach/770.0,
+            'peak_source': 'measured peer copy per direction on this pool (B200_PROFILING.md)',
+            'traffic': None, 'algorithmic_bytes_per_launch': nv_bytes, 'avg_launch_ms': ms,
+            'launches_per_step': 2,
+            'how': 'CUDA events around the launch inside T.forward (eager), average of 20, max over ranks; bytes = the '
+                   '(P-1)/P of the local spectral block that cross NVLink (the local 1/P is an HBM store)'}
 
 
 def mkm_workload(comm, N, steps=2):

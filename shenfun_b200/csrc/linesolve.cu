@@ -205,6 +205,438 @@ __global__ void __launch_bounds__(MAXT) helm_chunked_kernel(const __grid_constan
         if (k < nrow) up[k * rs] = x[k];
 }
 
+template <class T> __device__ __forceinline__ void cp_async_elem(T *dst, const T *src, bool ok);
+template <> __device__ __forceinline__ void cp_async_elem<cplx>(cplx *dst, const cplx *src, bool ok) { cp_async_16(dst, src, ok); }
+template <> __device__ __forceinline__ void cp_async_elem<double>(double *dst, const double *src, bool ok) { cp_async_8(dst, src, ok); }
+
+// ---- Helmholtz, tile-resident variant ------------------------------------------------------------
+// A CTA stages LW adjacent lines x all rows in shared memory (cp.async, 16 B per copy, LW*16 B
+// contiguous per row) together with their 1/d0, and a thread owns RP rows of ONE parity of ONE
+// line.  The NCH chunks of a (line, parity) recurrence sit in NCH adjacent lanes, so the chunk maps are
+// scanned with shuffles inside a lane segment (amap_seg_scan): no shared-memory maps, and only two
+// CTA barriers in the kernel (tile loaded / tile ready to be written out).  The rows of a thread are
+// 2*RP rows apart from its neighbour's, so the line index is rotated by the chunk index in shared
+// memory ((l + c) mod LW): a quarter-warp reads 8 distinct 16 B slots.
+template <class T, int LW, int RP, int NCH, int MINB>
+__global__ void __launch_bounds__(2 * LW * NCH, MINB) helm_tile_kernel(const __grid_constant__ HelmDesc d) {
+    using V = Val<T>;
+    constexpr int NC = V::NC;
+    constexpr int NT = 2 * LW * NCH;          // threads
+    constexpr int RC = 2 * RP;                // rows of a chunk (both parities)
+    constexpr int NR = RC * NCH;              // rows of the tile (>= n)
+    constexpr int NBF = NC + 1;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    T *xs = reinterpret_cast<T *>(smraw);                      // [NR][LW]
+    double *ivs = reinterpret_cast<double *>(xs + NR * LW);    // [NR][LW]
+    // the O(N) diagonals, skewed by one entry per chunk: the lanes of a segment read rows RC apart
+    // (lanes run along the chunks), which from global memory costs one wavefront per lane
+    double2 *tFs = reinterpret_cast<double2 *>(ivs + NR * LW);  // [NR + NCH]
+    double2 *tBs = tFs + (NR + NCH);
+    const int n = d.n;
+    const int64_t o = blockIdx.x / d.tiles_per_outer;
+    const int64_t cc0 = (blockIdx.x % d.tiles_per_outer) * LW;
+    const int64_t rs = d.inner;
+    const T *bb = reinterpret_cast<const T *>(d.b) + (o * d.n_u) * rs + cc0;
+    T *ub = reinterpret_cast<T *>(d.u) + (o * d.n_u) * rs + cc0;
+    const double *ivb = d.invd0 + (o * d.n_fac) * rs + cc0;
+
+    // ---- stage the tile
+    for (int idx = threadIdx.x; idx < NR * LW; idx += NT) {
+        const int i = idx / LW, l = idx % LW;
+        const bool ok = (i < n) && (cc0 + l < d.inner);
+        const int slot = i * LW + ((l + i / RC) % LW);
+        cp_async_elem<T>(&xs[slot], ok ? bb + (int64_t)i * rs + l : bb, ok);
+        cp_async_8(&ivs[slot], ok ? (const void *)(ivb + (int64_t)i * rs + l) : (const void *)ivb, ok);
+    }
+    for (int i = threadIdx.x; i < NR; i += NT) {
+        cp_async_16(&tFs[i + i / RC], &d.tabF[i], true);
+        cp_async_16(&tBs[i + i / RC], &d.tabB[i], true);
+    }
+    const int c = threadIdx.x % NCH;
+    const int pr = threadIdx.x / NCH;         // (line, parity)
+    const int p = pr & 1, l = pr >> 1;
+    const bool line_ok = cc0 + l < d.inner;
+    const int64_t line = o * d.inner + cc0 + l;
+    const double al = line_ok ? d.alfa[line] : 0.0, be = line_ok ? d.beta[line] : 0.0;
+    const int i0 = c * RC + p;                // first row of this thread; rows i0 + 2q
+    const int sw = (l + c) % LW;              // this chunk's slot of line l
+    const int swm = (l + c + LW - 1) % LW;    // slot in the chunk below (row i0 - 2 when q == 0)
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- forward substitution
+    double Lk[RP], a4[RP], Dp[RP];
+    {
+        AMap<1, NBF> m;
+        T yh = V::zero();
+        double Dh = 0.0, M = 1.0;
+#pragma unroll
+        for (int q = 0; q < RP; ++q) {
+            const int i = i0 + 2 * q;
+            const double2 t = tFs[i + c];
+            const double ivm2 = (q == 0) ? ((i >= 2) ? ivs[(i - 2) * LW + swm] : 0.0) : ivs[(i - 2) * LW + sw];
+            Lk[q] = be * t.x * ivm2;
+            a4[q] = al * t.y;
+            yh = V::fnma(Lk[q], yh, xs[i * LW + sw]);
+            Dh = fma(-Lk[q], Dh, a4[q]);
+            M *= -Lk[q];
+        }
+        m.A[0] = M;
+#pragma unroll
+        for (int v = 0; v < NC; ++v) m.b[v] = V::get(yh, v);
+        m.b[NC] = Dh;
+        double s[NBF];
+        amap_seg_scan<1, NBF, NCH, false>(m, s, c);
+        T y = V::zero();
+#pragma unroll
+        for (int v = 0; v < NC; ++v) V::set(y, v, s[v]);
+        double Dc = s[NC];
+#pragma unroll
+        for (int q = 0; q < RP; ++q) {
+            const int i = i0 + 2 * q;
+            Dp[q] = Dc;
+            y = V::fnma(Lk[q], y, xs[i * LW + sw]);
+            xs[i * LW + sw] = y;
+            Dc = fma(-Lk[q], Dc, a4[q]);
+        }
+    }
+    // ---- back substitution; (Lk, Dp, a4) are recycled as (d1, d2, 1/d0)
+    {
+#pragma unroll
+        for (int q = 0; q < RP; ++q) {
+            const int i = i0 + 2 * q;
+            const double2 t = tBs[i + c];
+            const double e1 = (i < n - 2) ? fma(-Lk[q], Dp[q], fma(al, t.x, be * t.y)) : 0.0;
+            const double e2 = (i < n - 4) ? fma(-Lk[q], Dp[q], a4[q]) : 0.0;
+            Lk[q] = e1;
+            Dp[q] = e2;
+            a4[q] = ivs[i * LW + sw];
+        }
+        AMap<2, NC> m;
+        T un = V::zero(), sg = V::zero();
+        double Hu[2] = {1.0, 0.0}, Hs[2] = {0.0, 1.0};
+#pragma unroll
+        for (int q = RP - 1; q >= 0; --q) {
+            const int i = i0 + 2 * q;
+            T v = V::fnma(Lk[q], un, xs[i * LW + sw]);
+            v = V::fnma(Dp[q], sg, v);
+            v = V::mul(a4[q], v);
+            sg = V::add(sg, un);
+            un = v;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double hv = -(fma(Lk[q], Hu[j], Dp[q] * Hs[j])) * a4[q];
+                Hs[j] += Hu[j];
+                Hu[j] = hv;
+            }
+        }
+        m.A[0] = Hu[0]; m.A[1] = Hu[1]; m.A[2] = Hs[0]; m.A[3] = Hs[1];
+#pragma unroll
+        for (int v = 0; v < NC; ++v) { m.b[v * 2] = V::get(un, v); m.b[v * 2 + 1] = V::get(sg, v); }
+        double s[2 * NC];
+        amap_seg_scan<2, NC, NCH, true>(m, s, c);
+#pragma unroll
+        for (int v = 0; v < NC; ++v) { V::set(un, v, s[v * 2]); V::set(sg, v, s[v * 2 + 1]); }
+#pragma unroll
+        for (int q = RP - 1; q >= 0; --q) {
+            const int i = i0 + 2 * q;
+            T v = V::fnma(Lk[q], un, xs[i * LW + sw]);
+            v = V::fnma(Dp[q], sg, v);
+            v = V::mul(a4[q], v);
+            sg = V::add(sg, un);
+            un = v;
+            xs[i * LW + sw] = v;
+        }
+    }
+    __syncthreads();
+    // ---- write the tile out (rows < n, lines inside the array)
+    for (int idx = threadIdx.x; idx < NR * LW; idx += NT) {
+        const int i = idx / LW, ll = idx % LW;
+        if (i < n && cc0 + ll < d.inner) ub[(int64_t)i * rs + ll] = xs[i * LW + ((ll + i / RC) % LW)];
+    }
+}
+
+template <class T, int LW, int RP, int NCH, int MINB = 1>
+static int launch_helm_tile(HelmDesc d, cudaStream_t st) {
+    constexpr int NR = 2 * RP * NCH;
+    constexpr size_t smem = (size_t)NR * LW * (sizeof(T) + sizeof(double)) + 2 * (size_t)(NR + NCH) * sizeof(double2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SHB_CUDA(cudaFuncSetAttribute(helm_tile_kernel<T, LW, RP, NCH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        attr_set = true;
+    }
+    d.tiles_per_outer = (d.inner + LW - 1) / LW;
+    const int64_t grid = d.outer * d.tiles_per_outer;
+    helm_tile_kernel<T, LW, RP, NCH, MINB><<<(unsigned)grid, 2 * LW * NCH, smem, st>>>(d);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+template <class T>
+static int launch_helm_tile_any(const HelmDesc &d, cudaStream_t st) {
+    const int n = d.n;
+    if (n <= 128) return launch_helm_tile<T, 8, 8, 8, 2>(d, st);
+    if (n <= 256) return launch_helm_tile<T, 8, 8, 16, 2>(d, st);
+    static const int tv = getenv("SHB_HELM_TILE") ? atoi(getenv("SHB_HELM_TILE")) : 0;
+    if (n <= 512) {
+        // measured at 512^3 (B200): <8,16,16> at 164 registers (one CTA per SM) 0.95 ms; capped to 128
+        // registers (two CTAs per SM) 0.76 ms; <4,8,32> 0.97 ms; <8,8,32> 0.95 ms
+        if (tv == 1) return launch_helm_tile<T, 8, 16, 16, 1>(d, st);
+        if (tv == 2) return launch_helm_tile<T, 4, 8, 32, 2>(d, st);
+        return launch_helm_tile<T, 8, 16, 16, 2>(d, st);
+    }
+    if (n <= 1024) return launch_helm_tile<T, 4, 16, 32, 2>(d, st);
+    return SHB_ERR_UNSUPPORTED;
+}
+
+// ---- banded LU substitution, tile-resident (shared factor table) -----------------------------------
+// Same engine as helm_tile_kernel for the solvers that apply ONE factored banded matrix to every
+// line (the inverse mass matrix of every Chebyshev / Legendre forward transform, la.TDMA / PDMA / ...
+// along an axis): forward  y_i = b_i - sum_p L_p[i] y_{i-p*STEP},  backward
+// x_i = (y_i - sum_q U_q[i] x_{i+q*STEP}) / D[i], factors in the table layout of banded.cu
+// (fac[KL-p][i] = L_p, fac[KL][i] = D, fac[KL+q][i] = U_q).  The table goes to shared memory once
+// per CTA (1/D formed there), skewed by one entry per chunk like the Helmholtz diagonals.
+struct BandTileDesc {
+    void *u;
+    const double *fac;
+    int64_t outer, inner;
+    int n, n_u;
+    int64_t tiles_per_outer;
+};
+
+
+template <class T, int KL, int KU, int STEP, int LW, int RP, int NCH, int MINB>
+__global__ void __launch_bounds__(STEP *LW *NCH, MINB) banded_tile_kernel(const __grid_constant__ BandTileDesc d) {
+    using V = Val<T>;
+    constexpr int NC = V::NC;
+    constexpr int NT = STEP * LW * NCH;
+    constexpr int RC = STEP * RP;
+    constexpr int NR = RC * NCH;
+    constexpr int NS = NR + NCH;              // skewed table length
+    constexpr int KLm = KL > 0 ? KL : 1, KUm = KU > 0 ? KU : 1;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    T *xs = reinterpret_cast<T *>(smraw);                      // [NR][LW]
+    double *tl = reinterpret_cast<double *>(xs + NR * LW);     // [KLm][NS]
+    double *tu = tl + KLm * NS;                                 // [KUm][NS]
+    double *td = tu + KUm * NS;                                 // [NS]  1/D
+    const int n = d.n;
+    const int64_t o = blockIdx.x / d.tiles_per_outer;
+    const int64_t cc0 = (blockIdx.x % d.tiles_per_outer) * LW;
+    const int64_t rs = d.inner;
+    T *ub = reinterpret_cast<T *>(d.u) + (o * d.n_u) * rs + cc0;
+
+    for (int idx = threadIdx.x; idx < NR * LW; idx += NT) {
+        const int i = idx / LW, l = idx % LW;
+        const bool ok = (i < n) && (cc0 + l < d.inner);
+        cp_async_elem<T>(&xs[i * LW + ((l + i / RC) % LW)], ok ? ub + (int64_t)i * rs + l : ub, ok);
+    }
+    for (int i = threadIdx.x; i < NR; i += NT) {
+        const int ii = i + i / RC;
+#pragma unroll
+        for (int p = 1; p <= KL; ++p) tl[(p - 1) * NS + ii] = (i < n && i - p * STEP >= 0) ? __ldg(&d.fac[(KL - p) * n + i]) : 0.0;
+#pragma unroll
+        for (int q = 1; q <= KU; ++q) tu[(q - 1) * NS + ii] = (i < n && i + q * STEP < n) ? __ldg(&d.fac[(KL + q) * n + i]) : 0.0;
+        td[ii] = (i < n) ? 1.0 / __ldg(&d.fac[KL * n + i]) : 0.0;
+    }
+    const int c = threadIdx.x % NCH;
+    const int pr = threadIdx.x / NCH;
+    const int p = pr % STEP, l = pr / STEP;
+    const int i0 = c * RC + p;
+    const int sw = (l + c) % LW;
+    cp_async_wait_all();
+    __syncthreads();
+
+    if (KL > 0) {
+        // ---- forward substitution: state s[k] = y_{i-(k+1)*STEP}
+        double lc[RP][KLm];
+        T sv[KLm];
+        double H[KLm][KLm];
+#pragma unroll
+        for (int a = 0; a < KLm; ++a) {
+            sv[a] = V::zero();
+#pragma unroll
+            for (int b = 0; b < KLm; ++b) H[a][b] = (a == b) ? 1.0 : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < RP; ++q) {
+            const int i = i0 + STEP * q;
+#pragma unroll
+            for (int a = 0; a < KL; ++a) lc[q][a] = tl[a * NS + i + c];
+            T y = xs[i * LW + sw];
+            double hn[KLm];
+#pragma unroll
+            for (int b = 0; b < KLm; ++b) hn[b] = 0.0;
+#pragma unroll
+            for (int a = 0; a < KL; ++a) {
+                y = V::fnma(lc[q][a], sv[a], y);
+#pragma unroll
+                for (int b = 0; b < KL; ++b) hn[b] = fma(-lc[q][a], H[a][b], hn[b]);
+            }
+#pragma unroll
+            for (int a = KL - 1; a >= 1; --a) {
+                sv[a] = sv[a - 1];
+#pragma unroll
+                for (int b = 0; b < KL; ++b) H[a][b] = H[a - 1][b];
+            }
+            sv[0] = y;
+#pragma unroll
+            for (int b = 0; b < KL; ++b) H[0][b] = hn[b];
+        }
+        AMap<KLm, NC> m;
+#pragma unroll
+        for (int a = 0; a < KLm; ++a) {
+#pragma unroll
+            for (int b = 0; b < KLm; ++b) m.A[a * KLm + b] = H[a][b];
+#pragma unroll
+            for (int v = 0; v < NC; ++v) m.b[v * KLm + a] = V::get(sv[a], v);
+        }
+        double s[NC * KLm];
+        amap_seg_scan<KLm, NC, NCH, false>(m, s, c);
+#pragma unroll
+        for (int a = 0; a < KLm; ++a)
+#pragma unroll
+            for (int v = 0; v < NC; ++v) V::set(sv[a], v, s[v * KLm + a]);
+#pragma unroll
+        for (int q = 0; q < RP; ++q) {
+            const int i = i0 + STEP * q;
+            T y = xs[i * LW + sw];
+#pragma unroll
+            for (int a = 0; a < KL; ++a) y = V::fnma(lc[q][a], sv[a], y);
+#pragma unroll
+            for (int a = KL - 1; a >= 1; --a) sv[a] = sv[a - 1];
+            sv[0] = y;
+            xs[i * LW + sw] = y;
+        }
+    }
+    {
+        // ---- back substitution: state s[k] = x_{i+(k+1)*STEP}
+        double uc[RP][KUm], dc[RP];
+        T sv[KUm];
+        double H[KUm][KUm];
+#pragma unroll
+        for (int a = 0; a < KUm; ++a) {
+            sv[a] = V::zero();
+#pragma unroll
+            for (int b = 0; b < KUm; ++b) H[a][b] = (a == b) ? 1.0 : 0.0;
+        }
+#pragma unroll
+        for (int q = RP - 1; q >= 0; --q) {
+            const int i = i0 + STEP * q;
+#pragma unroll
+            for (int a = 0; a < KU; ++a) uc[q][a] = tu[a * NS + i + c];
+            dc[q] = td[i + c];
+            T y = xs[i * LW + sw];
+            double hn[KUm];
+#pragma unroll
+            for (int b = 0; b < KUm; ++b) hn[b] = 0.0;
+#pragma unroll
+            for (int a = 0; a < KU; ++a) {
+                y = V::fnma(uc[q][a], sv[a], y);
+#pragma unroll
+                for (int b = 0; b < KU; ++b) hn[b] = fma(-uc[q][a], H[a][b], hn[b]);
+            }
+            y = V::mul(dc[q], y);
+#pragma unroll
+            for (int a = KU - 1; a >= 1; --a) {
+                sv[a] = sv[a - 1];
+#pragma unroll
+                for (int b = 0; b < KU; ++b) H[a][b] = H[a - 1][b];
+            }
+            if (KU > 0) {
+                sv[0] = y;
+#pragma unroll
+                for (int b = 0; b < KU; ++b) H[0][b] = hn[b] * dc[q];
+            } else {
+                xs[i * LW + sw] = y;          // diagonal system: done
+            }
+        }
+        if (KU > 0) {
+            AMap<KUm, NC> m;
+#pragma unroll
+            for (int a = 0; a < KUm; ++a) {
+#pragma unroll
+                for (int b = 0; b < KUm; ++b) m.A[a * KUm + b] = H[a][b];
+#pragma unroll
+                for (int v = 0; v < NC; ++v) m.b[v * KUm + a] = V::get(sv[a], v);
+            }
+            double s[NC * KUm];
+            amap_seg_scan<KUm, NC, NCH, true>(m, s, c);
+#pragma unroll
+            for (int a = 0; a < KUm; ++a)
+#pragma unroll
+                for (int v = 0; v < NC; ++v) V::set(sv[a], v, s[v * KUm + a]);
+#pragma unroll
+            for (int q = RP - 1; q >= 0; --q) {
+                const int i = i0 + STEP * q;
+                T y = xs[i * LW + sw];
+#pragma unroll
+                for (int a = 0; a < KU; ++a) y = V::fnma(uc[q][a], sv[a], y);
+                y = V::mul(dc[q], y);
+#pragma unroll
+                for (int a = KU - 1; a >= 1; --a) sv[a] = sv[a - 1];
+                sv[0] = y;
+                xs[i * LW + sw] = y;
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NR * LW; idx += NT) {
+        const int i = idx / LW, ll = idx % LW;
+        if (i < n && cc0 + ll < d.inner) ub[(int64_t)i * rs + ll] = xs[i * LW + ((ll + i / RC) % LW)];
+    }
+}
+
+template <class T, int KL, int KU, int STEP, int LW, int RP, int NCH, int MINB>
+static int launch_banded_tile(BandTileDesc d, cudaStream_t st) {
+    constexpr int NR = STEP * RP * NCH, NS = NR + NCH;
+    constexpr int KLm = KL > 0 ? KL : 1, KUm = KU > 0 ? KU : 1;
+    constexpr size_t smem = (size_t)NR * LW * sizeof(T) + (size_t)(KLm + KUm + 1) * NS * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SHB_CUDA(cudaFuncSetAttribute(banded_tile_kernel<T, KL, KU, STEP, LW, RP, NCH, MINB>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    d.tiles_per_outer = (d.inner + LW - 1) / LW;
+    const int64_t grid = d.outer * d.tiles_per_outer;
+    banded_tile_kernel<T, KL, KU, STEP, LW, RP, NCH, MINB><<<(unsigned)grid, STEP * LW * NCH, smem, st>>>(d);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+template <class T, int KL, int KU, int STEP>
+static int launch_banded_tile_n(const BandTileDesc &d, cudaStream_t st) {
+    const int rows = (d.n + STEP - 1) / STEP;      // rows per parity class
+    constexpr bool wide = (KL + KU >= 3);
+    if (rows <= 64) return launch_banded_tile<T, KL, KU, STEP, 8, 8, 8, 2>(d, st);
+    if (rows <= 128) return launch_banded_tile<T, KL, KU, STEP, 8, 8, 16, 2>(d, st);
+    if (rows <= 256) {
+        if (wide) return launch_banded_tile<T, KL, KU, STEP, 4, 8, 32, 2>(d, st);
+        return launch_banded_tile<T, KL, KU, STEP, 8, 16, 16, 2>(d, st);
+    }
+    if (rows <= 512) return launch_banded_tile<T, KL, KU, STEP, 4, 16, 32, 2>(d, st);
+    return SHB_ERR_UNSUPPORTED;
+}
+
+int banded_tile_launch(int kl, int ku, int step, void *u, const double *fac, int64_t outer, int64_t inner, int n,
+                       int n_u, int is_complex, cudaStream_t st) {
+    static const bool off = getenv("SHB_BANDED_TILE") && atoi(getenv("SHB_BANDED_TILE")) == 0;
+    if (off || inner < 4) return SHB_ERR_UNSUPPORTED;
+    BandTileDesc d;
+    d.u = u; d.fac = fac; d.outer = outer; d.inner = inner; d.n = n; d.n_u = n_u;
+#define SHB_BT(KLv, KUv)                                                                                   \
+    if (kl == KLv && ku == KUv) {                                                                           \
+        if (step == 2) return is_complex ? launch_banded_tile_n<cplx, KLv, KUv, 2>(d, st)                   \
+                                         : launch_banded_tile_n<double, KLv, KUv, 2>(d, st);                \
+        return is_complex ? launch_banded_tile_n<cplx, KLv, KUv, 1>(d, st)                                  \
+                          : launch_banded_tile_n<double, KLv, KUv, 1>(d, st);                               \
+    }
+    SHB_BT(1, 1) SHB_BT(2, 2) SHB_BT(1, 2) SHB_BT(0, 1) SHB_BT(0, 2)
+#undef SHB_BT
+    return SHB_ERR_UNSUPPORTED;
+}
+
 // 1/d0 per line: the d0 recurrence of la.pyx:744-756 (the only one with a division), one thread per
 // line; d1 and d2 are carried in registers only.  Run once per solver.
 __global__ void __launch_bounds__(128) helm_factor_inv_kernel(
@@ -266,7 +698,7 @@ static int launch_helm(HelmDesc d, cudaStream_t st) {
     return launch_helm_cl<T, RP, LW, 4, MAXT>(d, threads, smem, st);
 }
 
-int helm_rows_pad(int n) { return ((n + 15) / 16) * 16 + 16; }
+int helm_rows_pad(int n) { return n <= 128 ? 128 : n <= 256 ? 256 : n <= 512 ? 512 : ((n + 1023) / 1024) * 1024; }
 
 }  // namespace shb
 
@@ -301,8 +733,13 @@ int shb_helmholtz_solve_lean(const void *d_b, void *d_u, const double *d_tabF, c
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static const int variant = getenv("SHB_HELM_VARIANT") ? atoi(getenv("SHB_HELM_VARIANT")) : 0;
     int rc;
+    if (variant < 10) {
+        rc = is_complex ? launch_helm_tile_any<cplx>(d, st) : launch_helm_tile_any<double>(d, st);
+        if (rc == SHB_ERR_UNSUPPORTED) set_error("helmholtz_solve_lean: line length n=%d not covered", n);
+        return rc;
+    }
     if (is_complex) {
-        if (variant == 1 && n <= 512) rc = launch_helm<cplx, 4, 8, 512>(d, st);
+        if (variant == 11 && n <= 512) rc = launch_helm<cplx, 4, 8, 512>(d, st);
         else rc = launch_helm<cplx, 4, 4, 512>(d, st);
     } else {
         rc = (n <= 512) ? launch_helm<double, 4, 8, 512>(d, st) : launch_helm<double, 4, 4, 512>(d, st);

@@ -179,3 +179,45 @@ template <> struct Val<cplx> {
 };
 
 }  // namespace shb
+
+namespace shb {
+
+// Kogge-Stone scan of the chunk maps held by the W lanes of one aligned lane segment (W = number of
+// chunks of a line, a power of two <= 32): no shared memory, no CTA barrier.  On return s[] is the state
+// ENTERING this lane's chunk from the zero state; DESC: the recurrence runs from lane W-1 down to 0.
+template <int D, int NB, int W, bool DESC>
+__device__ __forceinline__ void amap_seg_scan(AMap<D, NB> m, double (&s)[NB * D], int c) {
+#pragma unroll
+    for (int off = 1; off < W; off <<= 1) {
+        AMap<D, NB> o;
+#pragma unroll
+        for (int i = 0; i < D * D; ++i)
+            o.A[i] = DESC ? __shfl_down_sync(0xffffffffu, m.A[i], off, W) : __shfl_up_sync(0xffffffffu, m.A[i], off, W);
+#pragma unroll
+        for (int i = 0; i < NB * D; ++i)
+            o.b[i] = DESC ? __shfl_down_sync(0xffffffffu, m.b[i], off, W) : __shfl_up_sync(0xffffffffu, m.b[i], off, W);
+        const AMap<D, NB> cmb = amap_compose(m, o);
+        const bool has = DESC ? (c + off < W) : (c >= off);
+        if (has) m = cmb;
+    }
+    const bool first = DESC ? (c == W - 1) : (c == 0);
+#pragma unroll
+    for (int i = 0; i < NB * D; ++i) {
+        const double e = DESC ? __shfl_down_sync(0xffffffffu, m.b[i], 1, W) : __shfl_up_sync(0xffffffffu, m.b[i], 1, W);
+        s[i] = first ? 0.0 : e;
+    }
+}
+
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc, bool pred) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc, bool pred) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+}  // namespace shb

@@ -671,7 +671,7 @@ class Helmholtz:
         self._tabs = [diag(A, 0, n), diag(A, 2, n-2), diag(A, 4, n-4), diag(B, -2, n-2), diag(B, 0, n), diag(B, 2, n-2)]
         # one stored array per line (1/d0); d1, d2, L are regenerated inside the chunk-parallel solve
         # (csrc/linesolve.cu).  Lines too long for one CTA keep the reference's four arrays.
-        self.lean = n <= Helmholtz.LEAN_MAX_N and os.environ.get('SHB_HELMHOLTZ_LEAN', '0') == '1'
+        self.lean = n <= Helmholtz.LEAN_MAX_N and os.environ.get('SHB_HELMHOLTZ_LEAN', '1') == '1'
         if self.lean:
             self.fac = torch.empty((op.outer, n, op.inner), dtype=torch.float64, device=self.alfa.device)
             ops.helmholtz_factor_lean(self._tabs, self.alfa, self.beta, self.fac, op.outer, op.inner, n)

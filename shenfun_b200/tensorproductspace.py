@@ -381,7 +381,12 @@ class _Transform:
                 hdl.barrier()
                 consumer(0, n2, n2)
             elif K == 1:
+                tm = getattr(self.space, '_time_producer', None)     # (start, end) CUDA events: bench.py's roofline
+                if tm is not None:
+                    tm[0].record()
                 producer(0, pitch, n2)
+                if tm is not None:
+                    tm[1].record()
                 hdl.barrier()
                 consumer(0, n2, n2)
             else:
