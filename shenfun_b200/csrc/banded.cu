@@ -25,7 +25,7 @@
 namespace shb {
 
 int banded_tile_launch(int kl, int ku, int step, void *u, const double *fac, int64_t outer, int64_t inner, int n,
-                       int n_u, int is_complex, cudaStream_t st);
+                       int n_u, int is_complex, cudaStream_t st, int per_line);
 
 constexpr int BD_THREADS = 128;
 constexpr int BD_MAXMAT = 4;
@@ -784,9 +784,11 @@ int shb_banded_solve(int kl, int ku, int step, void *d_u, const double *d_fac, i
     SHB_REQUIRE(d_u && d_fac && n >= 1 && n_u >= n && (step == 1 || step == 2), "bad arguments");
     if (outer * inner == 0) return SHB_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (fac_shared == 1) {
-        // one factored matrix for every line: chunk-parallel, tile-resident substitution (linesolve.cu)
-        const int rc = banded_tile_launch(kl, ku, step, d_u, d_fac, outer, inner, n, n_u, is_complex, st);
+    if (fac_shared == 1 || fac_shared == 0) {
+        // chunk-parallel, tile-resident substitution (linesolve.cu): one factored matrix for every line
+        // (shared table) or per-line factors in the batch layout
+        const int rc = banded_tile_launch(kl, ku, step, d_u, d_fac, outer, inner, n, n_u, is_complex, st,
+                                          fac_shared == 0);
         if (rc != SHB_ERR_UNSUPPORTED) return rc;
     }
     SHB_BAND_DISPATCH(kl, ku, return (launch_solve<KL, KU>(d_u, d_fac, outer, inner, n, n_u, step, fac_shared,

@@ -406,7 +406,9 @@ struct BandTileDesc {
 };
 
 
-template <class T, int KL, int KU, int STEP, int LW, int RP, int NCH, int MINB>
+// PL: per-line factors in the batch layout fac[KL+1+KU][outer][n][inner] (SolverGeneric1ND): staged
+// into shared memory next to the data tile instead of the shared table.
+template <class T, int KL, int KU, int STEP, int LW, int RP, int NCH, int MINB, bool PL>
 __global__ void __launch_bounds__(STEP *LW *NCH, MINB) banded_tile_kernel(const __grid_constant__ BandTileDesc d) {
     using V = Val<T>;
     constexpr int NC = V::NC;
@@ -420,6 +422,7 @@ __global__ void __launch_bounds__(STEP *LW *NCH, MINB) banded_tile_kernel(const 
     double *tl = reinterpret_cast<double *>(xs + NR * LW);     // [KLm][NS]
     double *tu = tl + KLm * NS;                                 // [KUm][NS]
     double *td = tu + KUm * NS;                                 // [NS]  1/D
+    double *ft = reinterpret_cast<double *>(xs + NR * LW);     // PL: [KL+1+KU][NR][LW], same rotation as xs
     const int n = d.n;
     const int64_t o = blockIdx.x / d.tiles_per_outer;
     const int64_t cc0 = (blockIdx.x % d.tiles_per_outer) * LW;
@@ -429,15 +432,27 @@ __global__ void __launch_bounds__(STEP *LW *NCH, MINB) banded_tile_kernel(const 
     for (int idx = threadIdx.x; idx < NR * LW; idx += NT) {
         const int i = idx / LW, l = idx % LW;
         const bool ok = (i < n) && (cc0 + l < d.inner);
-        cp_async_elem<T>(&xs[i * LW + ((l + i / RC) % LW)], ok ? ub + (int64_t)i * rs + l : ub, ok);
+        const int slot = i * LW + ((l + i / RC) % LW);
+        cp_async_elem<T>(&xs[slot], ok ? ub + (int64_t)i * rs + l : ub, ok);
+        if (PL) {
+            const double *fb = d.fac + (o * n) * rs + cc0;
+            const int64_t fsd = d.outer * (int64_t)n * rs;
+#pragma unroll
+            for (int dd = 0; dd < KL + 1 + KU; ++dd)
+                cp_async_8(&ft[dd * NR * LW + slot], ok ? fb + dd * fsd + (int64_t)i * rs + l : fb, ok);
+        }
     }
-    for (int i = threadIdx.x; i < NR; i += NT) {
-        const int ii = i + i / RC;
+    if (!PL) {
+        for (int i = threadIdx.x; i < NR; i += NT) {
+            const int ii = i + i / RC;
 #pragma unroll
-        for (int p = 1; p <= KL; ++p) tl[(p - 1) * NS + ii] = (i < n && i - p * STEP >= 0) ? __ldg(&d.fac[(KL - p) * n + i]) : 0.0;
+            for (int p = 1; p <= KL; ++p)
+                tl[(p - 1) * NS + ii] = (i < n && i - p * STEP >= 0) ? __ldg(&d.fac[(KL - p) * n + i]) : 0.0;
 #pragma unroll
-        for (int q = 1; q <= KU; ++q) tu[(q - 1) * NS + ii] = (i < n && i + q * STEP < n) ? __ldg(&d.fac[(KL + q) * n + i]) : 0.0;
-        td[ii] = (i < n) ? 1.0 / __ldg(&d.fac[KL * n + i]) : 0.0;
+            for (int q = 1; q <= KU; ++q)
+                tu[(q - 1) * NS + ii] = (i < n && i + q * STEP < n) ? __ldg(&d.fac[(KL + q) * n + i]) : 0.0;
+            td[ii] = (i < n) ? 1.0 / __ldg(&d.fac[KL * n + i]) : 0.0;
+        }
     }
     const int c = threadIdx.x % NCH;
     const int pr = threadIdx.x / NCH;
@@ -462,7 +477,9 @@ __global__ void __launch_bounds__(STEP *LW *NCH, MINB) banded_tile_kernel(const 
         for (int q = 0; q < RP; ++q) {
             const int i = i0 + STEP * q;
 #pragma unroll
-            for (int a = 0; a < KL; ++a) lc[q][a] = tl[a * NS + i + c];
+            for (int a = 0; a < KL; ++a)
+                lc[q][a] = PL ? ((i < n && i - (a + 1) * STEP >= 0) ? ft[(KL - 1 - a) * NR * LW + i * LW + sw] : 0.0)
+                              : tl[a * NS + i + c];
             T y = xs[i * LW + sw];
             double hn[KLm];
 #pragma unroll
@@ -524,8 +541,9 @@ __global__ void __launch_bounds__(STEP *LW *NCH, MINB) banded_tile_kernel(const 
         for (int q = RP - 1; q >= 0; --q) {
             const int i = i0 + STEP * q;
 #pragma unroll
-            for (int a = 0; a < KU; ++a) uc[q][a] = tu[a * NS + i + c];
-            dc[q] = td[i + c];
+            for (int a = 0; a < KU; ++a)
+                uc[q][a] = PL ? ((i + (a + 1) * STEP < n) ? ft[(KL + 1 + a) * NR * LW + i * LW + sw] : 0.0) : tu[a * NS + i + c];
+            dc[q] = PL ? ((i < n) ? 1.0 / ft[KL * NR * LW + i * LW + sw] : 0.0) : td[i + c];
             T y = xs[i * LW + sw];
             double hn[KUm];
 #pragma unroll
@@ -587,20 +605,22 @@ __global__ void __launch_bounds__(STEP *LW *NCH, MINB) banded_tile_kernel(const 
     }
 }
 
-template <class T, int KL, int KU, int STEP, int LW, int RP, int NCH, int MINB>
+template <class T, int KL, int KU, int STEP, int LW, int RP, int NCH, int MINB, bool PL = false>
 static int launch_banded_tile(BandTileDesc d, cudaStream_t st) {
     constexpr int NR = STEP * RP * NCH, NS = NR + NCH;
     constexpr int KLm = KL > 0 ? KL : 1, KUm = KU > 0 ? KU : 1;
-    constexpr size_t smem = (size_t)NR * LW * sizeof(T) + (size_t)(KLm + KUm + 1) * NS * sizeof(double);
+    constexpr size_t smem = (size_t)NR * LW * sizeof(T) +
+                            (PL ? (size_t)(KL + 1 + KU) * NR * LW * sizeof(double) : (size_t)(KLm + KUm + 1) * NS * sizeof(double));
+    static_assert(smem <= 227 * 1024, "tile does not fit in shared memory");
     static bool attr_set = false;
     if (!attr_set) {
-        SHB_CUDA(cudaFuncSetAttribute(banded_tile_kernel<T, KL, KU, STEP, LW, RP, NCH, MINB>,
+        SHB_CUDA(cudaFuncSetAttribute(banded_tile_kernel<T, KL, KU, STEP, LW, RP, NCH, MINB, PL>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     d.tiles_per_outer = (d.inner + LW - 1) / LW;
     const int64_t grid = d.outer * d.tiles_per_outer;
-    banded_tile_kernel<T, KL, KU, STEP, LW, RP, NCH, MINB><<<(unsigned)grid, STEP * LW * NCH, smem, st>>>(d);
+    banded_tile_kernel<T, KL, KU, STEP, LW, RP, NCH, MINB, PL><<<(unsigned)grid, STEP * LW * NCH, smem, st>>>(d);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }
@@ -619,12 +639,39 @@ static int launch_banded_tile_n(const BandTileDesc &d, cudaStream_t st) {
     return SHB_ERR_UNSUPPORTED;
 }
 
+// per-line factors: tiles sized so that two CTAs fit an SM where possible
+template <class T, int KL, int KU, int STEP>
+static int launch_banded_tile_pl(const BandTileDesc &d, cudaStream_t st) {
+    const int rows = (d.n + STEP - 1) / STEP;
+    constexpr bool wide = (KL + KU >= 3);
+    if (rows <= 64) return launch_banded_tile<T, KL, KU, STEP, 8, 8, 8, 2, true>(d, st);
+    if (rows <= 128) return launch_banded_tile<T, KL, KU, STEP, 8, 8, 16, 2, true>(d, st);
+    if (rows <= 256) return launch_banded_tile<T, KL, KU, STEP, 4, 8, 32, 2, true>(d, st);
+    if (rows <= 512) {
+        if (wide) return SHB_ERR_UNSUPPORTED;
+        return launch_banded_tile<T, KL, KU, STEP, 4, 16, 32, 1, true>(d, st);
+    }
+    return SHB_ERR_UNSUPPORTED;
+}
+
 int banded_tile_launch(int kl, int ku, int step, void *u, const double *fac, int64_t outer, int64_t inner, int n,
-                       int n_u, int is_complex, cudaStream_t st) {
+                       int n_u, int is_complex, cudaStream_t st, int per_line) {
     static const bool off = getenv("SHB_BANDED_TILE") && atoi(getenv("SHB_BANDED_TILE")) == 0;
     if (off || inner < 4) return SHB_ERR_UNSUPPORTED;
     BandTileDesc d;
     d.u = u; d.fac = fac; d.outer = outer; d.inner = inner; d.n = n; d.n_u = n_u;
+    if (per_line) {
+#define SHB_BTP(KLv, KUv)                                                                                  \
+    if (kl == KLv && ku == KUv) {                                                                           \
+        if (step == 2) return is_complex ? launch_banded_tile_pl<cplx, KLv, KUv, 2>(d, st)                  \
+                                         : launch_banded_tile_pl<double, KLv, KUv, 2>(d, st);               \
+        return is_complex ? launch_banded_tile_pl<cplx, KLv, KUv, 1>(d, st)                                 \
+                          : launch_banded_tile_pl<double, KLv, KUv, 1>(d, st);                              \
+    }
+        SHB_BTP(1, 1) SHB_BTP(2, 2) SHB_BTP(1, 2)
+#undef SHB_BTP
+        return SHB_ERR_UNSUPPORTED;
+    }
 #define SHB_BT(KLv, KUv)                                                                                   \
     if (kl == KLv && ku == KUv) {                                                                           \
         if (step == 2) return is_complex ? launch_banded_tile_n<cplx, KLv, KUv, 2>(d, st)                   \

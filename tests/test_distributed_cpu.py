@@ -54,6 +54,38 @@ def _worker(rank, world, port, results):
         dstv = torch.empty((3, 10, n1, 5), dtype=torch.float64)
         ex(srcv, dstv, 3, 'forward')
         assert np.array_equal(dstv.numpy(), GV[:, :, T.local_slice(True)[1]])
+        # --- the pencil facade of the mpi4py-fft surface (shenfun_b200.pencil) over the same exchange
+        from shenfun_b200.pencil import Subcomm, Pencil, DistArray
+        sc = Subcomm(comm, [0, 1, 1])
+        assert sc.dims == (2, 1, 1)
+        pA = Pencil(sc, (10, 9, 5), axis=2)
+        assert pA.subshape == (5, 9, 5) and pA.substart == (rank*5, 0, 0)
+        pB = pA.pencil(0)                                  # whole along 0, the ranks move to axis 2? no: to the
+        assert pB.subcomm.dims == (1, 1, 2)                # axis that was aligned (mpi4py-fft swaps the two)
+        pC = Pencil(Subcomm(comm, [1, 0, 1]), (10, 9, 5), axis=0)
+        tr = Pencil(sc, (10, 9, 5), axis=1).transfer(pC, np.complex128)
+        a = torch.from_numpy(np.ascontiguousarray(G[rank*5:rank*5+5]))
+        b = torch.empty(pC.subshape, dtype=torch.complex128)
+        tr.forward(a, b)
+        assert np.array_equal(b.numpy(), G[:, pC.substart[1]:pC.substart[1]+pC.subshape[1]])
+        a2 = torch.empty_like(a)
+        tr.backward(b, a2)
+        assert np.array_equal(a2.numpy(), a.numpy())
+        da = DistArray((10, 9, 5), subcomm=sc, dtype=np.complex128, alignment=1, buffer=a.clone(), device='cpu')
+        assert da.alignment == 1 and da.commsizes == [2, 1, 1] and da.local_slice()[0] == slice(rank*5, rank*5+5)
+        db = da.redistribute(0)
+        assert db.alignment == 0 and np.array_equal(db.v.numpy(), G[:, db.local_slice()[1]])
+        try:
+            Subcomm(comm, [1, 1, 1])
+            raise AssertionError('grid of one process on two ranks must be rejected')
+        except ValueError:
+            pass
+        try:
+            sf.TensorProductSpace(comm, [sf.FunctionSpace(8, 'F', dtype='D'), sf.FunctionSpace(8, 'F', dtype='D'),
+                                         sf.FunctionSpace(8, 'F', dtype='d')], slab=False)
+            raise AssertionError('pencil request must raise')
+        except NotImplementedError:
+            pass
         # reductions through the communicator facade
         assert comm.allreduce(float(rank+1)) == 3.0
         assert comm.bcast({'a': rank}, root=0) == {'a': 0}
