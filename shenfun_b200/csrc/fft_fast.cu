@@ -486,7 +486,11 @@ struct DctFastDesc {
     const cplx *tw, *tw3;
 };
 
-template <class SC, int MODE, int T>
+// NS: number of stencil diagonals known at compile time (1..3: the orthogonal, Dirichlet / Neumann and
+// biharmonic bases), 0: read it from the descriptor.  With the runtime loop the stencil sections were
+// 50-60 % of the instructions the kernel executes (ncu source counters, profiles/r2_*): branches and
+// index arithmetic around two or three multiply-adds.
+template <class SC, int MODE, int T, int NS>
 __global__ void __launch_bounds__(SC::P *T, (SC::P * T <= 512 && SC::EMAX <= 8 ? 2 : 1))
 dct_strided_kernel(const __grid_constant__ DctFastDesc d) {
     constexpr int M = SC::M, P = SC::P;
@@ -629,23 +633,32 @@ dct_strided_kernel(const __grid_constant__ DctFastDesc d) {
         __syncthreads();
     }
     if (j < SC::NBL && valid) {
+        const int nst = NS > 0 ? NS : d.nsten;
+        int so[NS > 0 ? NS : DCT_MAX_STENCIL];
+        const double *sp[NS > 0 ? NS : DCT_MAX_STENCIL];
+#pragma unroll
+        for (int i = 0; i < (NS > 0 ? NS : DCT_MAX_STENCIL); ++i) { so[i] = d.soff[i]; sp[i] = d.sten[i]; }
+        const int dim = d.dim, nsp = d.n_spec;
 #pragma unroll
         for (int q = 0; q < SC::BL; ++q)
 #pragma unroll
             for (int m = 0; m < SC::RL; ++m) {
                 const int k = (j + q * P) + m * SC::NBL;
-                if (k >= d.n_spec) continue;
+                if (k >= nsp) continue;
                 cplx acc = make_double2(0.0, 0.0);
-                if (k < d.dim) {
+                if (k < dim) {
                     if (plain) acc = v[q * SC::RL + m];
                     else {
-                        for (int i = 0; i < d.nsten; ++i) {
-                            const int jj = k + d.soff[i];
-                            if (jj < M) {
-                                const double a = d.sten[i] ? __ldg(&d.sten[i][k]) : 1.0;
-                                const cplx x = s(jj);
-                                acc.x = fma(a, x.x, acc.x);
-                                acc.y = fma(a, x.y, acc.y);
+#pragma unroll
+                        for (int i = 0; i < (NS > 0 ? NS : DCT_MAX_STENCIL); ++i) {
+                            if (i < nst) {
+                                const int jj = k + so[i];
+                                if (jj < M) {
+                                    const double a = sp[i] ? __ldg(sp[i] + k) : 1.0;
+                                    const cplx x = s(jj);
+                                    acc.x = fma(a, x.x, acc.x);
+                                    acc.y = fma(a, x.y, acc.y);
+                                }
                             }
                         }
                     }
@@ -655,19 +668,32 @@ dct_strided_kernel(const __grid_constant__ DctFastDesc d) {
     }
 }
 
-template <class SC, int MODE, int T>
-static int launch_dct(const DctFastDesc &d, cudaStream_t st) {
+template <class SC, int MODE, int T, int NS>
+static int launch_dct_ns(const DctFastDesc &d, cudaStream_t st) {
     constexpr size_t smem = (size_t)SC::M * T * sizeof(cplx);
     static bool attr_set = false;
     if (!attr_set) {
-        SHB_CUDA(cudaFuncSetAttribute(dct_strided_kernel<SC, MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SHB_CUDA(cudaFuncSetAttribute(dct_strided_kernel<SC, MODE, T, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         attr_set = true;
     }
     const int64_t ntiles = (d.nlines + T - 1) / T;
-    dct_strided_kernel<SC, MODE, T><<<(unsigned)ntiles, SC::P * T, smem, st>>>(d);
+    dct_strided_kernel<SC, MODE, T, NS><<<(unsigned)ntiles, SC::P * T, smem, st>>>(d);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
+}
+
+template <class SC, int MODE, int T>
+static int launch_dct(const DctFastDesc &d, cudaStream_t st) {
+    // DCT-III keeps the runtime stencil loop: unrolled variants of its prologue (recompute, publish /
+    // re-read, stencil straight from global memory) all measured slower on B200 (0.83 - 0.99 vs 0.78 ms)
+    if (MODE == FFT_DCT3) return launch_dct_ns<SC, MODE, T, 0>(d, st);
+    switch (d.nsten) {
+    case 1: return launch_dct_ns<SC, MODE, T, 1>(d, st);
+    case 2: return launch_dct_ns<SC, MODE, T, 2>(d, st);
+    case 3: return launch_dct_ns<SC, MODE, T, 3>(d, st);
+    default: return launch_dct_ns<SC, MODE, T, 0>(d, st);
+    }
 }
 
 #define SHB_DCT_CASES(MODE)                                                                          \

@@ -661,6 +661,11 @@ int banded_tile_launch(int kl, int ku, int step, void *u, const double *fac, int
     BandTileDesc d;
     d.u = u; d.fac = fac; d.outer = outer; d.inner = inner; d.n = n; d.n_u = n_u;
     if (per_line) {
+        // measured (B200, profiles/): staging the per-line factor arrays in shared memory next to the data
+        // (8 B cp.async, 4-line tiles) is SLOWER than the thread-per-line kernel (512^3 TDMA 1.41 vs 1.04 ms,
+        // 256^3 PDMA 0.21 vs 0.17 ms): opt-in only
+        static const bool pl_on = getenv("SHB_BANDED_TILE_PL") && atoi(getenv("SHB_BANDED_TILE_PL")) == 1;
+        if (!pl_on) return SHB_ERR_UNSUPPORTED;
 #define SHB_BTP(KLv, KUv)                                                                                  \
     if (kl == KLv && ku == KUv) {                                                                           \
         if (step == 2) return is_complex ? launch_banded_tile_pl<cplx, KLv, KUv, 2>(d, st)                  \
