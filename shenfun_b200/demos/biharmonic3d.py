@@ -84,7 +84,17 @@ def bench(n=256, family='L', reps=5):
     ms_ref = t(lambda: torch.matmul(a, bm))
     dgemm_peak = 2*4096.0**3/ms_ref/1e9
     del a, bm
+    # cuBLAS on the stage's own shape: (n x n) operator times n x (n*(n/2+1)*2) real columns
+    W = n*(n//2+1)*2
+    ar = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    xr = torch.randn(n, W, dtype=torch.float64, device='cuda')
+    cr = torch.empty(n, W, dtype=torch.float64, device='cuda')
+    ms_same = t(lambda: torch.matmul(ar, xr, out=cr))
+    same_tflops = 2.0*n*n*W/ms_same/1e9
+    del ar, xr, cr
     return {'workload': f'{family} ShenBiharmonic x Fourier^2 {n}^3', 'legendre_stage_ms': ms_gemm,
             'legendre_stage_tflops': flops/ms_gemm/1e9, 'cublas_dgemm_4096_tflops': dgemm_peak,
-            'legendre_stage_frac_of_dgemm_peak': flops/ms_gemm/1e9/dgemm_peak, 'forward_ms': ms_fwd, 'solve_ms': ms_solve,
+            'legendre_stage_frac_of_dgemm_peak': flops/ms_gemm/1e9/dgemm_peak,
+            'cublas_dgemm_same_shape_tflops': same_tflops, 'legendre_stage_frac_of_cublas_same_shape': flops/ms_gemm/1e9/same_tflops,
+            'forward_ms': ms_fwd, 'solve_ms': ms_solve,
             'scalar_product_solve_backward_ms': ms_chain}
