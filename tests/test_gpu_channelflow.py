@@ -18,11 +18,11 @@ def test_mkm_matches_reference(conv):
     assert rel_l2(c.u_.get(), g[f'u0_conv{conv}']) < 1e-12
     assert rel_l2(c.g_.get(), g[f'g0_conv{conv}']) < 1e-12
     t, tstep = c.solve(t=t, tstep=tstep, end_time=0.001)
-    assert rel_l2(c.H_.get(), g[f"H1_conv{conv}"]) < 1e-11
-    assert rel_l2(c.u_.get(), g[f"u1_conv{conv}"]) < 1e-11
+    assert rel_l2(c.H_.get(), g[f"H1_conv{conv}"]) < 1e-12
+    assert rel_l2(c.u_.get(), g[f"u1_conv{conv}"]) < 1e-12
     t, tstep = c.solve(t=t, tstep=tstep, end_time=0.003)
-    assert rel_l2(c.u_.get(), g[f"u3_conv{conv}"]) < 1e-11
-    assert rel_l2(c.g_.get(), g[f"g3_conv{conv}"]) < 1e-11
+    assert rel_l2(c.u_.get(), g[f"u3_conv{conv}"]) < 1e-12
+    assert rel_l2(c.g_.get(), g[f"g3_conv{conv}"]) < 1e-12
 
 
 def test_dot_grad3d_kernel():
