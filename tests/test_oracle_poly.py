@@ -89,8 +89,7 @@ def test_oracle_chebyshev_biharmonic():
     k2 = np.fft.rfftfreq(10, 1./10)[None, None, :]
     kk = k1**2+k2**2
     u = ola.biharmonic_solve(S, A, B, np.ones((1, 1, 1)), -2*kk, kk**2, g['cheb_biharm_f'], 0)
-    # LU of a matrix with condition number ~1e10 in two elimination orders: compare to cond*eps
-    assert rel_l2(u, g['cheb_biharm_u']) < 1e-9
+    assert rel_l2(u, g['cheb_biharm_u']) < 1e-12
 
 
 @pytest.mark.parametrize('name', ['ortho', 'dirichlet', 'neumann', 'biharmonic', 'dn'])
