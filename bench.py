@@ -606,30 +606,73 @@ def secondary_workloads(T, uh, args, peak, with_cpu=True):
 
 
 def solver_cpu_baseline(kind, n, cores):
-    """CPU leg of the solver configs on a bounded sample of lines (the lines are independent):
-    'helmholtz' = oracle.la.helmholtz_solve (la.pyx:744-756, 896-905 restated, numpy vectorised over
-    the lines); 'legendre' = one Legendre Vandermonde forward stage as a dense contraction
-    (spectralbase.py:539-548: np.dot(P, u))."""
-    from oracle import la as ola
+    """CPU leg of the solver configs on a bounded sample of lines (the lines are independent).
+    With oracle/_ref/refcy built (the reference's own la.pyx / transforms.pyx cythonised unchanged,
+    oracle/build_ref.sh) the leg runs the REFERENCE kernel: `kind: "reference"`; otherwise the numpy
+    port.  'helmholtz' = LU_Helmholtz once + Solve_Helmholtz timed (chebyshev/la.py:131-351 ->
+    la.pyx:708-947); 'legendre' = one Legendre scalar-product stage, the reference's default
+    'recursive' kind (spectralbase.py:536-558 -> transforms.pyx:175-263)."""
+    from oracle import la as ola, refcy
+    import shenfun_b200 as sf
     rng = np.random.default_rng(1234)
+    have_ref = refcy.available()
     if kind == 'helmholtz':
-        import shenfun_b200 as sf
         SD = sf.FunctionSpace(n, 'C', bc=(0, 0))
-        A = SD.spectral_matrix(0, 2).diags()
-        B = SD.mass_matrix().diags()
+        d = SD.dim()
+        A = SD.spectral_matrix(0, 2).diags()[:d, :d]
+        B = SD.mass_matrix().diags()[:d, :d]
         m1, m2 = 64, 33                                    # sample: 64 x 33 of the 512 x 257 lines
         k1 = np.fft.fftfreq(n, 1./n)[None, :m1, None]
         k2 = np.fft.rfftfreq(n, 1./n)[None, None, :m2]
         f = rng.standard_normal((n, m1, m2))+1j*rng.standard_normal((n, m1, m2))
-        f[SD.dim():] = 0
-        d = SD.dim()
-        t0 = time.perf_counter()
-        ola.helmholtz_solve(A[:d, :d], B[:d, :d], np.ones((1, 1, 1)), -(k1**2+k2**2), f, 0)
-        t = time.perf_counter()-t0
+        f[d:] = 0
         scale = (n*(n//2+1))/(m1*m2)
+        if have_ref:
+            la = refcy.load('la')
+            Ad = {k: np.ascontiguousarray(np.diagonal(A, k)) for k in (0, 2, 4)}
+            Bd = {k: np.ascontiguousarray(np.diagonal(B, k)) for k in (-2, 0, 2)}
+            d0, d1, d2, L = (np.zeros((n, m1, m2)) for _ in range(4))
+            la.LU_Helmholtz(Ad, Bd, np.ones((1, m1, m2)), np.ascontiguousarray(np.broadcast_to(-(k1**2+k2**2), (1, m1, m2))),
+                            False, d0, d1, d2, L, 0)
+            u = np.zeros_like(f)
+            la.Solve_Helmholtz(f, u, False, d0, d1, d2, L, 0)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                la.Solve_Helmholtz(f, u, False, d0, d1, d2, L, 0)
+            t = (time.perf_counter()-t0)/3
+            return {'value': 1.0/(t*scale), 'unit': 'solves/s', 'cores': 1, 'kind': 'reference',
+                    'sample': f'reference Solve_Helmholtz (optimization/cython/la.pyx, compiled unchanged into oracle/_ref) on '
+                              f'{m1}x{m2} of the {n}x{n//2+1} lines, factors precomputed: {t*1e3:.1f} ms, scaled by {scale:.1f}'}
+        t0 = time.perf_counter()
+        ola.helmholtz_solve(A, B, np.ones((1, 1, 1)), -(k1**2+k2**2), f, 0)
+        t = time.perf_counter()-t0
         return {'value': 1.0/(t*scale), 'unit': 'solves/s', 'cores': 1, 'kind': 'port',
                 'sample': f'factor + solve of {m1}x{m2} of the {n}x{n//2+1} lines (n = {n}), oracle/la.py '
                           f'helmholtz_solve (numpy, one thread): {t:.2f} s, scaled by {scale:.1f}'}
+    flops_full = 2.0*n*n*(n*(n//2+1)*2)
+    if have_ref:
+        tr = refcy.load('transforms')
+        SL = sf.FunctionSpace(n, 'L')
+        x, w = SL.points_and_weights(n)
+        kk = np.arange(n+1, dtype=float)
+        # Legendre three-term recurrence in the reference's table layout (spectralbase.py:476-480: jacobi `a`
+        # rows for alpha = beta = 0): P_{k+1} = ((2k+1) x P_k - k P_{k-1}) / (k+1)
+        a = np.zeros((3, n+1))
+        a[0] = (kk+1)/(2*kk+1)
+        a[1] = 0
+        a[2] = kk/(2*kk+1)
+        ncol = 16*(n//2+1)*2                               # sample: 16 of the n rows of (k, l) lines, real columns
+        u = rng.standard_normal((n, ncol))
+        out = np.zeros_like(u)
+        tr.scalar_product(u, out, x, w, 0, a)
+        t0 = time.perf_counter()
+        tr.scalar_product(u, out, x, w, 0, a)
+        t = time.perf_counter()-t0
+        scale = n/16.0
+        return {'value': flops_full/(t*scale)/1e12, 'unit': 'TFLOP/s', 'cores': 1, 'kind': 'reference', 'ms': t*scale*1e3,
+                'sample': f"reference transforms.scalar_product ('recursive' Legendre kernel, optimization/cython/"
+                          f'transforms.pyx, compiled unchanged) on 16/{n} of the lines: {t*1e3:.0f} ms, scaled by {scale:.0f}; '
+                          f'TFLOP/s counted as the dense contraction it replaces'}
     # Legendre stage: (n x n) operator times n x (n/2+1) complex columns, numpy BLAS
     P = rng.standard_normal((n, n))
     u = rng.standard_normal((n, 2*n*(n//2+1)))           # complex columns as pairs of real ones (real operator)
@@ -637,8 +680,8 @@ def solver_cpu_baseline(kind, n, cores):
     t0 = time.perf_counter()
     np.dot(P, u)
     t = time.perf_counter()-t0
-    return {'value': 2.0*n*n*u.shape[1]/t/1e12, 'unit': 'TFLOP/s', 'cores': cores, 'kind': 'port', 'ms': t*1e3,
-            'sample': f'one full Legendre Vandermonde stage of the {n}^3 transform as numpy.dot (BLAS dgemm/zgemm '
+    return {'value': flops_full/t/1e12, 'unit': 'TFLOP/s', 'cores': cores, 'kind': 'port', 'ms': t*1e3,
+            'sample': f'one full Legendre Vandermonde stage of the {n}^3 transform as numpy.dot (BLAS dgemm '
                       f'on the host cores): {t*1e3:.0f} ms'}
 
 

@@ -25,6 +25,8 @@ C = {
     'lts%': col('lts__throughput.avg.pct_of_peak_sustained'),
     'fp64%': col('sm__inst_executed_pipe_fp64', 'pct') if col('sm__inst_executed_pipe_fp64', 'pct') is not None
     else col('pipe_fp64', 'pct'),
+    'dmma%': col('sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active'),
+    'lsu%': col('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed'),
     'grid': col('launch__grid_size'),
     'block': col('launch__block_size'),
 }
@@ -47,7 +49,7 @@ def val(r, name):
     return v
 
 
-print('kernel | time_ms | rdGB | wrGB | dram% | regs | warps% | l1tex% | lts% | fp64% | grid | block')
+print('kernel | '+' | '.join(C.keys()))
 for r in data:
     name = re.sub(r'\(.*', '', r[ki]).replace('shb::', '')[:90]
     print(name, '|', ' | '.join(f'{val(r, k):.3f}' for k in C))
