@@ -317,6 +317,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_rt = (torch.linalg.vector_norm(h_out-h_in)/torch.linalg.vector_norm(h_in)).item()
     e2e_ms = t.item()/n_e2e
+    # what the host links give: every rank copies its block H2D, then D2H, all ranks at the same time
+    # (the e2e figure is bounded by this, not by the device work, once several GPUs share the host's PCIe fabric)
+    pcie = {}
+    d_tmp = torch.empty(T.shape(False), dtype=torch.float64, device=dev)
+    for name, fn in (('h2d', lambda: d_tmp.copy_(h_in, non_blocking=True)), ('d2h', lambda: h_out.copy_(d_tmp, non_blocking=True))):
+        fn()
+        barrier()
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)/5], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        pcie[name+'_GBs_per_gpu_all_ranks_concurrent'] = h_in.numel()*8/tt.item()/1e6
+    del d_tmp
 
     # ---- roofline of the dominant kernel (live CUDA events around single launches) --
     peak, peak_src = peaks()
@@ -370,7 +387,7 @@ def main():
                     'd2h_bytes_per_step': int(np.prod(T.shape(False)))*8, 'ms_per_step': e2e_ms,
                     'roundtrip_rel_err_host': e2e_rt,
                     'api': 'shenfun_b200.hostio.HostPipeline (H2D / transforms / D2H on three streams)',
-                    'host_numa_node': numa},
+                    'host_numa_node': numa, 'pcie': pcie},
             'gpu_launches': launches,
             'roofline': roof,
             'cpu_baseline': cpu,

@@ -68,3 +68,9 @@ class PFFT:
 
     def dimensions(self):
         return len(self.forward.input_array.shape)
+
+    def dtype(self, forward_output=False):
+        """mpi4py_fft.mpifft.PFFT.dtype: dtype of the arrays before / after the forward transform."""
+        if forward_output:
+            return self.forward.output_array.dtype
+        return self.forward.input_array.dtype

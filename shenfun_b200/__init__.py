@@ -17,6 +17,7 @@ from .matrices import TPMatrix, SparseMatrix, get_simplified_tpmatrices
 from .integrators import RK4, IntegratorBase, PDEIMEXRK, IMEXRK011, IMEXRK111, IMEXRK222, IMEXRK443
 from .utilities import cross, apply_mask, dx
 from . import la, chebyshev, legendre
+from .io import Checkpoint
 from .polybase import BoundaryConditions
 from ._lib import ShenB200Error
 

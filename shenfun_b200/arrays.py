@@ -33,6 +33,52 @@ def _to_tensor(x, dtype, device):
     return x
 
 
+def _refine_axis(base, u, ax, n_new):
+    """One axis of `Function.refine`: the coefficient array of `base` (N points) along `ax`
+    re-expressed for `n_new` points."""
+    from .fourier import R2C, C2C
+    n_old = base.N
+    shape = list(u.shape)
+    sl = lambda s: (slice(None),)*ax + (s,)                         # noqa: E731
+    if isinstance(base, R2C):
+        m_old, m_new = shape[ax], n_new//2+1
+        shape[ax] = m_new
+        out = u.new_zeros(shape)
+        if m_new >= m_old:
+            out[sl(slice(0, m_old))] = u
+            if n_old % 2 == 0:
+                out[sl(m_old-1)] = out[sl(m_old-1)].real*0.5
+        else:
+            out.copy_(u[sl(slice(0, m_new))])
+            if n_old % 2 == 0:
+                out[sl(m_new-1)] = out[sl(m_new-1)].real*2
+        return out
+    if isinstance(base, C2C):
+        shape[ax] = n_new
+        out = u.new_zeros(shape)
+        if n_new >= n_old:
+            h = n_old//2
+            out[sl(slice(0, h+1))] = u[sl(slice(0, h+1))]
+            out[sl(slice(n_new-h, None))] = u[sl(slice(n_old-h, None))]
+            if n_old % 2 == 0:
+                out[sl(h)] *= 0.5
+                out[sl(n_new-h)] *= 0.5
+        else:
+            h = n_new//2
+            out[sl(slice(0, h+1))] = u[sl(slice(0, h+1))]
+            out[sl(slice(n_new-h, None))] += u[sl(slice(n_old-h, None))]
+        return out
+    # polynomial bases: modes first, boundary dofs last
+    nbc = base.bcs.num_bcs() if hasattr(base, 'bcs') else 0
+    shape[ax] = n_new
+    out = u.new_zeros(shape)
+    k = min(n_old, n_new)-nbc
+    out[sl(slice(0, k))] = u[sl(slice(0, k))]
+    if nbc:
+        out[sl(slice(n_new-nbc, None))] = u[sl(slice(n_old-nbc, None))]
+    return out
+
+
 class ShenfunBaseArray(torch.Tensor):
     _forward_output = None
 
@@ -201,6 +247,54 @@ class Function(ShenfunBaseArray):
         """arguments.py:1689: zero the Nyquist coefficients in place."""
         self.function_space().mask_nyquist(self, mask=mask)
         return self
+
+    def assign(self, u_hat):
+        """arguments.py:1693-1733: copy self into `u_hat`, a Function on a space made of the same
+        bases at other resolutions."""
+        space, newspace = self.function_space(), u_hat.function_space()
+        if space.is_composite_space:
+            for i in range(len(space.flatten())):
+                self[i].assign(u_hat[i])
+            return u_hat
+        for b0, b1 in zip(space.bases, newspace.bases):
+            if type(b0) is not type(b1):
+                raise AssertionError('Can only assign on spaces with the same underlying bases')
+        return self.refine([b.N for b in newspace.bases], output_array=u_hat)
+
+    def refine(self, N, output_array=None):
+        """arguments.py:1735-1827: the same expansion on N quadrature points per axis -- zero-padded
+        where N grows, truncated where it shrinks.  Per-axis rules as in the reference:
+        fourier/bases.py:409-435 (R2C), :570-598 (C2C, symmetric interpolator: an even-N Nyquist
+        mode is split over +-N/2 when padding, summed when truncating), spectralbase.py:1363-1390
+        (polynomial bases; boundary dofs stay the last rows).  The reference's polynomial
+        truncation indexes with the source size and raises; here the low modes are kept.
+        Single-rank only: the reference redistributes between axes, this drop-in does not."""
+        space = self.function_space()
+        if space.is_composite_space:
+            comps = [self[i].refine(N) for i in range(len(space.flatten()))]
+            if output_array is None:
+                from .tensorproductspace import VectorSpace
+                output_array = Function(VectorSpace(comps[0].function_space()), val=None)
+            for i, c in enumerate(comps):
+                output_array[i] = c.v
+            return output_array
+        nd = len(space.bases)
+        if isinstance(N, numbers.Number):
+            N = (int(N),)*nd
+        if len(N) != nd:
+            raise ValueError(f'N has {len(N)} entries, the space has {nd} axes')
+        if getattr(space.comm, 'Get_size', lambda: 1)() > 1:
+            raise NotImplementedError('Function.refine on a distributed space')
+        cur, fresh = self.v, False
+        for ax, (base, n_new) in enumerate(zip(space.bases, N)):
+            if int(n_new) != base.N:
+                cur, fresh = _refine_axis(base, cur, ax, int(n_new)), True
+        if output_array is None:
+            return Function(space.get_refined(N), buffer=cur if fresh else cur.clone())
+        if tuple(output_array.shape) != tuple(cur.shape):
+            raise ValueError(f'output_array has shape {tuple(output_array.shape)}, refined array {tuple(cur.shape)}')
+        output_array.v.copy_(cur)
+        return output_array
 
     def set_boundary_dofs(self):
         """arguments.py:1525-1539 (no-op for spaces without boundary lifting)."""

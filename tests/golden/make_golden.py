@@ -292,6 +292,26 @@ def poly_3d_inhom():
     save('poly3d_inhom', **out)
 
 
+def refine_assign():
+    """Function.refine / Function.assign (forms/arguments.py:1693-1827): spectral padding and
+    truncation to another resolution, Fourier^3 (even and odd sizes) and Chebyshev x Fourier^2."""
+    out = {}
+    cases = {'f3d': ([('F', 12, 'D'), ('F', 10, 'D'), ('F', 8, 'd')], [(18, 16, 12), (8, 6, 6), (12, 15, 9)]),
+             'c3d': ([('C', 12, None), ('F', 8, 'D'), ('F', 6, 'd')], [(18, 12, 10), (12, 6, 4), (16, 8, 6)])}
+    for tag, (spec, targets) in cases.items():
+        bases = [sf.FunctionSpace(n, f, bc=(0, 0)) if f == 'C' else sf.FunctionSpace(n, f, dtype=dt) for f, n, dt in spec]
+        T = sf.TensorProductSpace(sf.comm, bases)
+        u = rng.standard_normal(T.shape(False))
+        ua = sf.Array(T)
+        ua[:] = u
+        uh = T.forward(ua, sf.Function(T))
+        out[f'uh_{tag}'] = np.array(uh)
+        for N in targets:
+            r = uh.refine(N)
+            out[f"ref_{tag}_{'x'.join(map(str, N))}"] = np.array(r)
+    save('refine', **out)
+
+
 def solvers():
     """la.TDMA/PDMA/... along axes; SolverGeneric1ND Poisson / biharmonic; Chebyshev Helmholtz."""
     from shenfun import la, inner, div, grad, TestFunction, TrialFunction, Dx

@@ -86,6 +86,28 @@ def _worker(rank, world, port, results):
             raise AssertionError('pencil request must raise')
         except NotImplementedError:
             pass
+        # --- checkpoint: two ranks write their blocks of one global array; each reads its own back,
+        # rank 0 also checks the whole file against the numpy model
+        import shutil
+        import tempfile
+        base = os.path.join(tempfile.gettempdir(), f'shb_chk_{port}')
+        U = sf.Function(T, buffer=np.ascontiguousarray(G[T.local_slice(True)]))
+        chk = sf.Checkpoint(base, checkevery=1, data={'0': {'U': [U]}})
+        chk.update(0.25, 3)
+        V = sf.Function(T)
+        sf.Checkpoint(base).read(V, 'U')
+        assert np.array_equal(V.get(), G[T.local_slice(True)])
+        if rank == 0:
+            assert np.array_equal(np.load(os.path.join(base+'.chk', 'U', '0.npy')), G)
+        comm.barrier()
+        if rank == 0:
+            shutil.rmtree(base+'.chk', ignore_errors=True)
+            shutil.rmtree(base+'.old.chk', ignore_errors=True)
+        try:
+            U.refine((12, 12, 12))
+            raise AssertionError('refine on a distributed space must raise')
+        except NotImplementedError:
+            pass
         # reductions through the communicator facade
         assert comm.allreduce(float(rank+1)) == 3.0
         assert comm.bcast({'a': rank}, root=0) == {'a': 0}
