@@ -1309,6 +1309,140 @@ static int launch_c2r_cross(const FastDesc &d, const double *b, int64_t L, cudaS
 }
 
 
+// ---- kernel B', 3/2-rule lines of two spectral vector fields: two real lines per complex transform --
+// The fields a and b (N/2+1 Hermitian modes per line, N = 2 MP, n_fft = 3 MP) are transformed as the
+// complex lines z_c = a_c + i b_c: spectrum Z[k] = A[k] + i B[k], Z[-k] = conj A[k] + i conj B[k],
+// which is the 2 MP -> 3 MP complex padding of fft_strided_pad3x_kernel on contiguous lines (three
+// residue transforms of MP points over register-held inputs).  The half-length pre-twiddle of the
+// real transform disappears, three transforms of 3 MP points replace six of 3 MP / 2 + split, and the
+// cross product is one fused multiply-add per output:
+//     (a x b)_{c+2} = a_c b_{c+1} - a_{c+1} b_c = Im(conj(z_c) z_{c+1}).
+// One warp per component, one CTA (three warps) per spatial line; every residue's values are handed to
+// the neighbouring warp through the exchange buffer, the three output lines are assembled in shared
+// memory and leave as 16-byte stores.
+template <class SC>
+__global__ void __launch_bounds__(96, 5) fft_c2r_cross3_kernel(const cplx *__restrict__ A, const cplx *__restrict__ B,
+                                                               double *__restrict__ out, const int64_t L,
+                                                               const cplx *__restrict__ tw, const cplx *__restrict__ tw3,
+                                                               const double scale) {
+    constexpr int MP = SC::M, P = SC::P;
+    static_assert(P == 32, "one warp per line");
+    constexpr int NIN = MP + 1, NF = 3 * MP;
+    constexpr int LP = MP + (MP >> 3) + 2;
+    constexpr int EM = SC::B0 * SC::R0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *ex_all = reinterpret_cast<cplx *>(smem_raw);
+    double *ob_all = reinterpret_cast<double *>(ex_all + 3 * LP);
+    const int j = threadIdx.x & 31, c = threadIdx.x >> 5;
+    const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+    cplx *ex = ex_all + c * LP;
+    const cplx *exn = ex_all + c1 * LP;
+    double *ob = ob_all + c2 * NF;
+    const int64_t sp = blockIdx.x;
+    auto s = [&](int pos) -> cplx & { return ex[skew(pos)]; };
+    struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+
+    cplx xa[EM], xb[EM];
+    if (j < SC::NB0) {
+        const cplx *__restrict__ a = A + ((int64_t)c * L + sp) * NIN;
+        const cplx *__restrict__ b = B + ((int64_t)c * L + sp) * NIN;
+        cplx la[EM], lb[EM], ma[EM], mb[EM];
+#pragma unroll
+        for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m) {
+                const int k = (j + q * P) + m * SC::NB0;
+                la[q * SC::R0 + m] = __ldg(a + k);
+                lb[q * SC::R0 + m] = __ldg(b + k);
+                ma[q * SC::R0 + m] = __ldg(a + (MP - k));
+                mb[q * SC::R0 + m] = __ldg(b + (MP - k));
+            }
+#pragma unroll
+        for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m) {
+                const int e = q * SC::R0 + m;
+                const int k = (j + q * P) + m * SC::NB0;
+                if (k == 0) {       // zero mode: imaginary parts dropped; slot MP: the split Nyquist mode
+                    xa[e] = make_double2(la[e].x, lb[e].x);
+                    xb[e] = make_double2(ma[e].x, mb[e].x);
+                } else {
+                    xa[e] = make_double2(la[e].x - lb[e].y, la[e].y + lb[e].x);
+                    xb[e] = make_double2(ma[e].x + mb[e].y, mb[e].x - ma[e].y);
+                }
+            }
+    }
+#pragma unroll 1
+    for (int n2 = 0; n2 < 3; ++n2) {
+        // f = e^(4 pi i n2 / 3): the modes k - MP seen from output residue n2
+        const double fr = (n2 == 0) ? 1.0 : -0.5;
+        const double fi = (n2 == 0) ? 0.0 : (n2 == 1 ? -0.86602540378443864676372317075294 : 0.86602540378443864676372317075294);
+        cplx v[SC::EMAX];
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int k = (j + q * P) + m * SC::NB0;
+                    const cplx a = xa[q * SC::R0 + m], b = xb[q * SC::R0 + m];
+                    cplx z;
+                    if (k == 0) {
+                        z = make_double2(fma(fr, b.x, a.x), fma(fr, b.y, a.y));
+                    } else {
+                        z = make_double2(a.x + fr * b.x - fi * b.y, a.y + fr * b.y + fi * b.x);
+                        if (n2 > 0) z = cmulc(z, __ldg(&tw3[n2 * k]));        // * e^(+2 pi i n2 k / (3 MP))
+                    }
+                    v[q * SC::R0 + m] = z;
+                }
+        }
+        fft_stages<SC, true, true>(v, j, s, WarpSync(), tw);
+        __syncwarp();
+        if (j < SC::NBL) {
+#pragma unroll
+            for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m) s((j + q * P) + m * SC::NBL) = v[q * SC::RL + m];
+        }
+        __syncthreads();
+        if (j < SC::NBL) {
+#pragma unroll
+            for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m) {
+                    const int n1 = (j + q * P) + m * SC::NBL;
+                    const cplx z = v[q * SC::RL + m], zn = exn[skew(n1)];
+                    ob[3 * n1 + n2] = z.x * zn.y - z.y * zn.x;
+                }
+        }
+        __syncthreads();      // the exchange buffers are rewritten by the next residue
+    }
+    // warp c stores output line c (assembled by warp c+1)
+    const double2 *__restrict__ src = reinterpret_cast<const double2 *>(ob_all + c * NF);
+    double2 *__restrict__ dst = reinterpret_cast<double2 *>(out + ((int64_t)c * L + sp) * NF);
+    if (scale == 1.0) {
+        for (int i = j; i < NF / 2; i += 32) dst[i] = src[i];
+    } else {
+        for (int i = j; i < NF / 2; i += 32) dst[i] = cscale(src[i], scale);
+    }
+}
+
+template <class SC>
+static int launch_c2r_cross3(const void *a, const void *b, void *out, int64_t L, double scale, cudaStream_t st) {
+    constexpr int MP = SC::M;
+    constexpr size_t smem = (size_t)3 * (MP + (MP >> 3) + 2) * sizeof(cplx) + (size_t)9 * MP * sizeof(double);
+    const cplx *tw = twiddle_table(0, MP), *tw3 = twiddle_table(0, 3 * MP);
+    if (!tw || !tw3) { set_error("fft: twiddle table allocation failed"); return SHB_ERR_NOMEM; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SHB_CUDA(cudaFuncSetAttribute(fft_c2r_cross3_kernel<SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    fft_c2r_cross3_kernel<SC><<<(unsigned)L, 96, smem, st>>>(reinterpret_cast<const cplx *>(a), reinterpret_cast<const cplx *>(b),
+                                                            reinterpret_cast<double *>(out), L, tw, tw3, scale);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
 // flags bit 0: dealias_direct; bit 1: `b` is a spectral vector field (both fields transformed here)
 int fft_c2r_cross_launch(const void *in, const void *b, void *out, int64_t L, int n_fft, int N, double scale,
                          int flags, cudaStream_t st) {
@@ -1322,6 +1456,16 @@ int fft_c2r_cross_launch(const void *in, const void *b, void *out, int64_t L, in
     d.in_cr = d.out_cr = 0; d.in_cs = d.out_cs = 0; d.use_peer = 0;
     for (int p = 0; p < 8; ++p) d.out_peer[p] = nullptr;
     if (L == 0) return SHB_OK;
+    // both fields spectral on 3/2-rule lines: the two-lines-per-complex-transform kernel (SHB_NO_CROSS3=1: off)
+    static const bool no_cross3 = getenv("SHB_NO_CROSS3") != nullptr;
+    if (dual && !(flags & 1) && !no_cross3 && N % 4 == 0 && 2 * n_fft == 3 * N && L <= 0x7fffffff) {
+        switch (N / 2) {
+        case 32:  return launch_c2r_cross3<Sched<32, 8, 4, 1, 32>>(in, b, out, L, scale, st);
+        case 64:  return launch_c2r_cross3<Sched<64, 8, 8, 1, 32>>(in, b, out, L, scale, st);
+        case 128: return launch_c2r_cross3<Sched<128, 8, 4, 4, 32>>(in, b, out, L, scale, st);
+        case 256: return launch_c2r_cross3<Sched<256, 8, 8, 4, 32>>(in, b, out, L, scale, st);
+        }
+    }
     static const int sizes[] = {32, 64, 128, 256, 384, 512, 768};
     bool ok = false;
     for (int x : sizes) ok = ok || (x == M);

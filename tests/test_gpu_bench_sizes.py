@@ -182,6 +182,24 @@ def test_c2r_cross(n_fft, N):
     assert rel_l2(out.cpu().numpy(), ref) < TOL
 
 
+@pytest.mark.parametrize('n_fft,N', [(768, 512), (384, 256), (192, 128), (96, 64)])
+@pytest.mark.parametrize('lines', [1, 203])
+def test_c2r_cross_two_spectral_fields_three_halves_rule(n_fft, N, lines):
+    """fft_c2r_cross3_kernel (two real lines per complex transform, three residue transforms): both
+    fields spectral, 3/2-rule padding, with and without a scale factor; random Nyquist / zero-mode
+    imaginary parts must be ignored as numpy.fft.irfft does."""
+    rng = np.random.default_rng(n_fft+lines)
+    ns = N//2+1
+    ah = crand(rng, (3, lines, ns))
+    bh = crand(rng, (3, lines, ns))
+    ref = np.cross(of.c2r_backward(ah, 2, N, n_fft), of.c2r_backward(bh, 2, N, n_fft), axis=0)
+    out = torch.empty((3, lines, n_fft), dtype=torch.float64, device='cuda')
+    ops.fft_c2r_cross(dev(ah), dev(bh), out, lines, n_fft, N)
+    assert rel_l2(out.cpu().numpy(), ref) < TOL
+    ops.fft_c2r_cross(dev(ah), dev(bh), out, lines, n_fft, N, scale=0.375)
+    assert rel_l2(out.cpu().numpy(), 0.375*ref) < TOL
+
+
 # ---- whole plans at the BASELINE line lengths -------------------------------------------------
 @pytest.mark.parametrize('N', [(512, 8, 6), (8, 512, 6), (6, 8, 512), (1024, 4, 6), (4, 1024, 6), (6, 4, 1024),
                                (768, 8, 6), (8, 768, 6), (6, 8, 768)])
