@@ -1411,18 +1411,20 @@ __global__ void __launch_bounds__(96, 5) fft_c2r_cross3_kernel(const cplx *__res
                 for (int m = 0; m < SC::RL; ++m) {
                     const int n1 = (j + q * P) + m * SC::NBL;
                     const cplx z = v[q * SC::RL + m], zn = exn[skew(n1)];
-                    ob[3 * n1 + n2] = z.x * zn.y - z.y * zn.x;
+                    const double o = z.x * zn.y - z.y * zn.x;
+                    ob[3 * n1 + n2] = (scale == 1.0) ? o : o * scale;
                 }
         }
+        if (n2 == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // `ob` is read by the bulk-copy engine
         __syncthreads();      // the exchange buffers are rewritten by the next residue
     }
-    // warp c stores output line c (assembled by warp c+1)
-    const double2 *__restrict__ src = reinterpret_cast<const double2 *>(ob_all + c * NF);
-    double2 *__restrict__ dst = reinterpret_cast<double2 *>(out + ((int64_t)c * L + sp) * NF);
-    if (scale == 1.0) {
-        for (int i = j; i < NF / 2; i += 32) dst[i] = src[i];
-    } else {
-        for (int i = j; i < NF / 2; i += 32) dst[i] = cscale(src[i], scale);
+    // output line c (assembled by warp c+1) leaves as one bulk copy shared -> global: no LDS / STG wavefronts
+    if (j == 0) {
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(ob_all + c * NF);
+        double *dst = out + ((int64_t)c * L + sp) * NF;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "n"(NF * 8) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
 
@@ -1458,7 +1460,8 @@ int fft_c2r_cross_launch(const void *in, const void *b, void *out, int64_t L, in
     if (L == 0) return SHB_OK;
     // both fields spectral on 3/2-rule lines: the two-lines-per-complex-transform kernel (SHB_NO_CROSS3=1: off)
     static const bool no_cross3 = getenv("SHB_NO_CROSS3") != nullptr;
-    if (dual && !(flags & 1) && !no_cross3 && N % 4 == 0 && 2 * n_fft == 3 * N && L <= 0x7fffffff) {
+    if (dual && !(flags & 1) && !no_cross3 && N % 4 == 0 && 2 * n_fft == 3 * N && L <= 0x7fffffff &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         switch (N / 2) {
         case 32:  return launch_c2r_cross3<Sched<32, 8, 4, 1, 32>>(in, b, out, L, scale, st);
         case 64:  return launch_c2r_cross3<Sched<64, 8, 8, 1, 32>>(in, b, out, L, scale, st);
