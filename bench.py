@@ -545,8 +545,9 @@ def ns_cpu_baseline(n, steps, workers):
 
 def ns_cross_kernel_roofline(peak):
     """Dominant kernel of the NS step: the six-component C2R fused with the cross product
-    (`fft_c2r_cross_kernel<Sched<384,...>,1,true>`: 768-point lines, 512 modes kept).  Algorithmic
-    bytes: six spectral lines read (257 complex each), three physical lines written (768 reals)."""
+    (`fft_c2r_cross3_kernel<Sched<256,...>>`: 768-point lines, 512 modes kept, two real lines per
+    complex transform).  Algorithmic bytes: six spectral lines read (257 complex each), three
+    physical lines written (768 reals)."""
     import torch
     from shenfun_b200 import ops
     nl = 768*768
@@ -558,7 +559,7 @@ def ns_cross_kernel_roofline(peak):
     del ab, abc, out
     torch.cuda.empty_cache()
     ach = nbytes/(ms*1e-3)/1e9
-    return {'bound': 'hbm', 'kernel': 'fft_c2r_cross_kernel (six C2R 768-point lines + cross product)', 'achieved': ach,
+    return {'bound': 'hbm', 'kernel': 'fft_c2r_cross3_kernel (six C2R 768-point lines as three complex ones + cross product)', 'achieved': ach,
             'peak': peak, 'unit': 'GB/s', 'frac': ach/peak, 'algorithmic_bytes_per_launch': nbytes, 'avg_launch_ms': ms,
             'launches_per_step': 4, 'traffic': 25390000000,
             'traffic_source': 'profiles/r1_ncu_full_summary_final.txt (dram read 14.55 GB + write 10.84 GB)'}

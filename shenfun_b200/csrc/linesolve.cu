@@ -217,7 +217,7 @@ template <> __device__ __forceinline__ void cp_async_elem<double>(double *dst, c
 // CTA barriers in the kernel (tile loaded / tile ready to be written out).  The rows of a thread are
 // 2*RP rows apart from its neighbour's, so the line index is rotated by the chunk index in shared
 // memory ((l + c) mod LW): a quarter-warp reads 8 distinct 16 B slots.
-template <class T, int LW, int RP, int NCH, int MINB>
+template <class T, int LW, int RP, int NCH, int MINB, bool BULK>
 __global__ void __launch_bounds__(2 * LW * NCH, MINB) helm_tile_kernel(const __grid_constant__ HelmDesc d) {
     using V = Val<T>;
     constexpr int NC = V::NC;
@@ -225,13 +225,19 @@ __global__ void __launch_bounds__(2 * LW * NCH, MINB) helm_tile_kernel(const __g
     constexpr int RC = 2 * RP;                // rows of a chunk (both parities)
     constexpr int NR = RC * NCH;              // rows of the tile (>= n)
     constexpr int NBF = NC + 1;
+    // BULK (complex data): rows are moved by the bulk-copy engine (cp.async.bulk, one LW*16 B row per
+    // copy, both directions), so the tile traffic costs no LSU wavefronts.  A row must then stay
+    // contiguous in shared memory: instead of rotating the line index, the rows of chunk c start c
+    // entries (16 B) later -- the same bank spread for the lanes of a segment.
+    constexpr int XSZ = NR * LW + (BULK ? NCH - 1 : 0), ISZ = NR * LW + (BULK ? 2 * (NCH - 1) : 0);
     extern __shared__ __align__(16) unsigned char smraw[];
     T *xs = reinterpret_cast<T *>(smraw);                      // [NR][LW]
-    double *ivs = reinterpret_cast<double *>(xs + NR * LW);    // [NR][LW]
+    double *ivs = reinterpret_cast<double *>(xs + XSZ);        // [NR][LW]
     // the O(N) diagonals, skewed by one entry per chunk: the lanes of a segment read rows RC apart
     // (lanes run along the chunks), which from global memory costs one wavefront per lane
-    double2 *tFs = reinterpret_cast<double2 *>(ivs + NR * LW);  // [NR + NCH]
+    double2 *tFs = reinterpret_cast<double2 *>(ivs + ISZ);      // [NR + NCH]
     double2 *tBs = tFs + (NR + NCH);
+    unsigned long long &mbar = *reinterpret_cast<unsigned long long *>(tBs + (NR + NCH));   // BULK only
     const int n = d.n;
     const int64_t o = blockIdx.x / d.tiles_per_outer;
     const int64_t cc0 = (blockIdx.x % d.tiles_per_outer) * LW;
@@ -239,14 +245,47 @@ __global__ void __launch_bounds__(2 * LW * NCH, MINB) helm_tile_kernel(const __g
     const T *bb = reinterpret_cast<const T *>(d.b) + (o * d.n_u) * rs + cc0;
     T *ub = reinterpret_cast<T *>(d.u) + (o * d.n_u) * rs + cc0;
     const double *ivb = d.invd0 + (o * d.n_fac) * rs + cc0;
+    const int w = (d.inner - cc0 < LW) ? (int)(d.inner - cc0) : LW;     // lines of this tile inside the array
+    const bool iv_bulk = BULK && (d.inner % 2 == 0);                    // 8-byte rows: 16 B alignment needs an even pitch
 
     // ---- stage the tile
-    for (int idx = threadIdx.x; idx < NR * LW; idx += NT) {
-        const int i = idx / LW, l = idx % LW;
-        const bool ok = (i < n) && (cc0 + l < d.inner);
-        const int slot = i * LW + ((l + i / RC) % LW);
-        cp_async_elem<T>(&xs[slot], ok ? bb + (int64_t)i * rs + l : bb, ok);
-        cp_async_8(&ivs[slot], ok ? (const void *)(ivb + (int64_t)i * rs + l) : (const void *)ivb, ok);
+    if constexpr (BULK) {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar);
+        if (threadIdx.x == 0) {
+            const unsigned tx = (unsigned)n * (unsigned)w * (unsigned)(sizeof(T) + (iv_bulk ? sizeof(double) : 0));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(tx) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // entries the copies do not write: rows >= n, lines outside the array
+        for (int idx = threadIdx.x; idx < NR * LW; idx += NT) {
+            const int i = idx / LW, l = idx % LW;
+            if (i >= n || l >= w) {
+                xs[i * LW + i / RC + l] = V::zero();
+                ivs[i * LW + 2 * (i / RC) + l] = 0.0;
+            } else if (!iv_bulk) {
+                cp_async_8(&ivs[i * LW + 2 * (i / RC) + l], ivb + (int64_t)i * rs + l, true);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += NT) {
+            const unsigned dx = (unsigned)__cvta_generic_to_shared(&xs[i * LW + i / RC]);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dx), "l"(bb + (int64_t)i * rs), "r"((unsigned)(w * sizeof(T))), "r"(mb) : "memory");
+            if (iv_bulk) {
+                const unsigned di = (unsigned)__cvta_generic_to_shared(&ivs[i * LW + 2 * (i / RC)]);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(di), "l"(ivb + (int64_t)i * rs), "r"((unsigned)(w * sizeof(double))), "r"(mb) : "memory");
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < NR * LW; idx += NT) {
+            const int i = idx / LW, l = idx % LW;
+            const bool ok = (i < n) && (cc0 + l < d.inner);
+            const int slot = i * LW + ((l + i / RC) % LW);
+            cp_async_elem<T>(&xs[slot], ok ? bb + (int64_t)i * rs + l : bb, ok);
+            cp_async_8(&ivs[slot], ok ? (const void *)(ivb + (int64_t)i * rs + l) : (const void *)ivb, ok);
+        }
     }
     for (int i = threadIdx.x; i < NR; i += NT) {
         cp_async_16(&tFs[i + i / RC], &d.tabF[i], true);
@@ -259,9 +298,19 @@ __global__ void __launch_bounds__(2 * LW * NCH, MINB) helm_tile_kernel(const __g
     const int64_t line = o * d.inner + cc0 + l;
     const double al = line_ok ? d.alfa[line] : 0.0, be = line_ok ? d.beta[line] : 0.0;
     const int i0 = c * RC + p;                // first row of this thread; rows i0 + 2q
-    const int sw = (l + c) % LW;              // this chunk's slot of line l
-    const int swm = (l + c + LW - 1) % LW;    // slot in the chunk below (row i0 - 2 when q == 0)
+    // this chunk's slot of line l, and the slot in the chunk below (row i0 - 2 when q == 0)
+    const int sw = BULK ? c + l : (l + c) % LW;
+    const int swi = BULK ? 2 * c + l : sw;
+    const int swim = BULK ? 2 * (c - 1) + l : (l + c + LW - 1) % LW;
     cp_async_wait_all();
+    if constexpr (BULK) {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mb) : "memory");
+        }
+    }
     __syncthreads();
 
     // ---- forward substitution
@@ -274,7 +323,7 @@ __global__ void __launch_bounds__(2 * LW * NCH, MINB) helm_tile_kernel(const __g
         for (int q = 0; q < RP; ++q) {
             const int i = i0 + 2 * q;
             const double2 t = tFs[i + c];
-            const double ivm2 = (q == 0) ? ((i >= 2) ? ivs[(i - 2) * LW + swm] : 0.0) : ivs[(i - 2) * LW + sw];
+            const double ivm2 = (q == 0) ? ((i >= 2) ? ivs[(i - 2) * LW + swim] : 0.0) : ivs[(i - 2) * LW + swi];
             Lk[q] = be * t.x * ivm2;
             a4[q] = al * t.y;
             yh = V::fnma(Lk[q], yh, xs[i * LW + sw]);
@@ -310,7 +359,7 @@ __global__ void __launch_bounds__(2 * LW * NCH, MINB) helm_tile_kernel(const __g
             const double e2 = (i < n - 4) ? fma(-Lk[q], Dp[q], a4[q]) : 0.0;
             Lk[q] = e1;
             Dp[q] = e2;
-            a4[q] = ivs[i * LW + sw];
+            a4[q] = ivs[i * LW + swi];
         }
         AMap<2, NC> m;
         T un = V::zero(), sg = V::zero();
@@ -348,29 +397,57 @@ __global__ void __launch_bounds__(2 * LW * NCH, MINB) helm_tile_kernel(const __g
             xs[i * LW + sw] = v;
         }
     }
+    if constexpr (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     // ---- write the tile out (rows < n, lines inside the array)
-    for (int idx = threadIdx.x; idx < NR * LW; idx += NT) {
-        const int i = idx / LW, ll = idx % LW;
-        if (i < n && cc0 + ll < d.inner) ub[(int64_t)i * rs + ll] = xs[i * LW + ((ll + i / RC) % LW)];
+    if constexpr (BULK) {
+        for (int i = threadIdx.x; i < n; i += NT) {
+            const unsigned sx = (unsigned)__cvta_generic_to_shared(&xs[i * LW + i / RC]);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(ub + (int64_t)i * rs), "r"(sx), "r"((unsigned)(w * sizeof(T))) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else {
+        for (int idx = threadIdx.x; idx < NR * LW; idx += NT) {
+            const int i = idx / LW, ll = idx % LW;
+            if (i < n && cc0 + ll < d.inner) ub[(int64_t)i * rs + ll] = xs[i * LW + ((ll + i / RC) % LW)];
+        }
     }
 }
 
-template <class T, int LW, int RP, int NCH, int MINB = 1>
-static int launch_helm_tile(HelmDesc d, cudaStream_t st) {
+template <class T, int LW, int RP, int NCH, int MINB, bool BULK>
+static int launch_helm_tile_b(HelmDesc d, cudaStream_t st) {
     constexpr int NR = 2 * RP * NCH;
-    constexpr size_t smem = (size_t)NR * LW * (sizeof(T) + sizeof(double)) + 2 * (size_t)(NR + NCH) * sizeof(double2);
+    constexpr size_t smem = (size_t)(NR * LW + (BULK ? NCH - 1 : 0)) * sizeof(T) +
+                            (size_t)(NR * LW + (BULK ? 2 * (NCH - 1) : 0)) * sizeof(double) +
+                            2 * (size_t)(NR + NCH) * sizeof(double2) + (BULK ? 16 : 0);
     static bool attr_set = false;
     if (!attr_set) {
-        SHB_CUDA(cudaFuncSetAttribute(helm_tile_kernel<T, LW, RP, NCH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SHB_CUDA(cudaFuncSetAttribute(helm_tile_kernel<T, LW, RP, NCH, MINB, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         attr_set = true;
     }
     d.tiles_per_outer = (d.inner + LW - 1) / LW;
     const int64_t grid = d.outer * d.tiles_per_outer;
-    helm_tile_kernel<T, LW, RP, NCH, MINB><<<(unsigned)grid, 2 * LW * NCH, smem, st>>>(d);
+    helm_tile_kernel<T, LW, RP, NCH, MINB, BULK><<<(unsigned)grid, 2 * LW * NCH, smem, st>>>(d);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
+}
+
+template <class T, int LW, int RP, int NCH, int MINB = 1>
+static int launch_helm_tile(const HelmDesc &d, cudaStream_t st) {
+    // SHB_HELM_BULK=1: complex tiles travel through the bulk-copy engine.  Measured slower on B200 (512^3:
+    // 1.005 vs 0.759 ms; 1024 x 192 x 512: 1.49 vs 0.92 ms): one 128-byte row per copy is too fine a grain for
+    // the engine, which pays off for multi-KB lines (fft_c2r_cross3_kernel).  Read per call so tests can switch.
+    const char *e = getenv("SHB_HELM_BULK");
+    const bool bulk = e && atoi(e) == 1;
+    if constexpr (sizeof(T) == 16) {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(d.b) | reinterpret_cast<uintptr_t>(d.u) |
+                               reinterpret_cast<uintptr_t>(d.invd0)) & 15) == 0;
+        if (bulk && aligned) return launch_helm_tile_b<T, LW, RP, NCH, MINB, true>(d, st);
+    }
+    return launch_helm_tile_b<T, LW, RP, NCH, MINB, false>(d, st);
 }
 
 template <class T>

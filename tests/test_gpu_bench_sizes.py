@@ -10,6 +10,8 @@ enough that persistent kernels walk several tiles per CTA.  Tolerance: relative 
 (north_star) unless a line next to the assert says why not.
 Reference behaviour: tests/test_tensorproductspace.py:59-120, tests/test_matrices.py:559-591.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -300,6 +302,13 @@ def test_chebyshev_helmholtz_long_lines(n, axis):
     ref = ola.helmholtz_solve(SD.spectral_matrix(0, 2).diags(), SD.mass_matrix().diags(), np.ones((1, 1, 1)),
                               -(k1**2+k2**2)-2.5, f, axis)
     assert rel_l2(x, ref) < TOL
+    # the bulk-copy tile transport (opt-in, csrc/linesolve.cu) must give the same bits
+    os.environ['SHB_HELM_BULK'] = '1'
+    try:
+        xb = H(sf.Function(T, buffer=f), sf.Function(T)).get()
+    finally:
+        del os.environ['SHB_HELM_BULK']
+    assert np.array_equal(xb, x)
     # solve o matvec round trip (tests/test_matrices.py:559-591)
     c = H.matvec(sf.Function(T, buffer=x), sf.Function(T)).get()
     sd = [slice(None)]*3
