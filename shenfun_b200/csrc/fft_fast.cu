@@ -1309,6 +1309,12 @@ static int launch_c2r_cross(const FastDesc &d, const double *b, int64_t L, cudaS
 }
 
 
+// distance (in CTAs' worth of work) of the L2 bulk prefetch of the C2R kernels below; SHB_PF_DIST=0: off
+static int l2_prefetch_distance(int dflt) {
+    static const int v = getenv("SHB_PF_DIST") ? atoi(getenv("SHB_PF_DIST")) : -1;
+    return v < 0 ? dflt : v;
+}
+
 // ---- kernel B', 3/2-rule lines of two spectral vector fields: two real lines per complex transform --
 // The fields a and b (N/2+1 Hermitian modes per line, N = 2 MP, n_fft = 3 MP) are transformed as the
 // complex lines z_c = a_c + i b_c: spectrum Z[k] = A[k] + i B[k], Z[-k] = conj A[k] + i conj B[k],
@@ -1324,7 +1330,7 @@ template <class SC>
 __global__ void __launch_bounds__(96, 5) fft_c2r_cross3_kernel(const cplx *__restrict__ A, const cplx *__restrict__ B,
                                                                double *__restrict__ out, const int64_t L,
                                                                const cplx *__restrict__ tw, const cplx *__restrict__ tw3,
-                                                               const double scale) {
+                                                               const double scale, const int pf_dist) {
     constexpr int MP = SC::M, P = SC::P;
     static_assert(P == 32, "one warp per line");
     constexpr int NIN = MP + 1, NF = 3 * MP;
@@ -1341,6 +1347,11 @@ __global__ void __launch_bounds__(96, 5) fft_c2r_cross3_kernel(const cplx *__res
     const int64_t sp = blockIdx.x;
     auto s = [&](int pos) -> cplx & { return ex[skew(pos)]; };
     struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+    // the lines of the CTA scheduled `pf_dist` spatial lines later are pulled into L2 now
+    if (j == 0 && pf_dist > 0 && sp + pf_dist < L) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A + ((int64_t)c * L + sp + pf_dist) * NIN), "n"(NIN * 16) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(B + ((int64_t)c * L + sp + pf_dist) * NIN), "n"(NIN * 16) : "memory");
+    }
 
     cplx xa[EM], xb[EM];
     if (j < SC::NB0) {
@@ -1440,9 +1451,148 @@ static int launch_c2r_cross3(const void *a, const void *b, void *out, int64_t L,
         attr_set = true;
     }
     fft_c2r_cross3_kernel<SC><<<(unsigned)L, 96, smem, st>>>(reinterpret_cast<const cplx *>(a), reinterpret_cast<const cplx *>(b),
-                                                            reinterpret_cast<double *>(out), L, tw, tw3, scale);
+                                                            reinterpret_cast<double *>(out), L, tw, tw3, scale, l2_prefetch_distance(384));
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
+}
+
+// ---- kernel B'', plain C2R on 3/2-rule lines: the same two-lines-per-complex-transform scheme for
+// independent lines.  A warp owns the adjacent lines 2p and 2p+1 (z = x_2p + i x_2p+1), runs the three
+// residue transforms, splits real / imaginary parts into the two output lines in shared memory and
+// sends them off as one bulk copy; no CTA-wide barrier.  An odd line count pairs the last line with zero.
+template <class SC, int W>
+__global__ void __launch_bounds__(32 * W, 15 / W) fft_c2r_pair3_kernel(const cplx *__restrict__ X, double *__restrict__ out,
+                                                                      const int64_t nlines, const cplx *__restrict__ tw,
+                                                                      const cplx *__restrict__ tw3, const double scale,
+                                                                      const int pf_dist) {
+    constexpr int MP = SC::M, P = SC::P;
+    static_assert(P == 32, "one warp per line pair");
+    constexpr int NIN = MP + 1, NF = 3 * MP;
+    constexpr int LP = MP + (MP >> 3) + 2;
+    constexpr int EM = SC::B0 * SC::R0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int j = threadIdx.x & 31, w = threadIdx.x >> 5;
+    cplx *ex = reinterpret_cast<cplx *>(smem_raw) + w * LP;
+    double *ob = reinterpret_cast<double *>(reinterpret_cast<cplx *>(smem_raw) + W * LP) + w * 2 * NF;
+    const int64_t p = (int64_t)blockIdx.x * W + w;
+    if (2 * p >= nlines) return;
+    const bool has_b = 2 * p + 1 < nlines;
+    auto s = [&](int pos) -> cplx & { return ex[skew(pos)]; };
+    struct WarpSync { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+    // the lines of a warp scheduled `pf_dist` pairs later are pulled into L2 now (one bulk prefetch)
+    if (j == 0 && pf_dist > 0 && 2 * (p + pf_dist) + 1 < nlines)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(X + 2 * (p + pf_dist) * NIN), "n"(2 * NIN * 16) : "memory");
+
+    cplx xa[EM], xb[EM];
+    if (j < SC::NB0) {
+        const cplx *__restrict__ a = X + 2 * p * NIN;
+        const cplx *__restrict__ b = has_b ? a + NIN : a;
+        const double bm = has_b ? 1.0 : 0.0;
+        cplx la[EM], lb[EM], ma[EM], mb[EM];
+#pragma unroll
+        for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m) {
+                const int k = (j + q * P) + m * SC::NB0;
+                la[q * SC::R0 + m] = __ldg(a + k);
+                lb[q * SC::R0 + m] = __ldg(b + k);
+                ma[q * SC::R0 + m] = __ldg(a + (MP - k));
+                mb[q * SC::R0 + m] = __ldg(b + (MP - k));
+            }
+#pragma unroll
+        for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+            for (int m = 0; m < SC::R0; ++m) {
+                const int e = q * SC::R0 + m;
+                const int k = (j + q * P) + m * SC::NB0;
+                const cplx B1 = cscale(lb[e], bm), B2 = cscale(mb[e], bm);
+                if (k == 0) {       // zero mode: imaginary parts dropped; slot MP: the split Nyquist mode
+                    xa[e] = make_double2(la[e].x, B1.x);
+                    xb[e] = make_double2(ma[e].x, B2.x);
+                } else {
+                    xa[e] = make_double2(la[e].x - B1.y, la[e].y + B1.x);
+                    xb[e] = make_double2(ma[e].x + B2.y, B2.x - ma[e].y);
+                }
+            }
+    }
+#pragma unroll 1
+    for (int n2 = 0; n2 < 3; ++n2) {
+        const double fr = (n2 == 0) ? 1.0 : -0.5;
+        const double fi = (n2 == 0) ? 0.0 : (n2 == 1 ? -0.86602540378443864676372317075294 : 0.86602540378443864676372317075294);
+        cplx v[SC::EMAX];
+        if (j < SC::NB0) {
+#pragma unroll
+            for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::R0; ++m) {
+                    const int k = (j + q * P) + m * SC::NB0;
+                    const cplx a = xa[q * SC::R0 + m], b = xb[q * SC::R0 + m];
+                    cplx z;
+                    if (k == 0) {
+                        z = make_double2(fma(fr, b.x, a.x), fma(fr, b.y, a.y));
+                    } else {
+                        z = make_double2(a.x + fr * b.x - fi * b.y, a.y + fr * b.y + fi * b.x);
+                        if (n2 > 0) z = cmulc(z, __ldg(&tw3[n2 * k]));
+                    }
+                    v[q * SC::R0 + m] = z;
+                }
+        }
+        fft_stages<SC, true, true>(v, j, s, WarpSync(), tw);
+        if (j < SC::NBL) {
+#pragma unroll
+            for (int q = 0; q < SC::BL; ++q)
+#pragma unroll
+                for (int m = 0; m < SC::RL; ++m) {
+                    const int n1 = (j + q * P) + m * SC::NBL;
+                    const cplx z = (scale == 1.0) ? v[q * SC::RL + m] : cscale(v[q * SC::RL + m], scale);
+                    ob[3 * n1 + n2] = z.x;
+                    ob[NF + 3 * n1 + n2] = z.y;
+                }
+        }
+        __syncwarp();      // the exchange buffer is rewritten by the next residue
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (j == 0) {
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(ob);
+        double *dst = out + 2 * p * NF;
+        const uint32_t bytes = (has_b ? 2 : 1) * NF * 8;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+template <class SC>
+static int launch_c2r_pair3(const void *in, void *out, int64_t nlines, double scale, cudaStream_t st) {
+    constexpr int MP = SC::M, W = 3;
+    constexpr size_t smem = (size_t)W * ((MP + (MP >> 3) + 2) * sizeof(cplx) + (size_t)6 * MP * sizeof(double));
+    const cplx *tw = twiddle_table(0, MP), *tw3 = twiddle_table(0, 3 * MP);
+    if (!tw || !tw3) { set_error("fft: twiddle table allocation failed"); return SHB_ERR_NOMEM; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SHB_CUDA(cudaFuncSetAttribute(fft_c2r_pair3_kernel<SC, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int64_t pairs = (nlines + 1) / 2;
+    fft_c2r_pair3_kernel<SC, W><<<(unsigned)((pairs + W - 1) / W), 32 * W, smem, st>>>(
+        reinterpret_cast<const cplx *>(in), reinterpret_cast<double *>(out), nlines, tw, tw3, scale, l2_prefetch_distance(1024));
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+// 3/2-rule C2R lines (n_fft = 3 N / 2, N a multiple of 4, no dealias_direct): SHB_ERR_UNSUPPORTED when not covered
+static int c2r_pair3(const void *in, void *out, int64_t nlines, int n_fft, int N, double scale, int flags, cudaStream_t st) {
+    static const bool off = getenv("SHB_NO_PAIR3") != nullptr;
+    if (off || (flags & 1) || N % 4 || 2 * n_fft != 3 * N || (reinterpret_cast<uintptr_t>(out) & 15) || nlines > 0x3fffffff)
+        return SHB_ERR_UNSUPPORTED;
+    switch (N / 2) {
+    case 32:  return launch_c2r_pair3<Sched<32, 8, 4, 1, 32>>(in, out, nlines, scale, st);
+    case 64:  return launch_c2r_pair3<Sched<64, 8, 8, 1, 32>>(in, out, nlines, scale, st);
+    case 128: return launch_c2r_pair3<Sched<128, 8, 4, 4, 32>>(in, out, nlines, scale, st);
+    case 256: return launch_c2r_pair3<Sched<256, 8, 8, 4, 32>>(in, out, nlines, scale, st);
+    }
+    return SHB_ERR_UNSUPPORTED;
 }
 
 // flags bit 0: dealias_direct; bit 1: `b` is a spectral vector field (both fields transformed here)
@@ -1643,6 +1793,10 @@ int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t 
     case FFT_R2C: if (n_fft % 2 || inner != 1) return SHB_ERR_UNSUPPORTED;
                   M = n_fft / 2; d.n_in = n_fft; d.n_out = ns; break;
     case FFT_C2R: if (n_fft % 2 || inner != 1) return SHB_ERR_UNSUPPORTED;
+                  if (!in_cr && !out_cr && !d.use_peer) {
+                      const int rc = c2r_pair3(in, out, d.nlines, n_fft, N, scale, flags, st);
+                      if (rc != SHB_ERR_UNSUPPORTED) return rc;
+                  }
                   M = n_fft / 2; d.n_in = ns; d.n_out = n_fft; break;
     default: return SHB_ERR_UNSUPPORTED;
     }

@@ -202,6 +202,22 @@ def test_c2r_cross_two_spectral_fields_three_halves_rule(n_fft, N, lines):
     assert rel_l2(out.cpu().numpy(), 0.375*ref) < TOL
 
 
+@pytest.mark.parametrize('n_fft,N', [(768, 512), (384, 256), (192, 128), (96, 64)])
+@pytest.mark.parametrize('lines', [1, 2, 203, 204])
+def test_c2r_three_halves_rule_line_pairs(n_fft, N, lines):
+    """fft_c2r_pair3_kernel: 3/2-rule C2R lines transformed two at a time as one complex line (odd line
+    counts pair the last line with zero), with and without a scale factor."""
+    rng = np.random.default_rng(n_fft+lines)
+    ah = crand(rng, (lines, N//2+1))
+    ref = of.c2r_backward(ah, 1, N, n_fft)
+    out = torch.full((lines+1, n_fft), 7.0, dtype=torch.float64, device='cuda')
+    ops.fft_c2r_backward(dev(ah), out[:lines], lines, 1, n_fft, N)
+    assert rel_l2(out[:lines].cpu().numpy(), ref) < TOL
+    assert torch.all(out[lines] == 7.0)                  # nothing written past the last line
+    ops.fft_c2r_backward(dev(ah), out[:lines], lines, 1, n_fft, N, scale=1.0/n_fft)
+    assert rel_l2(out[:lines].cpu().numpy(), ref/n_fft) < TOL
+
+
 # ---- whole plans at the BASELINE line lengths -------------------------------------------------
 @pytest.mark.parametrize('N', [(512, 8, 6), (8, 512, 6), (6, 8, 512), (1024, 4, 6), (4, 1024, 6), (6, 4, 1024),
                                (768, 8, 6), (8, 768, 6), (6, 8, 768)])
