@@ -172,6 +172,7 @@ struct FastDesc {
     int n_fft, N, n_in, n_out, flags;
     double scale;
     const cplx *tw, *tw2;
+    int pf = 0;       // fft_contig_kernel: L2 prefetch distance in CTAs (0: off)
     // peer-chunked addressing along the transform axis (fused all-to-all pack / unpack):
     // row r of outer index o lives at (r / cr) * cs + ((o * cr + r % cr) * inner + c); cr == 0: off
     int in_cr, out_cr;
@@ -961,6 +962,17 @@ __global__ void __launch_bounds__(SC::P *TL) fft_contig_kernel(const __grid_cons
     cplx *sm = reinterpret_cast<cplx *>(smem_raw) + (size_t)l * LP;
     const int64_t line = (int64_t)blockIdx.x * TL + l;
     const bool valid = line < d.nlines;
+    if (threadIdx.x == 0 && d.pf > 0) {
+        // the (contiguous) input lines of the CTA `pf` blocks ahead are pulled into L2 by one bulk prefetch
+        const int64_t l2 = ((int64_t)blockIdx.x + d.pf) * TL;
+        if (l2 + TL <= d.nlines) {
+            constexpr unsigned esz = (MODE == FFT_R2C) ? 8 : 16;
+            const char *src = reinterpret_cast<const char *>(d.in) + l2 * d.n_in * esz;
+            const unsigned bytes = TL * d.n_in * esz;
+            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && bytes % 16 == 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+        }
+    }
     const int N = d.N;
     const int n_fft = d.n_fft;
     const bool padded = (N < n_fft);
@@ -1655,6 +1667,7 @@ int fft_c2r_cross_launch(const void *in, const void *b, void *out, int64_t L, in
 template <class SC, int MODE, int T, bool CH>
 static int launch_strided_ch(const FastDesc &d, cudaStream_t st) {
     constexpr size_t smem = (size_t)SC::M * T * sizeof(cplx);
+
     static bool attr_set = false;
     if (!attr_set) {
         SHB_CUDA(cudaFuncSetAttribute(fft_strided_kernel<SC, MODE, T, CH>,
@@ -1705,8 +1718,14 @@ static int launch_strided(const FastDesc &d, cudaStream_t st) {
 }
 
 template <class SC, int MODE, int TL>
-static int launch_contig(const FastDesc &d, cudaStream_t st) {
+static int launch_contig(FastDesc d, cudaStream_t st) {
     constexpr size_t smem = (size_t)(SC::M + (SC::M >> 3) + 2) * TL * sizeof(cplx);
+    {
+        // about SHB_PF_CONTIG_MB (default 8) megabytes of input ahead of the running CTAs; 0: off
+        static const double mb = getenv("SHB_PF_CONTIG_MB") ? atof(getenv("SHB_PF_CONTIG_MB")) : 8.0;
+        const double per_cta = (double)TL * d.n_in * (MODE == FFT_R2C ? 8 : 16);
+        d.pf = mb > 0 ? (int)(mb * 1048576.0 / per_cta) : 0;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         SHB_CUDA(cudaFuncSetAttribute(fft_contig_kernel<SC, MODE, TL>,
