@@ -212,6 +212,10 @@ SHB_API int shb_lincomb(void *d_out, int nterms, const void *const *d_terms, con
 /* u *= mask on [ncomp][n] complex (Nyquist masking): replaces
  * shenfun/optimization/cython/applymask.pyx:15-169 (`apply_mask`).          */
 SHB_API int shb_apply_mask(void *d_u, const double *d_mask, int64_t n, int ncomp, void *stream);
+/* v = i (a f + b g), w = i (b f - a g) on complex arrays of n entries; a, b real tables of n12 entries
+ * broadcast over the leading index (demo/ChannelFlow.py:235-239, `compute_vw`). */
+SHB_API int shb_kmm_vw(const void *d_f, const void *d_g, const double *d_a, const double *d_b, void *d_v, void *d_w,
+                       int64_t n, int64_t n12, void *stream);
 
 /* ------------------------------------------------------------------ */
 /* Batched banded line solvers along the middle axis of [outer][n][inner].

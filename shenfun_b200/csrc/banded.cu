@@ -811,11 +811,20 @@ int shb_banded_matvec(const void *d_u, void *d_out, int nmat, int ndiag, const i
     const int64_t tot = outer * (int64_t)n_out * inner;
     if (tot == 0) return SHB_OK;
     if (inner >= 32 && outer <= 65535) {
-        constexpr int R = 4;
-        dim3 grid((unsigned)((inner + 127) / 128), (unsigned)((n_out + R - 1) / R), (unsigned)outer);
+        // rows per thread: a thread re-reads ndiag - 1 neighbour rows per block of R (SHB_MATVEC_R = 4 | 16; MKM step 98.2 -> 97.6 ms with 16)
+        static const int rsel = getenv("SHB_MATVEC_R") ? atoi(getenv("SHB_MATVEC_R")) : 16;
         cudaStream_t st2 = reinterpret_cast<cudaStream_t>(stream);
-        if (is_complex) banded_matvec_col_kernel<cplx, R><<<grid, 128, 0, st2>>>((const cplx *)d_u, (cplx *)d_out, d);
-        else banded_matvec_col_kernel<double, R><<<grid, 128, 0, st2>>>((const double *)d_u, (double *)d_out, d);
+        if (rsel == 16) {
+            constexpr int R = 16;
+            dim3 grid((unsigned)((inner + 127) / 128), (unsigned)((n_out + R - 1) / R), (unsigned)outer);
+            if (is_complex) banded_matvec_col_kernel<cplx, R><<<grid, 128, 0, st2>>>((const cplx *)d_u, (cplx *)d_out, d);
+            else banded_matvec_col_kernel<double, R><<<grid, 128, 0, st2>>>((const double *)d_u, (double *)d_out, d);
+        } else {
+            constexpr int R = 4;
+            dim3 grid((unsigned)((inner + 127) / 128), (unsigned)((n_out + R - 1) / R), (unsigned)outer);
+            if (is_complex) banded_matvec_col_kernel<cplx, R><<<grid, 128, 0, st2>>>((const cplx *)d_u, (cplx *)d_out, d);
+            else banded_matvec_col_kernel<double, R><<<grid, 128, 0, st2>>>((const double *)d_u, (double *)d_out, d);
+        }
         SHB_CUDA(cudaGetLastError());
         return SHB_OK;
     }

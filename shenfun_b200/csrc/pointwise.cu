@@ -341,6 +341,34 @@ int shb_lincomb(void *d_out, int nterms, const void *const *d_terms, const doubl
     return SHB_OK;
 }
 
+// Velocity components from f = du/dx and the wall-normal vorticity g under the divergence constraint
+// (demo/ChannelFlow.py:235-239):  v = i (a f + b g),  w = i (b f - a g),  a = ky/(ky^2+kz^2), b = kz/(...)
+// broadcast over the wall-normal index.  One pass instead of eight element-wise launches.
+__global__ void __launch_bounds__(PW_THREADS) kmm_vw_kernel(const cplx *__restrict__ f, const cplx *__restrict__ g,
+                                                            const double *__restrict__ a, const double *__restrict__ b,
+                                                            cplx *__restrict__ v, cplx *__restrict__ w, int64_t n,
+                                                            int64_t n12) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = i % n12;
+        const double A = __ldg(&a[k]), B = __ldg(&b[k]);
+        const cplx F = f[i], G = g[i];
+        const cplx t1 = make_double2(fma(A, F.x, B * G.x), fma(A, F.y, B * G.y));
+        const cplx t2 = make_double2(fma(B, F.x, -A * G.x), fma(B, F.y, -A * G.y));
+        v[i] = make_double2(-t1.y, t1.x);
+        w[i] = make_double2(-t2.y, t2.x);
+    }
+}
+
+int shb_kmm_vw(const void *d_f, const void *d_g, const double *d_a, const double *d_b, void *d_v, void *d_w, int64_t n,
+               int64_t n12, void *stream) {
+    SHB_REQUIRE(d_f && d_g && d_a && d_b && d_v && d_w && n >= 0 && n12 >= 1, "bad arguments");
+    if (n == 0) return SHB_OK;
+    kmm_vw_kernel<<<pw_blocks(n), PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const cplx *)d_f, (const cplx *)d_g, d_a, d_b, (cplx *)d_v, (cplx *)d_w, n, n12);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
 int shb_apply_mask(void *d_u, const double *d_mask, int64_t n, int ncomp, void *stream) {
     SHB_REQUIRE(d_u && d_mask && n >= 0 && ncomp >= 1, "bad arguments");
     if (n == 0) return SHB_OK;

@@ -138,8 +138,7 @@ class KMM:
             self.h2.v.copy_(self.H_.v[2, :, 0, 0].real)
         f = self.dudx().v
         g = self.g_.v
-        u[1] = 1j*(self.K_over_K2[0]*f+self.K_over_K2[1]*g)
-        u[2] = 1j*(self.K_over_K2[1]*f-self.K_over_K2[0]*g)
+        ops.kmm_vw(ops.plain(f), ops.plain(g), self.K_over_K2[0], self.K_over_K2[1], u[1], u[2])
         if self.owns_00:
             self.pdes1d['v0'].compute_rhs(rk)
             u[1, :, 0, 0] = self.pdes1d['v0'].solve_step(rk).v.to(u.dtype)

@@ -180,6 +180,15 @@ def lincomb(out, terms, coefs, mask=None, saves=()):
     return out
 
 
+def kmm_vw(f, g, a, b, v, w):
+    """v = i(a f + b g), w = i(b f - a g); a, b real, broadcast over the leading index
+    (demo/ChannelFlow.py:235-239)."""
+    n12 = a.numel()
+    assert b.numel() == n12 and f.numel() % n12 == 0 and g.numel() == f.numel() == v.numel() == w.numel()
+    _call('shb_kmm_vw', _req(f, C128, 'f'), _req(g, C128, 'g'), _req(a, F64, 'a'), _req(b, F64, 'b'),
+          _req(v, C128, 'v'), _req(w, C128, 'w'), f.numel(), n12, _lib.stream_ptr())
+
+
 def apply_mask(u_hat, mask):
     n = mask.numel()
     _call('shb_apply_mask', _req(u_hat, C128, 'u_hat'), _req(mask, F64, 'mask'), n, u_hat.numel()//n,

@@ -37,3 +37,23 @@ def test_dot_grad3d_kernel():
     out = torch.empty((3,)+shape, dtype=torch.float64, device='cuda')
     ops.dot_grad3d(torch.from_numpy(u).cuda(), [torch.from_numpy(x).cuda() for x in g], out)
     assert np.abs(out.cpu().numpy()-ref).max() < 1e-14
+
+
+@pytest.mark.gpu
+def test_kmm_vw_kernel_matches_the_reference_expression():
+    """shb_kmm_vw against demo/ChannelFlow.py:238-239 evaluated with torch."""
+    import torch
+    from shenfun_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(3)
+    n0, n1, n2 = 19, 12, 7
+    f = torch.randn(n0, n1, n2, dtype=torch.complex128, device='cuda', generator=g)
+    gg = torch.randn(n0, n1, n2, dtype=torch.complex128, device='cuda', generator=g)
+    a = torch.randn(1, n1, n2, dtype=torch.float64, device='cuda', generator=g)
+    b = torch.randn(1, n1, n2, dtype=torch.float64, device='cuda', generator=g)
+    u = torch.zeros(3, n0, n1, n2, dtype=torch.complex128, device='cuda')
+    ops.kmm_vw(f, gg, a, b, u[1], u[2])
+    v_ref = 1j*(a*f+b*gg)
+    w_ref = 1j*(b*f-a*gg)
+    assert (u[1]-v_ref).abs().max().item() <= 1e-14*v_ref.abs().max().item()
+    assert (u[2]-w_ref).abs().max().item() <= 1e-14*w_ref.abs().max().item()
+    assert u[0].abs().max().item() == 0.0
