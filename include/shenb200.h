@@ -352,6 +352,16 @@ SHB_API int shb_cheb_backward(const void *d_in, void *d_out, int64_t outer, int6
  * (shenfun/spectralbase.py:448-491, 516-558; optimization/cython/transforms.pyx:175-323). */
 SHB_API int shb_gemm_axis(const double *d_A, const void *d_u, void *d_out, int M, int K, int64_t outer,
                           int64_t inner, int is_complex, void *stream);
+/* Same contraction for an operator with the parity structure of the symmetric families (Legendre, Jacobi(a,a),
+ * Chebyshev: basis functions even / odd, quadrature points symmetric): half the tensor-core work.
+ *   forward != 0: A[i][K-1-j] = (-1)^i A[i][j] (K even; values -> coefficients),
+ *   forward == 0: A[M-1-i][k] = (-1)^k A[i][k] (M even; coefficients -> values).
+ * d_A2 = the two half operators [2][Mh][Kp], Kp even and zero padded: forward: A2[p][i][j] = A[2i+p][j]
+ * (Mh = ceil(M/2), j < K/2); backward: A2[p][i][k] = A[i][2k+p] (Mh = M/2, k < ceil(K/2)).
+ * Returns SHB_ERR_UNSUPPORTED for layouts it does not cover (inner*(complex?2:1) odd or 1, unaligned
+ * pointers): call shb_gemm_axis then. */
+SHB_API int shb_gemm_axis_parity(const double *d_A2, const void *d_u, void *d_out, int M, int K, int Kp, int forward,
+                                 int64_t outer, int64_t inner, int is_complex, void *stream);
 
 #ifdef __cplusplus
 }

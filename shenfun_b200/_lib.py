@@ -63,6 +63,7 @@ def _declare(lib):
         'shb_biharmonic_solve': [vp, vp, vp, i64, i64, i32, i32, i32, vp],
         'shb_biharmonic_matvec': [vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp],
         'shb_gemm_axis': [vp, vp, vp, i32, i32, i64, i64, i32, vp],
+        'shb_gemm_axis_parity': [vp, vp, vp, i32, i32, i32, i32, i64, i64, i32, vp],
         'shb_cheb_backward': [vp, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp],
     }
     for name, argtypes in sig.items():
@@ -98,6 +99,9 @@ def load():
         lib._signatures = _declare(lib)
         _lib = lib
     return _lib
+
+
+SHB_ERR_UNSUPPORTED = -3        # include/shenb200.h: shb_status
 
 
 def check(rc):

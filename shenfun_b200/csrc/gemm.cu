@@ -225,6 +225,140 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemm_axis_kernel(const __grid_c
     }
 }
 
+// ---- parity-split contraction -----------------------------------------------------------------------
+// Legendre / Jacobi(a,a) / Chebyshev functions are even or odd and their quadrature points are symmetric,
+// so an operator matrix of these families satisfies either
+//   FWD (values -> coefficients):  A[i][K-1-j] = (-1)^i A[i][j]   ->  even rows act on s_j = u_j + u_{K-1-j},
+//                                                                     odd rows on d_j = u_j - u_{K-1-j},
+//   BWD (coefficients -> values):  A[M-1-i][k] = (-1)^k A[i][k]   ->  e_i = sum_{k even}, o_i = sum_{k odd},
+//                                                                     out_i = e_i + o_i, out_{M-1-i} = e_i - o_i
+// and the contraction is two products of half the size: HALF the tensor-core work of the dense product.
+// The butterflies cost nothing extra here: FWD forms s, d in registers when the B fragments are read
+// from the two staged row tiles (rows j and their mirrors), BWD adds / subtracts the two accumulator
+// sets in the epilogue.  `A2` holds the two half operators [2][Mh][Kp] (Kp even, zero padded), built
+// on the host by ops.gemm_axis after testing the structure numerically.
+// CTA tile: 64 rows of EACH set x 64 columns, 16 contraction indices of each set per stage.
+constexpr int GP_BM = 64, GP_BN = 64, GP_BK = 16, GP_AS = GP_BK + 4, GP_XS = GP_BN + 8, GP_STAGES = 2;
+constexpr size_t GP_SMEM = GP_STAGES * 2 * ((size_t)GP_BM * GP_AS + (size_t)GP_BK * GP_XS) * sizeof(double);
+
+struct ParityDesc {
+    const double *A2;
+    const double *X;
+    double *C;
+    int M, K, Mh, Kh, Kp;
+    int64_t W, xs_batch, xs_k, cs_batch, cs_m;
+};
+
+template <bool FWD>
+__global__ void __launch_bounds__(GM_THREADS, 2) gemm_axis_parity_kernel(const __grid_constant__ ParityDesc d) {
+    extern __shared__ __align__(16) unsigned char gm_smem[];
+    double *sA = reinterpret_cast<double *>(gm_smem);                           // [stage][set][BM][AS]
+    double *sX = sA + (size_t)GP_STAGES * 2 * GP_BM * GP_AS;                    // [stage][set][BK][XS]
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 1, wn = warp & 1;      // 16 rows of each set x 32 columns per warp
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t w0 = (int64_t)blockIdx.x * GP_BN;
+    const int m0 = blockIdx.y * GP_BM;
+    const double *X = d.X + (int64_t)blockIdx.z * d.xs_batch;
+    double *C = d.C + (int64_t)blockIdx.z * d.cs_batch;
+
+    double acc[2][4][4];
+#pragma unroll
+    for (int s_ = 0; s_ < 2; ++s_)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[s_][j][e] = 0.0;
+
+    auto load_tiles = [&](int buf, int k0) {
+        double *a = sA + (size_t)buf * 2 * GP_BM * GP_AS;
+        double *x = sX + (size_t)buf * 2 * GP_BK * GP_XS;
+#pragma unroll
+        for (int r = 0; r < (2 * GP_BM * GP_BK) / (2 * GM_THREADS); ++r) {
+            const int e = tid + r * GM_THREADS;
+            const int set = e / (GP_BM * GP_BK / 2), e2 = e % (GP_BM * GP_BK / 2);
+            const int kk = (e2 % (GP_BK / 2)) * 2, mm = e2 / (GP_BK / 2);
+            const int gm = m0 + mm, gk = k0 + kk;
+            const bool ok = (gm < d.Mh && gk < d.Kp);
+            cp_async16g(&a[(set * GP_BM + mm) * GP_AS + kk], ok ? &d.A2[((int64_t)set * d.Mh + gm) * d.Kp + gk] : d.A2, ok);
+        }
+#pragma unroll
+        for (int r = 0; r < (2 * GP_BK * GP_BN) / (2 * GM_THREADS); ++r) {
+            const int e = tid + r * GM_THREADS;
+            const int set = e / (GP_BK * GP_BN / 2), e2 = e % (GP_BK * GP_BN / 2);
+            const int ww = (e2 % (GP_BN / 2)) * 2, kk = e2 / (GP_BN / 2);
+            const int gk = k0 + kk;
+            const int row = FWD ? (set == 0 ? gk : d.K - 1 - gk) : 2 * gk + set;
+            const int64_t gw = w0 + ww;
+            const bool ok = (gk < d.Kh && row < d.K && gw < d.W);
+            cp_async16g(&x[(set * GP_BK + kk) * GP_XS + ww], ok ? &X[(int64_t)row * d.xs_k + gw] : X, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int nk = (d.Kh + GP_BK - 1) / GP_BK;
+#pragma unroll
+    for (int p = 0; p < GP_STAGES - 1; ++p) {
+        if (p < nk) load_tiles(p, p * GP_BK);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt % GP_STAGES;
+        asm volatile("cp.async.wait_group %0;" ::"n"(GP_STAGES - 2) : "memory");
+        __syncthreads();
+        if (kt + GP_STAGES - 1 < nk) load_tiles((kt + GP_STAGES - 1) % GP_STAGES, (kt + GP_STAGES - 1) * GP_BK);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const double *a = sA + (size_t)buf * 2 * GP_BM * GP_AS;
+        const double *x0 = sX + (size_t)buf * 2 * GP_BK * GP_XS;
+        const double *x1 = x0 + GP_BK * GP_XS;
+        double af[2][8];
+#pragma unroll
+        for (int s_ = 0; s_ < 2; ++s_)
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                af[s_][e] = a[(s_ * GP_BM + wm * 16 + g + 8 * (e & 1)) * GP_AS + t + 4 * (e >> 1)];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double b0[4], b1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double p0 = x0[(t + 4 * e) * GP_XS + wn * 32 + j * 8 + g];
+                const double p1 = x1[(t + 4 * e) * GP_XS + wn * 32 + j * 8 + g];
+                b0[e] = FWD ? p0 + p1 : p0;
+                b1[e] = FWD ? p0 - p1 : p1;
+            }
+            dmma16(acc[0][j], af[0], b0);
+            dmma16(acc[1][j], af[1], b1);
+        }
+    }
+    // epilogue: c[0..1] = C[g][2t + {0,1}], c[2..3] = C[g + 8][2t + {0,1}] of each 16 x 8 tile
+    const bool c16 = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (d.cs_m % 2 == 0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = m0 + wm * 16 + g + 8 * h;       // row of the half problem
+        if (i >= d.Mh) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t gw = w0 + wn * 32 + j * 8 + t * 2;
+            const double e0 = acc[0][j][2 * h], e1 = acc[0][j][2 * h + 1];
+            const double o0 = acc[1][j][2 * h], o1 = acc[1][j][2 * h + 1];
+            const int ra = FWD ? 2 * i : i, rb = FWD ? 2 * i + 1 : d.M - 1 - i;
+            const double a0 = FWD ? e0 : e0 + o0, a1 = FWD ? e1 : e1 + o1;
+            const double b0 = FWD ? o0 : e0 - o0, b1 = FWD ? o1 : e1 - o1;
+            if (c16 && gw + 1 < d.W) {
+                if (ra < d.M) *reinterpret_cast<double2 *>(&C[(int64_t)ra * d.cs_m + gw]) = make_double2(a0, a1);
+                if (rb < d.M) *reinterpret_cast<double2 *>(&C[(int64_t)rb * d.cs_m + gw]) = make_double2(b0, b1);
+            } else {
+                if (ra < d.M && gw < d.W) C[(int64_t)ra * d.cs_m + gw] = a0;
+                if (ra < d.M && gw + 1 < d.W) C[(int64_t)ra * d.cs_m + gw + 1] = a1;
+                if (rb < d.M && gw < d.W) C[(int64_t)rb * d.cs_m + gw] = b0;
+                if (rb < d.M && gw + 1 < d.W) C[(int64_t)rb * d.cs_m + gw + 1] = b1;
+            }
+        }
+    }
+}
+
 }  // namespace shb
 
 using namespace shb;
@@ -257,6 +391,34 @@ int shb_gemm_axis(const double *d_A, const void *d_u, void *d_out, int M, int K,
     dim3 grid((unsigned)((d.W + GM_BN - 1) / GM_BN), (unsigned)((M + GM_BM - 1) / GM_BM), (unsigned)d.nbatch);
     if (k4) gemm_axis_kernel<false><<<grid, GM_THREADS, GM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(d);
     else gemm_axis_kernel<true><<<grid, GM_THREADS, GM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(d);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+/* Parity-split contraction (see gemm_axis_parity_kernel): A2 = the two half operators [2][Mh][Kp] built by the
+ * caller; forward != 0: column-mirror structure (K even), else row-mirror structure (M even).  Needs inner*(complex?2:1)
+ * > 1 and even, 16-byte aligned arrays; SHB_ERR_UNSUPPORTED otherwise (use shb_gemm_axis). */
+int shb_gemm_axis_parity(const double *d_A2, const void *d_u, void *d_out, int M, int K, int Kp, int forward,
+                         int64_t outer, int64_t inner, int is_complex, void *stream) {
+    SHB_REQUIRE(d_A2 && d_u && d_out && M >= 1 && K >= 1 && Kp >= 2 && Kp % 2 == 0 && outer >= 0 && inner >= 0, "bad arguments");
+    if (d_u == d_out) { set_error("gemm_axis_parity: in-place is not supported"); return SHB_ERR_ARG; }
+    if (outer * inner == 0) return SHB_OK;
+    const int64_t W = inner * (is_complex ? 2 : 1);
+    if (W < 2 || W % 2 || outer > 65535 || (forward ? K % 2 : M % 2) ||
+        ((reinterpret_cast<uintptr_t>(d_A2) | reinterpret_cast<uintptr_t>(d_u) | reinterpret_cast<uintptr_t>(d_out)) & 15))
+        return SHB_ERR_UNSUPPORTED;
+    ParityDesc d;
+    d.A2 = d_A2; d.X = (const double *)d_u; d.C = (double *)d_out; d.M = M; d.K = K; d.Kp = Kp;
+    d.Mh = forward ? (M + 1) / 2 : M / 2;
+    d.Kh = forward ? K / 2 : (K + 1) / 2;
+    if (d.Kh > Kp) { set_error("gemm_axis_parity: operator pitch %d < %d", Kp, d.Kh); return SHB_ERR_ARG; }
+    d.W = W; d.xs_batch = (int64_t)K * W; d.xs_k = W; d.cs_batch = (int64_t)M * W; d.cs_m = W;
+    SHB_CUDA(cudaFuncSetAttribute(gemm_axis_parity_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM));
+    SHB_CUDA(cudaFuncSetAttribute(gemm_axis_parity_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM));
+    dim3 grid((unsigned)((W + GP_BN - 1) / GP_BN), (unsigned)((d.Mh + GP_BM - 1) / GP_BM), (unsigned)outer);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (forward) gemm_axis_parity_kernel<true><<<grid, GM_THREADS, GP_SMEM, st>>>(d);
+    else gemm_axis_parity_kernel<false><<<grid, GM_THREADS, GP_SMEM, st>>>(d);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }

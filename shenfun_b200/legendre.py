@@ -175,7 +175,9 @@ class Orthogonal(PolyBase):
             B = np.zeros((Np, self.N))
             B[:, :dim] = V @ K.T
             nbc = self.bcs.num_bcs()
-            if nbc:
+            # homogeneous conditions: the boundary dofs are zero by definition, their columns stay zero and the
+            # operator keeps the parity structure ops.gemm_axis exploits (half the tensor-core work)
+            if nbc and not self.bcs.is_homogeneous():
                 L = self.bc_basis()                           # (nbc, 4)
                 B[:, dim:] = V[:, :4] @ L[:, :min(4, self.N)].T if self.N >= 4 else 0
             self._tables['ops'] = (ops.as_device_tensor(np.ascontiguousarray(F)),

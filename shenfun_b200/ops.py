@@ -295,12 +295,65 @@ def cheb_backward(uh, out, outer, inner, n_phys, n_spec, dim, soff, sten, nbc=0,
           None if bc_lift is None else _req(bc_lift, F64, 'bc_lift'), _lib.stream_ptr())
 
 
+_PARITY = {}        # operator data_ptr -> (operator (kept alive), packed halves | None, forward flag, Kp)
+
+
+def _parity_halves(A):
+    """Test a (M, K) operator for the parity structure of the symmetric families and pack its two half
+    operators for `shb_gemm_axis_parity` (include/shenb200.h).  None when the structure is absent."""
+    import numpy as np
+    a = A.detach().cpu().numpy()
+    M, K = a.shape
+    tol = 1e-13*max(1.0, float(np.abs(a).max()))
+    sgn_r = (-1.0)**np.arange(M)[:, None]
+    sgn_c = (-1.0)**np.arange(K)[None, :]
+    if K % 2 == 0 and K >= 4 and np.abs(a[:, ::-1]-sgn_r*a).max() <= tol:          # values -> coefficients
+        Kh, Mh = K//2, (M+1)//2
+        Kp = Kh+Kh % 2
+        sym = 0.5*(a[:, :Kh]+sgn_r*a[:, ::-1][:, :Kh])
+        h = np.zeros((2, Mh, Kp))
+        h[0, :, :Kh] = sym[0::2]
+        h[1, :M//2, :Kh] = sym[1::2]
+        return as_device_tensor(h), 1, Kp
+    if M % 2 == 0 and M >= 4 and np.abs(a[::-1, :]-sgn_c*a).max() <= tol:          # coefficients -> values
+        Mh, Kh = M//2, (K+1)//2
+        Kp = Kh+Kh % 2
+        sym = 0.5*(a[:Mh]+sgn_c*a[::-1][:Mh])
+        h = np.zeros((2, Mh, Kp))
+        h[0, :, :Kh] = sym[:, 0::2]
+        h[1, :, :K//2] = sym[:, 1::2]
+        return as_device_tensor(h), 0, Kp
+    return None
+
+
 def gemm_axis(A, u, out, outer, inner):
-    """out[o][i][c] = sum_j A[i][j] u[o][j][c] (A real (M, K) device matrix)."""
+    """out[o][i][c] = sum_j A[i][j] u[o][j][c] (A real (M, K) device matrix).  Operators with the parity
+    structure of the symmetric families (tested once per operator on the host; do the first call outside
+    CUDA-graph capture) go through the half-size contraction `shb_gemm_axis_parity`; SHB_GEMM_PARITY=0: off."""
+    import os
+    global LAUNCHES
     assert u.dtype == out.dtype
     M, K = A.shape
+    cplx = int(u.dtype.is_complex)
+    W = inner*(2 if cplx else 1)
+    if W >= 2 and W % 2 == 0 and outer <= 65535 and os.environ.get('SHB_GEMM_PARITY', '1') != '0':
+        key = (A.data_ptr(), M, K)
+        ent = _PARITY.get(key)
+        if ent is None or ent[0] is not A:
+            if len(_PARITY) > 64:
+                _PARITY.clear()
+            ent = _PARITY[key] = (A, _parity_halves(A))
+        if ent[1] is not None:
+            A2, fwd, Kp = ent[1]
+            L = _lib.load()
+            rc = L.shb_gemm_axis_parity(_req(A2, F64, 'A2'), _req(u, u.dtype, 'u'), _req(out, out.dtype, 'out'), M, K, Kp,
+                                        fwd, outer, inner, cplx, _lib.stream_ptr())
+            if rc != _lib.SHB_ERR_UNSUPPORTED:
+                _lib.check(rc)
+                LAUNCHES += 1
+                return
     _call('shb_gemm_axis', _req(A, F64, 'A'), _req(u, u.dtype, 'u'), _req(out, out.dtype, 'out'), M, K, outer, inner,
-          int(u.dtype.is_complex), _lib.stream_ptr())
+          cplx, _lib.stream_ptr())
 
 
 def tail_matvec(u, out, r, t, scale, w, outer, inner, n_rows, n_cols, n_u, n_out, accumulate):
