@@ -562,7 +562,7 @@ def ns_cross_kernel_roofline(peak):
     return {'bound': 'hbm', 'kernel': 'fft_c2r_cross3_kernel (six C2R 768-point lines as three complex ones + cross product)', 'achieved': ach,
             'peak': peak, 'unit': 'GB/s', 'frac': ach/peak, 'algorithmic_bytes_per_launch': nbytes, 'avg_launch_ms': ms,
             'launches_per_step': 4, 'traffic': 25390000000,
-            'traffic_source': 'profiles/r1_ncu_full_summary_final.txt (dram read 14.55 GB + write 10.84 GB)'}
+            'traffic_source': 'profiles/r2_ncu_full_summary.txt (fft_c2r_cross3_kernel: dram read 14.55 GB + write 10.84 GB)'}
 
 
 def secondary_workloads(T, uh, args, peak, with_cpu=True):

@@ -22,7 +22,7 @@ namespace shb {
 
 constexpr int GM_BM = 128, GM_BN = 64, GM_BK = 32, GM_THREADS = 256;
 constexpr int GM_AS = GM_BK + 4;     // A tile row pitch (doubles): pitch % 16 == 4 -> conflict-free fragments
-constexpr int GM_XS = GM_BN + 8;     // X tile row pitch: pitch % 16 == 8
+constexpr int GM_XS = GM_BN + 4;     // X tile row pitch: pitch % 16 == 4 (the 16 lanes of a half-warp hit 16 distinct 8-byte banks)
 constexpr int GM_STAGES = 2;
 constexpr size_t GM_SMEM = GM_STAGES * ((size_t)GM_BM * GM_AS + (size_t)GM_BK * GM_XS) * sizeof(double);
 
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemm_axis_kernel(const __grid_c
 // sets in the epilogue.  `A2` holds the two half operators [2][Mh][Kp] (Kp even, zero padded), built
 // on the host by ops.gemm_axis after testing the structure numerically.
 // CTA tile: 64 rows of EACH set x 64 columns, 16 contraction indices of each set per stage.
-constexpr int GP_BM = 64, GP_BN = 64, GP_BK = 16, GP_AS = GP_BK + 4, GP_XS = GP_BN + 8, GP_STAGES = 2;
+constexpr int GP_BM = 64, GP_BN = 64, GP_BK = 16, GP_AS = GP_BK + 4, GP_XS = GP_BN + 4, GP_STAGES = 3;
 constexpr size_t GP_SMEM = GP_STAGES * 2 * ((size_t)GP_BM * GP_AS + (size_t)GP_BK * GP_XS) * sizeof(double);
 
 struct ParityDesc {
