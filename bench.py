@@ -412,7 +412,7 @@ def _time_launch(fn, reps=10):
     return e0.elapsed_time(e1)/reps
 
 
-# ncu kernel name of each stage of the forward plan (profiles/r1_ncu_full_summary_final.txt)
+# ncu kernel name of each stage of the forward plan (profiles/r2_ncu_full_summary.txt)
 _STAGE_KERNEL = {
     'r2c_axis2': 'void fft_contig_kernel<Sched<256, 8, 8, 4, 32>, 2, 8>',
     'c2c_axis1': 'void fft_strided_kernel<Sched<512, 8, 8, 8, 64>, 0, 8, 0>',
@@ -423,7 +423,7 @@ _STAGE_KERNEL = {
 def ncu_traffic_bytes(stage):
     """dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernel, per launch, from the
     committed `ncu --set full` capture (profiles/); None when the summary is not there."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_full_summary_final.txt')
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r2_ncu_full_summary.txt')
     want = _STAGE_KERNEL.get(stage)
     if want is None or not os.path.exists(path):
         return None
@@ -458,7 +458,7 @@ def dominant_kernel_roofline(T, u, uh, peak, peak_src):
     ach = nbytes/(ms*1e-3)/1e9
     return {'bound': 'hbm', 'kernel': name, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach/peak,
             'peak_source': peak_src, 'traffic': ncu_traffic_bytes(name),
-            'traffic_source': 'profiles/r1_ncu_full_summary_final.txt (ncu --set full, dram read + write per launch)',
+            'traffic_source': 'profiles/r2_ncu_full_summary.txt (ncu --set full, dram read + write per launch)',
             'algorithmic_bytes_per_launch': nbytes,
             'avg_launch_ms': ms,
             'all_stages_gbs': {k: v[1]/(v[0]*1e-3)/1e9 for k, v in stages.items()}}
