@@ -77,6 +77,15 @@ SHB_API int shb_fft_c2c_backward(const void *d_in, void *d_out, int64_t outer, i
  * shb_cross3d separately). */
 SHB_API int shb_fft_c2r_cross(const void *d_in, const void *d_b, void *d_out, int64_t nlines, int n_fft,
                               int N, double scale, int flags, void *stream);
+/* First pass of the Navier-Stokes nonlinear term (demo/NavierStokes.py:37-39: `curl_hat = cross(K, U_hat) * 1j`
+ * followed by the padded backward of both fields): u_hat [3][N][inner] (inner = n1*n2 spectral columns) ->
+ * out [6][n_fft][inner], n_fft = 3N/2: fields 0..2 the 3/2-rule padded backward C2C of u_hat along the
+ * leading axis, fields 3..5 the same of i k x u_hat, formed on the fly from the wavenumber tables
+ * k0 [N], k1 [n1], k2 [n2].  The vorticity spectrum never exists in memory.  SHB_ERR_UNSUPPORTED unless
+ * N/2 is one of 64, 128, 256, 512. */
+SHB_API int shb_fft_c2c_backward_curl(const void *d_u_hat, void *d_out, int64_t inner, int n2, int n_fft, int N,
+                                      const double *d_k0, const double *d_k1, const double *d_k2, double scale,
+                                      void *stream);
 
 /* C2C transform fused with the local half of the slab all-to-all (replaces the pack /
  * unpack that mpi4py_fft.pencil.Transfer expresses as MPI sub-array datatypes; call sites

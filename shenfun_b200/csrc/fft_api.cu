@@ -39,6 +39,18 @@ int shb_fft_c2r_cross(const void *d_in, const void *d_b, void *d_out, int64_t nl
     return rc;
 }
 
+int shb_fft_c2c_backward_curl(const void *d_u_hat, void *d_out, int64_t inner, int n2, int n_fft, int N,
+                              const double *d_k0, const double *d_k1, const double *d_k2, double scale, void *stream) {
+    if (!d_u_hat || !d_out || d_u_hat == d_out || !d_k0 || !d_k1 || !d_k2 || inner < 0 || n2 < 1 || n_fft < 1 || N < 1) {
+        set_error("fft_c2c_backward_curl: bad arguments");
+        return SHB_ERR_ARG;
+    }
+    int rc = fft_pad3_curl_launch(d_u_hat, d_out, inner, n2, n_fft, N, d_k0, d_k1, d_k2, scale,
+                                  reinterpret_cast<cudaStream_t>(stream));
+    if (rc == SHB_ERR_UNSUPPORTED) set_error("fft_c2c_backward_curl: no fused kernel for N=%d -> n_fft=%d", N, n_fft);
+    return rc;
+}
+
 int shb_fft_c2c_peer(int backward, const void *d_in, void *const *d_peer_out, int nranks, int64_t outer,
                      int64_t inner, int n_fft, int N, double scale, int flags, int in_chunk_rows,
                      int out_chunk_rows, void *stream) {

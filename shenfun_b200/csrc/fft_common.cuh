@@ -70,6 +70,8 @@ int fft_generic_launch(int mode, const void *in, void *out, int64_t outer, int64
                        int n_fft, int N, double scale, int flags, cudaStream_t st);
 
 // returns SHB_ERR_UNSUPPORTED when no specialised kernel covers the case
+int fft_pad3_curl_launch(const void *u_hat, void *out, int64_t inner, int n2, int n_fft, int N, const double *k0,
+                         const double *k1, const double *k2, double scale, cudaStream_t st);
 int fft_fast_launch(int mode, const void *in, void *out, int64_t outer, int64_t inner,
                     int n_fft, int N, double scale, int flags, cudaStream_t st, int in_cr = 0, int out_cr = 0,
                     void *const *peer_out = nullptr, int npeer = 0);

@@ -173,6 +173,9 @@ struct FastDesc {
     double scale;
     const cplx *tw, *tw2;
     int pf = 0;       // fft_contig_kernel: L2 prefetch distance in CTAs (0: off)
+    // fft_strided_pad3x_kernel<..., CURL>: wavenumber tables of the three axes, extent of the last axis
+    const double *k0 = nullptr, *k1 = nullptr, *k2 = nullptr;
+    int curl_n2 = 1;
     // peer-chunked addressing along the transform axis (fused all-to-all pack / unpack):
     // row r of outer index o lives at (r / cr) * cs + ((o * cr + r % cr) * inner + c); cr == 0: off
     int in_cr, out_cr;
@@ -818,83 +821,111 @@ __global__ void __launch_bounds__(SC::P *T, (SC::P * T <= 256 ? 3 : 1)) fft_stri
     }
 }
 
-template <class SC, int T, bool CH>
+// CURL (Navier-Stokes, first pass of the padded backward of [u_hat; curl u_hat]): the input holds the THREE
+// velocity components only; a CTA owns one column tile and produces its six fields one after the other:
+// the three velocity components, then fields 3..5 formed on the fly as i k x u_hat from two velocity
+// lines and the wavenumber tables (demo/NavierStokes.py:37).  The velocity tile comes from HBM once -- the
+// loads of the vorticity fields hit L2, the CTA read the same lines microseconds earlier -- and the
+// vorticity spectrum is never written to or read from HBM.  (Six CTAs per tile, one per field, run
+// together but each missed L2 on its own: no gain measured.)
+template <class SC, int T, bool CH, bool CURL = false>
 __global__ void __launch_bounds__(SC::P *T, (SC::P * T <= 256 ? 2 : 1)) fft_strided_pad3x_kernel(const __grid_constant__ FastDesc d) {
+    static_assert(!(CH && CURL), "the fused curl runs on the plain layout");
     constexpr int MP = SC::M, P = SC::P;          // M' and threads per line
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *sm = reinterpret_cast<cplx *>(smem_raw);
     const int c = threadIdx.x % T;
     const int j = threadIdx.x / T;
     const int64_t line = (int64_t)blockIdx.x * T + c;
-    const bool valid = line < d.nlines;
-    const int64_t o = valid ? line / d.inner : 0, cc = valid ? line % d.inner : 0;
+    const bool valid = CURL ? line < d.inner : line < d.nlines;
     const cplx *__restrict__ inb = reinterpret_cast<const cplx *>(d.in);
     cplx *__restrict__ outb = reinterpret_cast<cplx *>(d.out);
-    auto in_at = [&](int r) -> const cplx & {
-        if (CH && d.in_cr) {
-            const int p = r / d.in_cr;
-            return inb[p * d.in_cs + ((o * d.in_cr + (r - p * d.in_cr)) * d.inner + cc)];
-        }
-        return inb[(o * d.n_in + r) * d.inner + cc];
-    };
-    auto out_at = [&](int r) -> cplx & {
-        if (CH && d.out_cr) {
-            const int p = r / d.out_cr;
-            const int64_t off = (o * d.out_cr + (r - p * d.out_cr)) * d.inner + cc;
-            if (d.use_peer) return d.out_peer[p][off];
-            return outb[p * d.out_cs + off];
-        }
-        return outb[(o * d.n_out + r) * d.inner + cc];
-    };
-    // every thread keeps its 2 x EMAX inputs in registers and runs the three residue transforms
-    // (n2 = 0, 1, 2) back to back: the inputs are read from HBM/L2 once instead of three times
-    cplx xa[SC::B0 * SC::R0], xb[SC::B0 * SC::R0];
-    if (j < SC::NB0) {
-#pragma unroll
-        for (int q = 0; q < SC::B0; ++q)
-#pragma unroll
-            for (int m = 0; m < SC::R0; ++m) {
-                const int k = (j + q * P) + m * SC::NB0;
-                xa[q * SC::R0 + m] = valid ? in_at(k) : make_double2(0.0, 0.0);
-                xb[q * SC::R0 + m] = valid ? in_at(k + MP) : make_double2(0.0, 0.0);
-            }
+    const int64_t cc = CURL ? (valid ? line : 0) : (valid ? line % d.inner : 0);
+    double kcol[3] = {0.0, 0.0, 0.0};
+    if (CURL) {
+        kcol[1] = __ldg(&d.k1[cc / d.curl_n2]);
+        kcol[2] = __ldg(&d.k2[cc % d.curl_n2]);
     }
     auto s = [&](int pos) -> cplx & { return sm[pos * T + c]; };
     const double scale = d.scale;
 #pragma unroll 1
-    for (int n2 = 0; n2 < 3; ++n2) {
-        // f = e^(4 pi i n2 / 3)
-        const double fr = (n2 == 0) ? 1.0 : -0.5;
-        const double fi = (n2 == 0) ? 0.0 : (n2 == 1 ? -0.86602540378443864676372317075294 : 0.86602540378443864676372317075294);
-        cplx v[SC::EMAX];
+    for (int fld = 0; fld < (CURL ? 6 : 1); ++fld) {
+        const int64_t o = CURL ? (int64_t)fld : (valid ? line / d.inner : 0);
+        // CURL: field 3 + ci = i (k_a u_b - k_b u_a), a = ci + 1, b = ci + 2 (mod 3); k_0 varies along the line
+        const int ci = fld >= 3 ? fld - 3 : 0;
+        const int fa = (ci + 1) % 3, fb = (ci + 2) % 3;
+        auto in_at = [&](int r) -> cplx {
+            if (CH && d.in_cr) {
+                const int p = r / d.in_cr;
+                return inb[p * d.in_cs + ((o * d.in_cr + (r - p * d.in_cr)) * d.inner + cc)];
+            }
+            if (CURL && fld >= 3) {
+                const double k0r = __ldg(&d.k0[r]);
+                const double ka = fa == 0 ? k0r : kcol[fa], kb = fb == 0 ? k0r : kcol[fb];
+                const cplx ub = inb[((int64_t)fb * d.n_in + r) * d.inner + cc];
+                const cplx ua = inb[((int64_t)fa * d.n_in + r) * d.inner + cc];
+                const cplx t = make_double2(ka * ub.x - kb * ua.x, ka * ub.y - kb * ua.y);
+                return make_double2(-t.y, t.x);
+            }
+            return inb[(o * d.n_in + r) * d.inner + cc];
+        };
+        auto out_at = [&](int r) -> cplx & {
+            if (CH && d.out_cr) {
+                const int p = r / d.out_cr;
+                const int64_t off = (o * d.out_cr + (r - p * d.out_cr)) * d.inner + cc;
+                if (d.use_peer) return d.out_peer[p][off];
+                return outb[p * d.out_cs + off];
+            }
+            return outb[(o * d.n_out + r) * d.inner + cc];
+        };
+        // every thread keeps its 2 x EMAX inputs in registers and runs the three residue transforms
+        // (n2 = 0, 1, 2) back to back: the inputs are read from HBM/L2 once instead of three times
+        cplx xa[SC::B0 * SC::R0], xb[SC::B0 * SC::R0];
         if (j < SC::NB0) {
 #pragma unroll
             for (int q = 0; q < SC::B0; ++q)
 #pragma unroll
                 for (int m = 0; m < SC::R0; ++m) {
                     const int k = (j + q * P) + m * SC::NB0;
-                    const cplx a = xa[q * SC::R0 + m], b = xb[q * SC::R0 + m];
-                    cplx z;
-                    if (k == 0) {
-                        z = make_double2(fma(fr, b.x, a.x), fma(fr, b.y, a.y));
-                    } else {
-                        z = make_double2(a.x + fr * b.x - fi * b.y, a.y + fr * b.y + fi * b.x);
-                        if (n2 > 0) z = cmulc(z, __ldg(&d.tw2[n2 * k]));      // * e^(+2 pi i n2 k / M)
+                    xa[q * SC::R0 + m] = valid ? in_at(k) : make_double2(0.0, 0.0);
+                    xb[q * SC::R0 + m] = valid ? in_at(k + MP) : make_double2(0.0, 0.0);
+                }
+        }
+#pragma unroll 1
+        for (int n2 = 0; n2 < 3; ++n2) {
+            // f = e^(4 pi i n2 / 3)
+            const double fr = (n2 == 0) ? 1.0 : -0.5;
+            const double fi = (n2 == 0) ? 0.0 : (n2 == 1 ? -0.86602540378443864676372317075294 : 0.86602540378443864676372317075294);
+            cplx v[SC::EMAX];
+            if (j < SC::NB0) {
+#pragma unroll
+                for (int q = 0; q < SC::B0; ++q)
+#pragma unroll
+                    for (int m = 0; m < SC::R0; ++m) {
+                        const int k = (j + q * P) + m * SC::NB0;
+                        const cplx a = xa[q * SC::R0 + m], b = xb[q * SC::R0 + m];
+                        cplx z;
+                        if (k == 0) {
+                            z = make_double2(fma(fr, b.x, a.x), fma(fr, b.y, a.y));
+                        } else {
+                            z = make_double2(a.x + fr * b.x - fi * b.y, a.y + fr * b.y + fi * b.x);
+                            if (n2 > 0) z = cmulc(z, __ldg(&d.tw2[n2 * k]));      // * e^(+2 pi i n2 k / M)
+                        }
+                        v[q * SC::R0 + m] = z;
                     }
-                    v[q * SC::R0 + m] = z;
-                }
-        }
-        fft_stages<SC, true, true>(v, j, s, CtaSync(), d.tw);
-        if (j < SC::NBL && valid) {
+            }
+            fft_stages<SC, true, true>(v, j, s, CtaSync(), d.tw);
+            if (j < SC::NBL && valid) {
 #pragma unroll
-            for (int q = 0; q < SC::BL; ++q)
+                for (int q = 0; q < SC::BL; ++q)
 #pragma unroll
-                for (int m = 0; m < SC::RL; ++m) {
-                    const int n1 = (j + q * P) + m * SC::NBL;
-                    out_at(3 * n1 + n2) = cscale(v[q * SC::RL + m], scale);
-                }
+                    for (int m = 0; m < SC::RL; ++m) {
+                        const int n1 = (j + q * P) + m * SC::NBL;
+                        out_at(3 * n1 + n2) = cscale(v[q * SC::RL + m], scale);
+                    }
+            }
+            __syncthreads();      // shared exchange buffer is reused by the next residue
         }
-        __syncthreads();      // shared exchange buffer is reused by the next residue
     }
 }
 
@@ -930,6 +961,43 @@ static int launch_pad3(FastDesc d, cudaStream_t st) {
     }
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
+}
+
+template <class SC, int T>
+static int launch_pad3_curl(FastDesc d, cudaStream_t st) {
+    constexpr size_t smem = (size_t)SC::M * T * sizeof(cplx);
+    d.tw = twiddle_table(0, SC::M);
+    d.tw2 = twiddle_table(0, 3 * SC::M);
+    if (!d.tw || !d.tw2) { set_error("fft: twiddle table allocation failed"); return SHB_ERR_NOMEM; }
+    static bool a0 = false;
+    if (!a0) { SHB_CUDA(cudaFuncSetAttribute(fft_strided_pad3x_kernel<SC, T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); a0 = true; }
+    const int64_t ntiles = (d.inner + T - 1) / T;
+    fft_strided_pad3x_kernel<SC, T, false, true><<<(unsigned)ntiles, SC::P * T, smem, st>>>(d);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
+// out[0..2] = padded backward of u_hat[0..2] along the leading axis, out[3..5] = the same of i k x u_hat
+// (3/2 rule, N -> n_fft = 3N/2; u_hat: [3][N][inner], out: [6][n_fft][inner], inner = n1 * n2)
+int fft_pad3_curl_launch(const void *u_hat, void *out, int64_t inner, int n2, int n_fft, int N, const double *k0,
+                         const double *k1, const double *k2, double scale, cudaStream_t st) {
+    if (N % 2 || 2 * n_fft != 3 * N || n2 < 1 || inner % n2) return SHB_ERR_UNSUPPORTED;
+    FastDesc d;
+    d.in_cr = d.out_cr = 0; d.use_peer = 0; d.in_cs = d.out_cs = 0;
+    for (int p = 0; p < 8; ++p) d.out_peer[p] = nullptr;
+    d.in = u_hat; d.out = out; d.outer = 6; d.inner = inner; d.nlines = 6 * inner;
+    d.n_fft = n_fft; d.N = N; d.n_in = N; d.n_out = n_fft; d.flags = 0; d.scale = scale;
+    d.cw = inner; d.cvalid = inner; d.c0 = 0; d.in_rs = inner; d.out_rs = inner;
+    d.in_as = (int64_t)N * inner; d.out_as = (int64_t)n_fft * inner;
+    d.k0 = k0; d.k1 = k1; d.k2 = k2; d.curl_n2 = n2;
+    if (inner == 0) return SHB_OK;
+    switch (N / 2) {
+    case 64:  return launch_pad3_curl<Sched<64, 8, 8, 1, 8>, 8>(d, st);
+    case 128: return launch_pad3_curl<Sched<128, 8, 4, 4, 32>, 8>(d, st);
+    case 256: return launch_pad3_curl<Sched<256, 8, 8, 4, 32>, 8>(d, st);
+    case 512: return launch_pad3_curl<Sched<512, 8, 8, 8, 64>, 8>(d, st);
+    default: return SHB_ERR_UNSUPPORTED;
+    }
 }
 
 static const bool g_no_pad3 = getenv("SHB_FFT_NO_PAD3") != nullptr;

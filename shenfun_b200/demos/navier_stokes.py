@@ -105,6 +105,10 @@ class FusedNS:
         self.t = 0.0
         self.tstep = 0
         self._curl_ready = False
+        # opt-in (SHB_NS_CURL_FUSION=1; one rank, 3/2 rule, N/2 in {64 .. 512}): i k x u_hat is formed inside the
+        # first padded pass and the vorticity spectrum is never stored.  Not faster on B200 (see
+        # TensorProductSpace.curl_fusion_available), so the default keeps the stored spectrum.
+        self._curl_fused = pad and hasattr(self.Tp, 'curl_fusion_available') and self.Tp.curl_fusion_available()
 
     def initialize(self):
         taylor_green(self.TV, self.U)
@@ -120,6 +124,12 @@ class FusedNS:
         U1.copy_(uh)
         k0, k1, k2 = self.K
         for rk in range(4):
+            if self._curl_fused:
+                self.Tp.backward_cross_hat(uh, self.Up, curl_of=(k0, k1, k2))
+                self.TVp.forward(self.Up, self.dU)
+                ops.ns_rk_stage(dU, uh, U0, U1, self.P_hat.v if self.pressure else None, k0, k1, k2, nu,
+                                self.a[rk]*dt, self.b[rk]*dt, rk == 3, keep_dU=False, curl_out=None)
+                continue
             if not self._curl_ready:
                 ops.curl_hat(uh, self.curl_hat.v, k0, k1, k2)
             # W = backward(U_hat) x backward(curl_hat): one batched backward over the six spectral

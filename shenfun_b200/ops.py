@@ -103,6 +103,13 @@ def fft_c2r_cross(uh, b, out, nlines, n_fft, N, scale=1.0, dealias_direct=False)
           nlines, n_fft, N, scale, int(dealias_direct) | (2 if spectral_b else 0), _lib.stream_ptr())
 
 
+def fft_c2c_backward_curl(u_hat, out, inner, n2, n_fft, N, k0, k1, k2, scale=1.0):
+    """out[0:3] = 3/2-rule padded backward C2C of u_hat (3, N, inner) along the leading axis, out[3:6] the
+    same of i k x u_hat formed on the fly (demo/NavierStokes.py:37-39); out: (6, n_fft, inner)."""
+    _call('shb_fft_c2c_backward_curl', _req(u_hat, C128, 'u_hat'), _req(out, C128, 'out'), inner, n2, n_fft, N,
+          _req(k0, F64, 'k0'), _req(k1, F64, 'k1'), _req(k2, F64, 'k2'), scale, _lib.stream_ptr())
+
+
 def fft_r2c_forward(u, out, outer, inner, n_fft, N, scale):
     _call('shb_fft_r2c_forward', _req(u, F64, 'in'), _req(out, C128, 'out'),
           outer, inner, n_fft, N, scale, _lib.stream_ptr())

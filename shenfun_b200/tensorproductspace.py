@@ -19,6 +19,7 @@ Differences in *how* (not what):
     :393-396): physical space sharded on axis (first-transformed+1) % ndim,
     spectral space on the axis transformed just before it.
 """
+import os
 import numpy as np
 import torch
 
@@ -703,19 +704,46 @@ class TensorProductSpace:
         ops.cross3d(tmp, bt, ot)
         return out
 
-    def backward_cross_hat(self, ab_hat, out):
+    def curl_fusion_available(self):
+        """True when `backward_cross_hat(u_hat, out, curl_of=K)` can form i k x u_hat inside the first padded
+        pass (`shb_fft_c2c_backward_curl`): one rank, Fourier^3 with 3/2-rule padding, the leading axis
+        transformed first and served by the residue-split padding kernel.  Opt-in (SHB_NS_CURL_FUSION=1):
+        measured on B200 at 512^3 it saves the 6.5 GB per stage of the stored vorticity spectrum but the
+        two-loads-per-element first pass gives the time back (122.8 vs 121.0 ms per step)."""
+        st = self.backward.steps
+        if self.comm.Get_size() != 1 or self.dimensions != 3 or len(st) != 3 or any(s.kind != 'axis' for s in st):
+            return False
+        s0, b0 = st[0], st[0].base
+        return (s0.axis == 0 and b0.family() == 'fourier' and b0.short_name() == 'C2C' and not b0.dealias_direct
+                and 2*b0.physical_len() == 3*b0.N and b0.N//2 in (64, 128, 256, 512)
+                and os.environ.get('SHB_NS_CURL_FUSION') == '1')
+
+    def backward_cross_hat(self, ab_hat, out, curl_of=None):
         """out = backward(a_hat) x backward(b_hat) with both spectral fields stacked in one
         (6,)+spectral array `ab_hat` = [a_hat; b_hat]: the earlier axis passes run once over the six
         components, the last pass transforms all six lines of a spatial line in one kernel and
         writes only the cross product (`shb_fft_c2r_cross`, spectral `b`).  Falls back to
-        `backward` + `backward_cross` when no fused kernel covers the size."""
+        `backward` + `backward_cross` when no fused kernel covers the size.
+
+        `curl_of=(k0, k1, k2)` (flat wavenumber tables; requires `curl_fusion_available()`): `ab_hat` is the
+        (3,)+spectral field a_hat alone and b_hat = i k x a_hat is formed inside the first pass."""
         from ._lib import ShenB200Error
         ab, ot = ops.as_device_tensor(ab_hat), ops.plain(out)
-        assert ab.shape[0] == 6 and ab.is_contiguous()
+        assert ab.shape[0] == (6 if curl_of is None else 3) and ab.is_contiguous()
         last = self.backward.steps[-1]
         base = last.base
         ok = (last.kind == 'axis' and base.family() == 'fourier' and base.short_name() == 'R2C'
               and last.axis == self.dimensions-1 and not getattr(self, '_no_cross_fusion', False))
+        overrides = None
+        if curl_of is not None:
+            assert ok and self.curl_fusion_available(), 'curl fusion is not available for this space'
+            b0 = self.backward.steps[0].base
+            k0, k1, k2 = curl_of
+
+            def first(cur, dst, outer, inner):
+                assert outer == 6 and inner % k2.numel() == 0
+                ops.fft_c2c_backward_curl(cur, dst, inner, k2.numel(), b0.physical_len(), b0.N, k0, k1, k2)
+            overrides = {0: first}
         if ok:
             def fused(cur, dst, outer, inner):
                 assert inner == 1 and outer % 6 == 0
@@ -723,14 +751,15 @@ class TensorProductSpace:
                 ops.fft_c2r_cross(half[0], half[1], dst, outer//6, base.physical_len(), base.N, 1.0,
                                   base.dealias_direct)
             try:
-                self.backward._run(ab, ot, 6, last_override=fused)
+                self.backward._run(ab, ot, 6, last_override=fused, overrides=overrides)
                 return out
             except ShenB200Error as e:
-                if 'fft_c2r_cross' not in str(e):
+                if 'fft_c2r_cross' not in str(e) or curl_of is not None:
                     raise
                 self._no_cross_fusion = True
             finally:
                 self.backward._last_override = None
+                self.backward._overrides = None
         bp = torch.empty_like(ot)
         self.backward._run(ab[3:], bp, 3)
         return self.backward_cross(ab[:3], bp, out)

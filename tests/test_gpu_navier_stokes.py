@@ -112,3 +112,44 @@ def test_backward_of_two_fields_fused_with_cross_product(N, pf):
     out = sf.Array(TVp)
     Tp.backward_cross_hat(ab, out)
     assert rel_l2(out.get(), ref) < TOL
+
+
+def test_curl_formed_inside_the_first_padded_pass():
+    """`shb_fft_c2c_backward_curl` (i k x u_hat formed on the fly in the first 3/2-rule pass, the vorticity
+    spectrum never stored): the kernel against numpy on random data, and two RK4 steps at 128^3 against
+    the step that stores the vorticity spectrum and against the numpy oracle of demo/NavierStokes.py."""
+    import os
+    from shenfun_b200 import ops
+    from oracle import fourier as of, navier_stokes as ons
+    rng = np.random.default_rng(11)
+    N, n1, n2 = 128, 5, 7
+    uh = rng.standard_normal((3, N, n1, n2))+1j*rng.standard_normal((3, N, n1, n2))
+    k0 = np.fft.fftfreq(N, 1./N)
+    k1 = rng.standard_normal(n1)
+    k2 = rng.standard_normal(n2)
+    K = np.meshgrid(k0, k1, k2, indexing='ij')
+    curl = 1j*np.array([K[1]*uh[2]-K[2]*uh[1], K[2]*uh[0]-K[0]*uh[2], K[0]*uh[1]-K[1]*uh[0]])
+    ref = of.c2c_backward(np.concatenate([uh, curl]), 1, 192)
+    out = torch.empty((6, 192, n1, n2), dtype=torch.complex128, device='cuda')
+    dv = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()       # noqa: E731
+    ops.fft_c2c_backward_curl(dv(uh), out, n1*n2, n2, 192, N, dv(k0), dv(k1), dv(k2))
+    assert rel_l2(out.cpu().numpy(), ref) < TOL
+
+    os.environ['SHB_NS_CURL_FUSION'] = '1'
+    try:
+        a = ns.FusedNS((128, 128, 128), dt=0.005, padding_factor=1.5).initialize()
+        assert a._curl_fused
+        for _ in range(2):
+            a.step()
+    finally:
+        del os.environ['SHB_NS_CURL_FUSION']
+    b = ns.FusedNS((128, 128, 128), dt=0.005, padding_factor=1.5).initialize()
+    assert not b._curl_fused
+    for _ in range(2):
+        b.step()
+    ua, ub = a.U_hat.get(), b.U_hat.get()
+    assert rel_l2(ua, ub) < 1e-13
+    o = ons.NavierStokes((128, 128, 128), nu=0.000625, dt=0.005, padding_factor=1.5).initialize()
+    for _ in range(2):
+        o.step()
+    assert rel_l2(ua, o.U_hat) < TOL
