@@ -333,7 +333,29 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         pcie[name+'_GBs_per_gpu_all_ranks_concurrent'] = h_in.numel()*8/tt.item()/1e6
-    del d_tmp
+    # both directions at once on two streams (what the pipeline asks of the link): bytes per direction / time
+    d_tmp2 = torch.empty_like(d_tmp)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    barrier()
+    cur_stream = torch.cuda.current_stream()
+    e0.record()
+    s_up.wait_stream(cur_stream)
+    s_dn.wait_stream(cur_stream)
+    for _ in range(5):
+        with torch.cuda.stream(s_up):
+            d_tmp.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_out.copy_(d_tmp2, non_blocking=True)
+    cur_stream.wait_stream(s_up)
+    cur_stream.wait_stream(s_dn)
+    e1.record()
+    barrier()
+    tt = torch.tensor([e0.elapsed_time(e1)/5], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    pcie['bidirectional_GBs_per_direction_per_gpu'] = h_in.numel()*8/tt.item()/1e6
+    pcie['e2e_frac_of_bidirectional_link'] = (h_in.numel()*8/(e2e_ms*1e6))/pcie['bidirectional_GBs_per_direction_per_gpu']
+    del d_tmp, d_tmp2
 
     # ---- roofline of the dominant kernel (live CUDA events around single launches) --
     peak, peak_src = peaks()
