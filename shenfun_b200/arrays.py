@@ -268,7 +268,9 @@ class Function(ShenfunBaseArray):
         mode is split over +-N/2 when padding, summed when truncating), spectralbase.py:1363-1390
         (polynomial bases; boundary dofs stay the last rows).  The reference's polynomial
         truncation indexes with the source size and raises; here the low modes are kept.
-        Single-rank only: the reference redistributes between axes, this drop-in does not."""
+        On a distributed space the reference redistributes between the axes (`DistArray.redistribute`);
+        here every rank gathers the spectral array, refines it and keeps its block of the refined
+        space -- refine is set-up / post-processing work, not part of a time step."""
         space = self.function_space()
         if space.is_composite_space:
             comps = [self[i].refine(N) for i in range(len(space.flatten()))]
@@ -283,12 +285,21 @@ class Function(ShenfunBaseArray):
             N = (int(N),)*nd
         if len(N) != nd:
             raise ValueError(f'N has {len(N)} entries, the space has {nd} axes')
-        if getattr(space.comm, 'Get_size', lambda: 1)() > 1:
-            raise NotImplementedError('Function.refine on a distributed space')
+        distributed = getattr(space.comm, 'Get_size', lambda: 1)() > 1
         cur, fresh = self.v, False
+        if distributed:
+            gshape, lshape = tuple(space.global_shape(True)), tuple(self.shape)
+            for ax in range(nd):
+                if gshape[ax] != lshape[ax]:
+                    cur, fresh = space.comm.allgather_blocks(cur, ax), True
         for ax, (base, n_new) in enumerate(zip(space.bases, N)):
             if int(n_new) != base.N:
                 cur, fresh = _refine_axis(base, cur, ax, int(n_new)), True
+        if distributed:
+            newspace = output_array.function_space() if output_array is not None else space.get_refined(N)
+            cur = cur[tuple(newspace.local_slice(True))].contiguous()
+            if output_array is None:
+                return Function(newspace, buffer=cur)
         if output_array is None:
             return Function(space.get_refined(N), buffer=cur if fresh else cur.clone())
         if tuple(output_array.shape) != tuple(cur.shape):

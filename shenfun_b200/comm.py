@@ -64,6 +64,26 @@ class Comm:
         dist.broadcast_object_list(lst, src=root, group=self._group)
         return lst[0]
 
+    def allgather_blocks(self, t, axis):
+        """Concatenate the ranks' blocks of a tensor along `axis` (uneven extents allowed); every rank
+        gets the whole array.  Host-side plumbing (refine, diagnostics), not a data-path collective."""
+        if not self._active() or self.Get_size() == 1:
+            return t
+        P = self.Get_size()
+        dev = self._device()
+        n = torch.tensor([t.shape[axis]], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(n) for _ in range(P)]
+        dist.all_gather(sizes, n, group=self._group)
+        sizes = [int(x.item()) for x in sizes]
+        m = max(sizes)
+        shp = list(t.shape)
+        shp[axis] = m
+        send = torch.zeros(shp, dtype=t.dtype, device=dev)
+        send.narrow(axis, 0, t.shape[axis]).copy_(t)
+        parts = [torch.empty_like(send) for _ in range(P)]
+        dist.all_gather(parts, send, group=self._group)
+        return torch.cat([p.narrow(axis, 0, k) for p, k in zip(parts, sizes)], dim=axis).to(t.device)
+
     def Dup(self):
         return self
 

@@ -103,11 +103,16 @@ def _worker(rank, world, port, results):
         if rank == 0:
             shutil.rmtree(base+'.chk', ignore_errors=True)
             shutil.rmtree(base+'.old.chk', ignore_errors=True)
-        try:
-            U.refine((12, 12, 12))
-            raise AssertionError('refine on a distributed space must raise')
-        except NotImplementedError:
-            pass
+        # refine on a distributed space: every rank ends with its block of the globally refined array
+        from shenfun_b200.arrays import _refine_axis
+        for Nn in ((16, 12, 12), (8, 6, 6)):
+            R = U.refine(Nn)
+            Tn = R.function_space()
+            gt = torch.from_numpy(G.copy())
+            for ax, (b, nn) in enumerate(zip(T.bases, Nn)):
+                gt = _refine_axis(b, gt, ax, nn)
+            assert tuple(gt.shape) == tuple(Tn.global_shape(True))
+            assert np.array_equal(R.get(), gt.numpy()[Tn.local_slice(True)])
         # reductions through the communicator facade
         assert comm.allreduce(float(rank+1)) == 3.0
         assert comm.bcast({'a': rank}, root=0) == {'a': 0}
