@@ -367,6 +367,9 @@ SHB_API int shb_gemm_axis(const double *d_A, const void *d_u, void *d_out, int M
  *   forward == 0: A[M-1-i][k] = (-1)^k A[i][k] (M even; coefficients -> values).
  * d_A2 = the two half operators [2][Mh][Kp], Kp even and zero padded: forward: A2[p][i][j] = A[2i+p][j]
  * (Mh = ceil(M/2), j < K/2); backward: A2[p][i][k] = A[i][2k+p] (Mh = M/2, k < ceil(K/2)).
+ * `forward` bits 0-1 = 2: checkerboard operator (A[i][j] = 0 for i + j odd, e.g. the Legendre <-> Chebyshev connection
+ * matrices, shenfun/legendre/dlt.py:353-474): A2[p][i][k] = A[2i+p][2k+p] (Mh = ceil(M/2), k < ceil(K/2)); bit 2 / bit 3:
+ * the halves are upper / lower triangular and their zero k-tiles are skipped.
  * Returns SHB_ERR_UNSUPPORTED for layouts it does not cover (inner*(complex?2:1) odd or 1, unaligned
  * pointers): call shb_gemm_axis then. */
 SHB_API int shb_gemm_axis_parity(const double *d_A2, const void *d_u, void *d_out, int M, int K, int Kp, int forward,

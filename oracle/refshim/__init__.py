@@ -32,6 +32,15 @@ def activate(reference='/root/reference'):
     stub = types.ModuleType('shenfun.optimization.cython')
     stub.Leg2Cheb = _Unavailable
     stub.Cheb2Leg = _Unavailable
+    try:
+        # Gamma(z+1/2)/Gamma(z+1) from the reference's own compiled transforms.pyx when oracle/_ref has it,
+        # else the closed form the reference keeps as a comment (legendre/dlt.py:344)
+        from oracle import refcy
+        stub.Lambda = refcy.load('transforms').Lambda
+    except Exception:  # noqa: BLE001
+        import numpy as _np
+        from scipy.special import gammaln as _gl
+        stub.Lambda = lambda z: _np.exp(_gl(_np.asarray(z, dtype=float)+0.5)-_gl(_np.asarray(z, dtype=float)+1))
     sys.modules['shenfun.optimization.cython'] = stub
     import numpy as np
     if not hasattr(np, 'asscalar'):

@@ -18,6 +18,8 @@ from .integrators import RK4, IntegratorBase, PDEIMEXRK, IMEXRK011, IMEXRK111, I
 from .utilities import cross, apply_mask, dx
 from . import la, chebyshev, legendre
 from .io import Checkpoint
+from . import dlt
+legendre.dlt = dlt          # shenfun.legendre.dlt: Leg2Cheb / Cheb2Leg / DLT
 from .polybase import BoundaryConditions
 from ._lib import ShenB200Error
 

@@ -246,11 +246,16 @@ struct ParityDesc {
     const double *X;
     double *C;
     int M, K, Mh, Kh, Kp;
+    int tri;               // MODE 2: +1 upper triangular halves (A2[p][i][k] = 0 for k < i), -1 lower, 0 full
     int64_t W, xs_batch, xs_k, cs_batch, cs_m;
 };
 
-template <bool FWD>
+// MODE 0: row-mirror structure (coefficients -> values), 1: column-mirror structure (values -> coefficients),
+// 2: checkerboard operator (A[i][j] = 0 for i + j odd: the Legendre <-> Chebyshev connection matrices): even rows
+//    act on even columns, odd rows on odd columns, no butterflies; triangular halves skip their zero k-tiles.
+template <int MODE>
 __global__ void __launch_bounds__(GM_THREADS, 2) gemm_axis_parity_kernel(const __grid_constant__ ParityDesc d) {
+    constexpr bool FWD = (MODE == 1);
     extern __shared__ __align__(16) unsigned char gm_smem[];
     double *sA = reinterpret_cast<double *>(gm_smem);                           // [stage][set][BM][AS]
     double *sX = sA + (size_t)GP_STAGES * 2 * GP_BM * GP_AS;                    // [stage][set][BK][XS]
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemm_axis_parity_kernel(const _
             const int set = e / (GP_BK * GP_BN / 2), e2 = e % (GP_BK * GP_BN / 2);
             const int ww = (e2 % (GP_BN / 2)) * 2, kk = e2 / (GP_BN / 2);
             const int gk = k0 + kk;
-            const int row = FWD ? (set == 0 ? gk : d.K - 1 - gk) : 2 * gk + set;
+            const int row = FWD ? (set == 0 ? gk : d.K - 1 - gk) : 2 * gk + set;      // MODE 0 and 2: even / odd rows
             const int64_t gw = w0 + ww;
             const bool ok = (gk < d.Kh && row < d.K && gw < d.W);
             cp_async16g(&x[(set * GP_BK + kk) * GP_XS + ww], ok ? &X[(int64_t)row * d.xs_k + gw] : X, ok);
@@ -297,17 +302,19 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemm_axis_parity_kernel(const _
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    const int nk = (d.Kh + GP_BK - 1) / GP_BK;
+    int nk = (d.Kh + GP_BK - 1) / GP_BK, kbeg = 0;
+    if (MODE == 2 && d.tri > 0) kbeg = m0 / GP_BK;                                     // zero tiles left of the diagonal
+    if (MODE == 2 && d.tri < 0) { const int e = (m0 + GP_BM + GP_BK - 1) / GP_BK; nk = e < nk ? e : nk; }
 #pragma unroll
     for (int p = 0; p < GP_STAGES - 1; ++p) {
-        if (p < nk) load_tiles(p, p * GP_BK);
+        if (kbeg + p < nk) load_tiles(p, (kbeg + p) * GP_BK);
         else asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (int kt = 0; kt < nk; ++kt) {
-        const int buf = kt % GP_STAGES;
+    for (int kt = kbeg; kt < nk; ++kt) {
+        const int buf = (kt - kbeg) % GP_STAGES;
         asm volatile("cp.async.wait_group %0;" ::"n"(GP_STAGES - 2) : "memory");
         __syncthreads();
-        if (kt + GP_STAGES - 1 < nk) load_tiles((kt + GP_STAGES - 1) % GP_STAGES, (kt + GP_STAGES - 1) * GP_BK);
+        if (kt + GP_STAGES - 1 < nk) load_tiles((kt - kbeg + GP_STAGES - 1) % GP_STAGES, (kt + GP_STAGES - 1) * GP_BK);
         else asm volatile("cp.async.commit_group;" ::: "memory");
         const double *a = sA + (size_t)buf * 2 * GP_BM * GP_AS;
         const double *x0 = sX + (size_t)buf * 2 * GP_BK * GP_XS;
@@ -343,9 +350,10 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemm_axis_parity_kernel(const _
             const int64_t gw = w0 + wn * 32 + j * 8 + t * 2;
             const double e0 = acc[0][j][2 * h], e1 = acc[0][j][2 * h + 1];
             const double o0 = acc[1][j][2 * h], o1 = acc[1][j][2 * h + 1];
-            const int ra = FWD ? 2 * i : i, rb = FWD ? 2 * i + 1 : d.M - 1 - i;
-            const double a0 = FWD ? e0 : e0 + o0, a1 = FWD ? e1 : e1 + o1;
-            const double b0 = FWD ? o0 : e0 - o0, b1 = FWD ? o1 : e1 - o1;
+            constexpr bool SPLIT = (MODE != 0);      // outputs are the even / odd rows themselves
+            const int ra = SPLIT ? 2 * i : i, rb = SPLIT ? 2 * i + 1 : d.M - 1 - i;
+            const double a0 = SPLIT ? e0 : e0 + o0, a1 = SPLIT ? e1 : e1 + o1;
+            const double b0 = SPLIT ? o0 : e0 - o0, b1 = SPLIT ? o1 : e1 - o1;
             if (c16 && gw + 1 < d.W) {
                 if (ra < d.M) *reinterpret_cast<double2 *>(&C[(int64_t)ra * d.cs_m + gw]) = make_double2(a0, a1);
                 if (rb < d.M) *reinterpret_cast<double2 *>(&C[(int64_t)rb * d.cs_m + gw]) = make_double2(b0, b1);
@@ -400,25 +408,30 @@ int shb_gemm_axis(const double *d_A, const void *d_u, void *d_out, int M, int K,
  * > 1 and even, 16-byte aligned arrays; SHB_ERR_UNSUPPORTED otherwise (use shb_gemm_axis). */
 int shb_gemm_axis_parity(const double *d_A2, const void *d_u, void *d_out, int M, int K, int Kp, int forward,
                          int64_t outer, int64_t inner, int is_complex, void *stream) {
+    const int mode = forward & 3, tri = (forward & 4) ? 1 : ((forward & 8) ? -1 : 0);
+    forward = (mode == 1);
     SHB_REQUIRE(d_A2 && d_u && d_out && M >= 1 && K >= 1 && Kp >= 2 && Kp % 2 == 0 && outer >= 0 && inner >= 0, "bad arguments");
     if (d_u == d_out) { set_error("gemm_axis_parity: in-place is not supported"); return SHB_ERR_ARG; }
     if (outer * inner == 0) return SHB_OK;
     const int64_t W = inner * (is_complex ? 2 : 1);
-    if (W < 2 || W % 2 || outer > 65535 || (forward ? K % 2 : M % 2) ||
+    if (W < 2 || W % 2 || outer > 65535 || (mode == 1 && K % 2) || (mode == 0 && M % 2) || mode == 3 ||
         ((reinterpret_cast<uintptr_t>(d_A2) | reinterpret_cast<uintptr_t>(d_u) | reinterpret_cast<uintptr_t>(d_out)) & 15))
         return SHB_ERR_UNSUPPORTED;
     ParityDesc d;
     d.A2 = d_A2; d.X = (const double *)d_u; d.C = (double *)d_out; d.M = M; d.K = K; d.Kp = Kp;
-    d.Mh = forward ? (M + 1) / 2 : M / 2;
-    d.Kh = forward ? K / 2 : (K + 1) / 2;
+    d.Mh = mode == 0 ? M / 2 : (M + 1) / 2;
+    d.Kh = mode == 1 ? K / 2 : (K + 1) / 2;
+    d.tri = mode == 2 ? tri : 0;
     if (d.Kh > Kp) { set_error("gemm_axis_parity: operator pitch %d < %d", Kp, d.Kh); return SHB_ERR_ARG; }
     d.W = W; d.xs_batch = (int64_t)K * W; d.xs_k = W; d.cs_batch = (int64_t)M * W; d.cs_m = W;
-    SHB_CUDA(cudaFuncSetAttribute(gemm_axis_parity_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM));
-    SHB_CUDA(cudaFuncSetAttribute(gemm_axis_parity_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM));
+    SHB_CUDA(cudaFuncSetAttribute(gemm_axis_parity_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM));
+    SHB_CUDA(cudaFuncSetAttribute(gemm_axis_parity_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM));
+    SHB_CUDA(cudaFuncSetAttribute(gemm_axis_parity_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM));
     dim3 grid((unsigned)((W + GP_BN - 1) / GP_BN), (unsigned)((d.Mh + GP_BM - 1) / GP_BM), (unsigned)outer);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (forward) gemm_axis_parity_kernel<true><<<grid, GM_THREADS, GP_SMEM, st>>>(d);
-    else gemm_axis_parity_kernel<false><<<grid, GM_THREADS, GP_SMEM, st>>>(d);
+    if (mode == 1) gemm_axis_parity_kernel<1><<<grid, GM_THREADS, GP_SMEM, st>>>(d);
+    else if (mode == 2) gemm_axis_parity_kernel<2><<<grid, GM_THREADS, GP_SMEM, st>>>(d);
+    else gemm_axis_parity_kernel<0><<<grid, GM_THREADS, GP_SMEM, st>>>(d);
     SHB_CUDA(cudaGetLastError());
     return SHB_OK;
 }

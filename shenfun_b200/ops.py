@@ -330,6 +330,18 @@ def _parity_halves(A):
         h[0, :, :Kh] = sym[:, 0::2]
         h[1, :, :K//2] = sym[:, 1::2]
         return as_device_tensor(h), 0, Kp
+    if M >= 4 and K >= 4 and not a[0::2, 1::2].any() and not a[1::2, 0::2].any():  # checkerboard (i + j odd: zero)
+        Mh, Kh = (M+1)//2, (K+1)//2
+        Kp = Kh+Kh % 2
+        h = np.zeros((2, Mh, Kp))
+        h[0, :, :Kh] = a[0::2, 0::2]
+        h[1, :M//2, :K//2] = a[1::2, 1::2]
+        flag = 2
+        if not np.tril(h[0], -1).any() and not np.tril(h[1], -1).any():
+            flag |= 4
+        elif not np.triu(h[0], 1).any() and not np.triu(h[1], 1).any():
+            flag |= 8
+        return as_device_tensor(h), flag, Kp
     return None
 
 

@@ -312,6 +312,37 @@ def refine_assign():
     save('refine', **out)
 
 
+def legendre_chebyshev_conversion():
+    """legendre/dlt.py: leg2cheb (:353-421, also transposed), cheb2leg (:423-474) along each axis of real
+    and complex arrays, even and odd lengths; DLT backward / forward / scalar product values through the
+    Legendre space (the reference's default kinds; the FFT-based DLT agrees with them to rounding)."""
+    from shenfun.legendre import dlt
+    out = {}
+    for N in (16, 33):
+        for axis in (0, 1):
+            shape = [5, 6]
+            shape[axis] = N
+            x = rng.standard_normal(shape)+1j*rng.standard_normal(shape)
+            out[f'x_{N}_{axis}'] = x
+            out[f'l2c_{N}_{axis}'] = dlt.leg2cheb(x.copy(), axis=axis)
+            out[f'l2cT_{N}_{axis}'] = dlt.leg2cheb(x.copy(), axis=axis, transpose=True)
+            out[f'c2l_{N}_{axis}'] = dlt.cheb2leg(x.copy(), axis=axis)
+        xr = rng.standard_normal((N, 4))
+        out[f'xr_{N}'] = xr
+        out[f'l2c_r_{N}'] = dlt.leg2cheb(xr.copy(), axis=0)
+        out[f'c2l_r_{N}'] = dlt.cheb2leg(xr.copy(), axis=0)
+        L = sf.FunctionSpace(N, 'L')
+        uh = sf.Function(L)
+        uh[:] = rng.standard_normal(N)
+        out[f'dlt_uh_{N}'] = np.array(uh)
+        ub = np.array(L.backward(uh.copy()))
+        out[f'dlt_bwd_{N}'] = ub
+        ua = sf.Array(L)
+        ua[:] = ub
+        out[f'dlt_sp_{N}'] = np.array(L.scalar_product(ua, sf.Function(L)))
+    save('dlt', **out)
+
+
 def solvers():
     """la.TDMA/PDMA/... along axes; SolverGeneric1ND Poisson / biharmonic; Chebyshev Helmholtz."""
     from shenfun import la, inner, div, grad, TestFunction, TrialFunction, Dx
