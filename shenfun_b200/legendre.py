@@ -47,12 +47,43 @@ def leggauss(N):
     return np.asarray(x, dtype=float), np.asarray(w, dtype=float)
 
 
+def leglobatto(N):
+    """Legendre-Gauss-Lobatto nodes (ascending, -1 and 1 included) and weights 2 / (N (N-1) L_{N-1}(x)^2):
+    the interior nodes are the roots of L_{N-1}', by Newton iteration in extended precision (the reference
+    iterates the same function in double precision, legendre/lobatto.py:7-46)."""
+    ld = np.longdouble
+    n = N-1
+    j = np.arange(N, dtype=ld)
+    x = -np.cos(ld(np.pi)*j/n)                       # Chebyshev-Lobatto start
+
+    def pn(x):
+        p0, p1 = np.ones_like(x), x.copy()
+        for m in range(2, n+1):
+            p0, p1 = p1, ((2*m-1)*x*p1-(m-1)*p0)/m
+        return p0, p1                                 # L_{n-1}, L_n
+
+    xi = x[1:-1]
+    for _ in range(100):
+        p0, p1 = pn(xi)
+        d1 = n*(xi*p1-p0)/(xi*xi-1)                   # L_n'
+        d2 = (2*xi*d1-n*(n+1)*p1)/(1-xi*xi)           # L_n'' from the Legendre equation
+        dx = d1/d2
+        xi = xi-dx
+        if np.abs(dx).max() < 1e-19:
+            break
+    x[1:-1] = xi
+    x = (x-x[::-1])/2
+    w = 2/(N*n*pn(x)[1]**2)
+    w = (w+w[::-1])/2
+    return np.asarray(x, dtype=float), np.asarray(w, dtype=float)
+
+
 class Orthogonal(PolyBase):
     def __init__(self, N, quad='LG', padding_factor=1, domain=(-1., 1.), dtype=float, dealias_direct=False,
                  bc=None, scaled=False, **kw):
         quad = 'LG' if quad is None else quad
-        if quad != 'LG':
-            raise NotImplementedError("Legendre quad='LG' only on the device path")
+        if quad not in ('LG', 'GL'):
+            raise NotImplementedError("Legendre quadrature: 'LG' (Gauss) or 'GL' (Gauss-Lobatto)")
         PolyBase.__init__(self, N, quad, padding_factor=padding_factor, domain=domain, dtype=dtype,
                           dealias_direct=dealias_direct, bc=bc, scaled=scaled)
 
@@ -74,7 +105,7 @@ class Orthogonal(PolyBase):
             N = self.physical_len()
         key = ('pw', N)
         if key not in self._tables:
-            self._tables[key] = leggauss(N)
+            self._tables[key] = leggauss(N) if self.quad == 'LG' else leglobatto(N)
         x, w = self._tables[key]
         if map_true_domain:
             x = self.map_true_domain(x)
@@ -86,6 +117,14 @@ class Orthogonal(PolyBase):
     def ortho_norm_sq(self, N=None):
         N = self.N if N is None else N
         return 2.0/(2*np.arange(N)+1.0)
+
+    def _gl_norm(self, G):
+        """Gauss-Lobatto points integrate L_{N-1}^2 to 2/(N-1), not 2/(2N-1); the reference puts that
+        discrete norm into its mass matrices (legendre/bases.py:157-164 `l2_norm_sq`)."""
+        if self.quad == 'GL' and self.N > 1:
+            G = G.copy()
+            G[self.N-1, self.N-1] = np.longdouble(2)/(self.N-1)
+        return G
 
     def ortho_deriv_matrix(self, N, k):
         """L_j' = sum_{i<j, i+j odd} (2i+1) L_i."""
@@ -107,6 +146,8 @@ class Orthogonal(PolyBase):
         par = (np.arange(N)[:, None]+np.arange(N)[None, :]) % 2
         if d_trial == 0:
             G = np.diag(ld(2)/(2*np.arange(N, dtype=ld)+1))
+            if d_test == 0 and N == self.N:
+                G = self._gl_norm(G)
         elif d_trial == 1:
             G = np.where((j > i) & (par == 1), ld(2), ld(0))
         elif d_trial == 2:

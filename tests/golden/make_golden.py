@@ -216,6 +216,40 @@ def poly_1d_gl():
     save('poly1d_CGL', **out)
 
 
+def poly_1d_lgl():
+    """Legendre bases on the Gauss-Lobatto points (quad='GL', legendre/bases.py:128-129, 157-164):
+    scalar product, forward, backward, plain and padded, mass matrix."""
+    out = {}
+    for name, bc in BCS.items():
+        for N in (16, 15):
+            S = sf.FunctionSpace(N, 'L', bc=bc, quad='GL') if bc is not None else sf.FunctionSpace(N, 'L', quad='GL')
+            tag = f'{name}_{N}'
+            u = rng.standard_normal(N)
+            out[f'u_{tag}'] = u
+            out[f'x_{tag}'] = S.points_and_weights()[0]
+            out[f'wq_{tag}'] = S.points_and_weights()[1]
+            out[f'sp_{tag}'] = np.array(S.scalar_product(u.copy()))
+            uh = np.array(S.forward(u.copy()))
+            out[f'fw_{tag}'] = uh
+            vh = np.zeros(N)
+            vh[:S.dim()] = rng.standard_normal(S.dim())
+            if name == 'inhom':
+                vh[S.dim():] = uh[S.dim():]
+            out[f'vh_{tag}'] = vh
+            out[f'bw_{tag}'] = np.array(S.backward(vh.copy()))
+            Sp = S.get_dealiased(1.5)
+            out[f'bwpad_{tag}'] = np.array(Sp.backward(vh.copy()))
+            w = rng.standard_normal(Sp.shape(False))
+            out[f'w_{tag}'] = w
+            out[f'fwpad_{tag}'] = np.array(Sp.forward(w.copy()))
+            if N == 16:
+                try:
+                    out[f'M00_{tag}'] = sf.SpectralMatrix((S, 0), (S, 0)).diags().toarray()
+                except Exception as e:  # noqa: BLE001
+                    print('skip matrix LGL', name, repr(e)[:80])
+    save('poly1d_LGL', **out)
+
+
 def poly_3d():
     """Chebyshev/Legendre x Fourier^2 tensor spaces, two axis orders, plain and 3/2-padded."""
     out = {}

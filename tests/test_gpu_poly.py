@@ -19,10 +19,12 @@ def _space1d(N, fam, bc):
     """'CGL' = Chebyshev on the Gauss-Lobatto points (quad='GL')."""
     if fam == 'CGL':
         return sf.FunctionSpace(N, 'C', bc=bc, quad='GL')
+    if fam == 'LGL':      # Legendre on the Gauss-Lobatto points (legendre/bases.py:128-129, 157-164)
+        return sf.FunctionSpace(N, 'L', bc=bc, quad='GL')
     return sf.FunctionSpace(N, fam, bc=bc)
 
 
-@pytest.mark.parametrize('fam', ['C', 'L', 'CGL'])
+@pytest.mark.parametrize('fam', ['C', 'L', 'CGL', 'LGL'])
 @pytest.mark.parametrize('name', NAMES)
 @pytest.mark.parametrize('N', [16, 15])
 def test_1d_transforms_golden(fam, name, N):
@@ -40,7 +42,7 @@ def test_1d_transforms_golden(fam, name, N):
     assert rel_l2(Sp.forward(g[f'w_{tag}']).cpu().numpy(), g[f'fwpad_{tag}']) < TOL
 
 
-@pytest.mark.parametrize('fam', ['C', 'L', 'CGL'])
+@pytest.mark.parametrize('fam', ['C', 'L', 'CGL', 'LGL'])
 @pytest.mark.parametrize('N', [16, 15])
 def test_1d_inhomogeneous_dirichlet(fam, N):
     g = load_golden('poly1d_'+fam)
