@@ -9,7 +9,7 @@ def FunctionSpace(N, family='Fourier', bc=None, dtype='d', quad=None, domain=Non
     """Return a 1-D function space.
 
     Same arguments as the reference factory.  Families on the device path:
-    Fourier ('F'), Chebyshev ('C'), Legendre ('L').
+    Fourier ('F'), Chebyshev ('C'), Legendre ('L'), orthogonal Jacobi ('J', alpha=, beta=).
     """
     fam = family.lower()
     par = dict(padding_factor=padding_factor, dealias_direct=dealias_direct)
@@ -27,4 +27,9 @@ def FunctionSpace(N, family='Fourier', bc=None, dtype='d', quad=None, domain=Non
         from . import legendre
         return legendre.make_space(N, bc=bc, quad=quad, domain=domain, dtype=dtype, scaled=scaled,
                                    basis=basis, **par)
+    if fam in ('jacobi', 'j'):
+        from . import jacobi
+        if domain is not None:
+            par['domain'] = tuple(float(d) for d in domain)
+        return jacobi.Orthogonal(N, quad=quad, alpha=kw.get('alpha', 0), beta=kw.get('beta', 0), bc=bc, dtype=dtype, **par)
     raise NotImplementedError(f'family {family!r} is outside the device hot path')

@@ -250,6 +250,31 @@ def poly_1d_lgl():
     save('poly1d_LGL', **out)
 
 
+def jacobi_1d():
+    """Orthogonal Jacobi spaces (jacobi/bases.py:150-260, quad='JG'): points, weights, norms, scalar product,
+    forward, backward, plain and padded."""
+    out = {}
+    for (al, be) in ((0, 0), (1, 1), (0.5, 0.5), (2, 1), (0, 1.5)):
+        for N in (16, 15):
+            S = sf.FunctionSpace(N, 'J', alpha=al, beta=be)
+            tag = f'{al}_{be}_{N}'
+            u = rng.standard_normal(N)
+            out[f'u_{tag}'] = u
+            out[f'x_{tag}'], out[f'wq_{tag}'] = S.points_and_weights()
+            out[f'h_{tag}'] = np.array([float(S.L2_norm_sq(i)) for i in range(N)])
+            out[f'sp_{tag}'] = np.array(S.scalar_product(u.copy()))
+            out[f'fw_{tag}'] = np.array(S.forward(u.copy()))
+            vh = rng.standard_normal(N)
+            out[f'vh_{tag}'] = vh
+            out[f'bw_{tag}'] = np.array(S.backward(vh.copy()))
+            Sp = S.get_dealiased(1.5)
+            out[f'bwpad_{tag}'] = np.array(Sp.backward(vh.copy()))
+            w = rng.standard_normal(Sp.shape(False))
+            out[f'w_{tag}'] = w
+            out[f'fwpad_{tag}'] = np.array(Sp.forward(w.copy()))
+    save('jacobi1d', **out)
+
+
 def poly_3d():
     """Chebyshev/Legendre x Fourier^2 tensor spaces, two axis orders, plain and 3/2-padded."""
     out = {}
