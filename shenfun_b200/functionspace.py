@@ -9,7 +9,8 @@ def FunctionSpace(N, family='Fourier', bc=None, dtype='d', quad=None, domain=Non
     """Return a 1-D function space.
 
     Same arguments as the reference factory.  Families on the device path:
-    Fourier ('F'), Chebyshev ('C'), Legendre ('L'), orthogonal Jacobi ('J', alpha=, beta=).
+    Fourier ('F'), Chebyshev ('C'), Legendre ('L'), orthogonal Jacobi ('J', alpha=, beta=) and Chebyshev of the
+    second kind ('U').
     """
     fam = family.lower()
     par = dict(padding_factor=padding_factor, dealias_direct=dealias_direct)
@@ -27,6 +28,11 @@ def FunctionSpace(N, family='Fourier', bc=None, dtype='d', quad=None, domain=Non
         from . import legendre
         return legendre.make_space(N, bc=bc, quad=quad, domain=domain, dtype=dtype, scaled=scaled,
                                    basis=basis, **par)
+    if fam in ('chebyshevu', 'u'):
+        from . import chebyshevu
+        if domain is not None:
+            par['domain'] = tuple(float(d) for d in domain)
+        return chebyshevu.Orthogonal(N, quad=quad, bc=bc, dtype=dtype, **par)
     if fam in ('jacobi', 'j'):
         from . import jacobi
         if domain is not None:

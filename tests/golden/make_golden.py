@@ -275,6 +275,26 @@ def jacobi_1d():
     save('jacobi1d', **out)
 
 
+def chebyshevu_1d():
+    """Orthogonal Chebyshev spaces of the second kind (chebyshevu/bases.py:60-190), quad 'GU' and 'GC'."""
+    out = {}
+    for quad in ('GU', 'GC'):
+        for N in (16, 15):
+            S = sf.FunctionSpace(N, 'U', quad=quad)
+            tag = f'{quad}_{N}'
+            u = rng.standard_normal(N)
+            out[f'u_{tag}'] = u
+            out[f'x_{tag}'], out[f'wq_{tag}'] = S.points_and_weights()
+            out[f'sp_{tag}'] = np.array(S.scalar_product(u.copy()))
+            out[f'fw_{tag}'] = np.array(S.forward(u.copy()))
+            vh = rng.standard_normal(N)
+            out[f'vh_{tag}'] = vh
+            out[f'bw_{tag}'] = np.array(S.backward(vh.copy()))
+            # (the reference's padded transforms of this family fail: chebyshevu/bases.py:252 scales the padded
+            # output with a factor of the un-padded length)
+    save('chebyshevu1d', **out)
+
+
 def poly_3d():
     """Chebyshev/Legendre x Fourier^2 tensor spaces, two axis orders, plain and 3/2-padded."""
     out = {}
