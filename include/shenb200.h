@@ -213,7 +213,9 @@ SHB_API int shb_rk4_stage_cplx(void *d_dU, void *d_u_hat, const void *d_U0, void
  * device pointers, coefs: HOST array; mask real [n_mask], applied per entry modulo n_mask, may be NULL);
  * up to two terms are also copied out unchanged (d_save_dst[k] = T_{save_idx[k]}).  One pass for the
  * right-hand side of an IMEX Runge-Kutta stage, rhs = (u0, v) + dt sum_j b_j N_j + dt sum_j a_j L_j with
- * the newest N and L kept for the later stages (shenfun/utilities/integrators.py:692-696, 803-812).  */
+ * the newest N and L kept for the later stages (shenfun/utilities/integrators.py:692-696, 803-812).
+ * is_complex bit 1 (complex data, no save slots): the result is also multiplied by i -- with a wavenumber
+ * mask this is a Fourier derivative of odd order.  */
 SHB_API int shb_lincomb(void *d_out, int nterms, const void *const *d_terms, const double *coefs,
                         const double *d_mask, int64_t n_mask, int64_t n, int is_complex, int nsave,
                         const int *save_idx, void *const *d_save_dst, void *stream);

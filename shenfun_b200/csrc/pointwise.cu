@@ -193,6 +193,7 @@ struct LinComb {
     const double *mask;       // [n_mask] or NULL
     int64_t n_mask;
     int cplx_shift;           // 1: two doubles per mask entry
+    int times_i;              // complex data: multiply the result by i (Fourier derivatives of odd order)
     double *save_dst[2];
     int save_idx[2];
     int nsave;
@@ -200,16 +201,19 @@ struct LinComb {
 __global__ void __launch_bounds__(PW_THREADS) lincomb_kernel(double *__restrict__ out, const LinComb p, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double acc = 0.0;
+        // times i: (x + i y) i = -y + i x, i.e. double 2e takes -(double 2e+1), double 2e+1 takes double 2e
+        const int64_t is = p.times_i ? (i ^ 1) : i;
 #pragma unroll
         for (int j = 0; j < LC_MAXT; ++j) {
             if (j < p.nterms) {
-                const double v = p.t[j][i];
+                const double v = p.t[j][is];
                 acc = fma(p.c[j], v, acc);
                 if (p.nsave > 0 && p.save_idx[0] == j) p.save_dst[0][i] = v;
                 if (p.nsave > 1 && p.save_idx[1] == j) p.save_dst[1][i] = v;
             }
         }
         if (p.mask) acc *= p.mask[(i >> p.cplx_shift) % p.n_mask];
+        if (p.times_i && !(i & 1)) acc = -acc;
         out[i] = acc;
     }
 }
@@ -328,6 +332,8 @@ int shb_lincomb(void *d_out, int nterms, const void *const *d_terms, const doubl
         SHB_REQUIRE(j >= nterms || p.t[j], "null term");
     }
     p.mask = d_mask; p.n_mask = d_mask ? n_mask : 1; p.cplx_shift = is_complex ? 1 : 0;
+    p.times_i = (is_complex & 2) ? 1 : 0;
+    SHB_REQUIRE(!p.times_i || ((is_complex & 1) && nsave == 0), "times-i needs complex data and no save slots");
     p.nsave = nsave;
     for (int k = 0; k < 2; ++k) {
         p.save_idx[k] = k < nsave ? save_idx[k] : -1;

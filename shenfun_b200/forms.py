@@ -279,15 +279,79 @@ class Inner:
 
 class Project:
     """Cached projection of an expression onto T (forms/project.py:172-272): right hand side
-    through `Inner`, then the mass matrix of T (banded solve along the non-periodic axis)."""
+    through `Inner`, then the mass matrix of T (banded solve along the non-periodic axis).
+
+    A single term `s * d^d u / dx^d` of a known Function u that lives in T itself, differentiated along
+    periodic axes only, needs neither: (v, D u) = (B (x) D_F) u and the projection applies B^-1, so the
+    result is the spectral array of u times the Fourier factors -- one point-wise pass instead of a
+    banded mat-vec and a banded solve (six of the nine velocity gradients of demo/ChannelFlow.py:69-77).
+    SHB_PROJECT_SHORTCUT=0 keeps the generic path."""
 
     def __init__(self, uh, T, output_array=None):
         self.T = T
-        self.rhs = Inner(TestFunction(T), uh)
         self.output_array = Function(T) if output_array is None else output_array
+        self._short = self._fourier_shortcut(uh, T)
+        self.rhs = Inner(TestFunction(T), uh) if self._short is None else None
+
+    @staticmethod
+    def _fourier_shortcut(uh, T):
+        import os
+        if os.environ.get('SHB_PROJECT_SHORTCUT', '1') == '0' or T.is_composite_space:
+            return None
+        e = as_expr(uh)
+        if len(e.terms) != 1 or len(e.terms[0]) != 1:
+            return None
+        s, c, d, r = e.terms[0][0]
+        if not isinstance(r, Function):
+            return None
+        usp = _scalar_space(r.function_space(), c)
+        if len(usp.bases) != len(T.bases):
+            return None
+        for ax, (tb, ub) in enumerate(zip(T.bases, usp.bases)):
+            if type(tb) is not type(ub) or hash(tb) != hash(ub):
+                return None
+            if tb.family() != 'fourier' and d[ax] != 0:
+                return None
+        sl = T.local_slice(True)
+        nd = len(T.bases)
+        arr = None
+        for ax, tb in enumerate(T.bases):
+            if tb.family() != 'fourier' or d[ax] == 0:
+                continue
+            num = np.asarray(tb.spectral_matrix(0, d[ax], tb).scaled_diagonal(0))
+            den = np.asarray(tb.spectral_matrix(0, 0, tb).scaled_diagonal(0))
+            if num.shape != den.shape or not np.all(den != 0):
+                return None
+            f = num/den
+            if f.shape[0] != tb.spectral_len():
+                return None
+            shape = [1]*nd
+            shape[ax] = sl[ax].stop-sl[ax].start
+            part = f[sl[ax]].reshape(shape)
+            arr = part if arr is None else arr*part
+        if arr is None:
+            return None
+        arr = np.asarray(arr*s, dtype=complex)
+        if np.abs(arr.imag).max() == 0:
+            mask, ti = arr.real, False
+        elif np.abs(arr.real).max() == 0:
+            mask, ti = arr.imag, True
+        else:
+            return None
+        first = min(ax for ax in range(nd) if arr.shape[ax] > 1)
+        tshape = tuple(T.shape(True))[first:]
+        mask = np.ascontiguousarray(np.broadcast_to(mask.reshape(arr.shape[first:]), tshape), dtype=float)
+        return r, c, ops.as_device_tensor(mask), ti
 
     def __call__(self):
         from .la import mass_solve
+        if self._short is not None:
+            r, c, mask, ti = self._short
+            src = ops.plain(r)
+            if r.function_space().is_composite_space:
+                src = src[c]
+            ops.lincomb(ops.plain(self.output_array), [src], [1.0], mask=mask, times_i=ti)
+            return self.output_array
         rhs = self.rhs()
         flat = self.T.flatten() if self.T.is_composite_space else [self.T]
         if all(all(b.family() == 'fourier' for b in s.bases) for s in flat):

@@ -170,9 +170,10 @@ def rk4_stage(dU, u_hat, U0, U1, L, a_dt, b_dt, last):
           float(b_dt), int(last), _lib.stream_ptr())
 
 
-def lincomb(out, terms, coefs, mask=None, saves=()):
+def lincomb(out, terms, coefs, mask=None, saves=(), times_i=False):
     """out = mask * sum_j coefs[j]*terms[j] in one pass; `saves` = [(term index, destination)] also
-    copies up to two terms out unchanged (the IMEX-RK stage right-hand side)."""
+    copies up to two terms out unchanged (the IMEX-RK stage right-hand side); `times_i` multiplies the
+    (complex) result by i."""
     import ctypes
     dt = out.dtype
     n = out.numel()
@@ -183,7 +184,8 @@ def lincomb(out, terms, coefs, mask=None, saves=()):
     si = (ctypes.c_int*max(len(saves), 1))(*[int(i) for i, _ in saves])
     sd = (ctypes.c_void_p*max(len(saves), 1))(*[_req(d, dt, 'save') for _, d in saves])
     _call('shb_lincomb', _req(out, dt, 'out'), len(terms), tp, cf, None if mask is None else _req(mask, F64, 'mask'),
-          0 if mask is None else mask.numel(), n, int(dt.is_complex), len(saves), si, sd, _lib.stream_ptr())
+          0 if mask is None else mask.numel(), n, int(dt.is_complex) | (2 if times_i else 0), len(saves), si, sd,
+          _lib.stream_ptr())
     return out
 
 

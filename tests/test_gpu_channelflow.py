@@ -57,3 +57,31 @@ def test_kmm_vw_kernel_matches_the_reference_expression():
     assert (u[1]-v_ref).abs().max().item() <= 1e-14*v_ref.abs().max().item()
     assert (u[2]-w_ref).abs().max().item() <= 1e-14*w_ref.abs().max().item()
     assert u[0].abs().max().item() == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('axis,order', [(1, 1), (2, 1), (1, 2), (2, 3)])
+def test_project_of_a_periodic_derivative_takes_the_pointwise_path(axis, order):
+    """Project(Dx(u, periodic axis, k), space of u) = u_hat times (i k)^order: the point-wise shortcut against
+    the generic banded mat-vec + mass solve (SHB_PROJECT_SHORTCUT=0)."""
+    import os
+    import torch
+    import shenfun_b200 as sf
+    SD = sf.FunctionSpace(32, 'C', bc=(0, 0))
+    T = sf.TensorProductSpace(sf.comm, (SD, sf.FunctionSpace(12, 'F', dtype='D'), sf.FunctionSpace(10, 'F', dtype='d')))
+    u = sf.Function(T)
+    u.v.normal_()
+    u.v[SD.dim():] = 0
+    P = sf.Project(sf.Dx(u, axis, order), T)
+    assert P._short is not None
+    fast = P().get().copy()
+    os.environ['SHB_PROJECT_SHORTCUT'] = '0'
+    try:
+        Pg = sf.Project(sf.Dx(u, axis, order), T)
+    finally:
+        del os.environ['SHB_PROJECT_SHORTCUT']
+    assert Pg._short is None
+    ref = Pg().get()
+    assert np.abs(fast-ref).max() <= 1e-12*np.abs(ref).max()
+    # a derivative along the non-periodic axis keeps the generic path
+    assert sf.Project(sf.Dx(u, 0, 1), sf.TensorProductSpace(sf.comm, (sf.FunctionSpace(32, 'C'), T.bases[1], T.bases[2])))._short is None
