@@ -223,6 +223,11 @@ SHB_API int shb_lincomb(void *d_out, int nterms, const void *const *d_terms, con
 /* u *= mask on [ncomp][n] complex (Nyquist masking): replaces
  * shenfun/optimization/cython/applymask.pyx:15-169 (`apply_mask`).          */
 SHB_API int shb_apply_mask(void *d_u, const double *d_mask, int64_t n, int ncomp, void *stream);
+/* out = mask * in (times i when times_i != 0) on complex arrays of n entries, mask real [n_mask] repeated along the
+ * leading index (n a multiple of n_mask, n / n_mask <= 65535): a derivative along periodic axes applied in spectral
+ * space, what `Project(Dx(u, periodic axis, k), space of u)` reduces to (forms/project.py:172-272). */
+SHB_API int shb_scale_mask(void *d_out, const void *d_in, const double *d_mask, int64_t n_mask, int64_t n, int times_i,
+                           void *stream);
 /* v = i (a f + b g), w = i (b f - a g) on complex arrays of n entries; a, b real tables of n12 entries
  * broadcast over the leading index (demo/ChannelFlow.py:235-239, `compute_vw`). */
 SHB_API int shb_kmm_vw(const void *d_f, const void *d_g, const double *d_a, const double *d_b, void *d_v, void *d_w,

@@ -45,6 +45,7 @@ def _declare(lib):
         'shb_rk4_stage': [vp, vp, vp, vp, vp, i64, i32, f64, f64, i32, vp],
         'shb_rk4_stage_cplx': [vp, vp, vp, vp, vp, i64, i32, f64, f64, i32, vp],
         'shb_apply_mask': [vp, vp, i64, i32, vp],
+        'shb_scale_mask': [vp, vp, vp, i64, i64, i32, vp],
         'shb_fft_c2c_backward_curl': [vp, vp, i64, i32, i32, i32, vp, vp, vp, f64, vp],
         'shb_kmm_vw': [vp, vp, vp, vp, vp, vp, i64, i64, vp],
         'shb_lincomb': [vp, i32, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp],

@@ -375,6 +375,33 @@ int shb_kmm_vw(const void *d_f, const void *d_g, const double *d_a, const double
     return SHB_OK;
 }
 
+// out = (i)^times_i * mask * in on complex arrays, mask real [n_mask] repeated along the leading index
+// (n = rows * n_mask): a Fourier derivative in spectral space.  The grid carries (column block, row), so
+// there is no per-element modulo.
+__global__ void __launch_bounds__(PW_THREADS) scale_mask_kernel(cplx *__restrict__ out, const cplx *__restrict__ in,
+                                                                const double *__restrict__ mask, int64_t n_mask,
+                                                                int times_i) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_mask) return;
+    const int64_t i = (int64_t)blockIdx.y * n_mask + c;
+    const double m = __ldg(&mask[c]);
+    const cplx x = in[i];
+    out[i] = times_i ? make_double2(-m * x.y, m * x.x) : make_double2(m * x.x, m * x.y);
+}
+
+int shb_scale_mask(void *d_out, const void *d_in, const double *d_mask, int64_t n_mask, int64_t n, int times_i,
+                   void *stream) {
+    SHB_REQUIRE(d_out && d_in && d_mask && n_mask >= 1 && n >= 0 && n % n_mask == 0, "bad arguments");
+    if (n == 0) return SHB_OK;
+    const int64_t rows = n / n_mask;
+    SHB_REQUIRE(rows <= 65535, "leading extent too large");
+    dim3 grid((unsigned)((n_mask + PW_THREADS - 1) / PW_THREADS), (unsigned)rows);
+    scale_mask_kernel<<<grid, PW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (cplx *)d_out, (const cplx *)d_in, d_mask, n_mask, times_i);
+    SHB_CUDA(cudaGetLastError());
+    return SHB_OK;
+}
+
 int shb_apply_mask(void *d_u, const double *d_mask, int64_t n, int ncomp, void *stream) {
     SHB_REQUIRE(d_u && d_mask && n >= 0 && ncomp >= 1, "bad arguments");
     if (n == 0) return SHB_OK;

@@ -350,7 +350,7 @@ class Project:
             src = ops.plain(r)
             if r.function_space().is_composite_space:
                 src = src[c]
-            ops.lincomb(ops.plain(self.output_array), [src], [1.0], mask=mask, times_i=ti)
+            ops.scale_mask(ops.plain(self.output_array), src, mask, times_i=ti)
             return self.output_array
         rhs = self.rhs()
         flat = self.T.flatten() if self.T.is_composite_space else [self.T]

@@ -198,6 +198,16 @@ def kmm_vw(f, g, a, b, v, w):
           _req(v, C128, 'v'), _req(w, C128, 'w'), f.numel(), n12, _lib.stream_ptr())
 
 
+def scale_mask(out, inp, mask, times_i=False):
+    """out = mask * inp (times i) on complex arrays; the real mask covers the trailing dimensions."""
+    n_mask, n = mask.numel(), inp.numel()
+    if n % n_mask or n//n_mask > 65535 or out.numel() != n:
+        return lincomb(out, [inp], [1.0], mask=mask, times_i=times_i)
+    _call('shb_scale_mask', _req(out, C128, 'out'), _req(inp, C128, 'in'), _req(mask, F64, 'mask'), n_mask, n,
+          int(bool(times_i)), _lib.stream_ptr())
+    return out
+
+
 def apply_mask(u_hat, mask):
     n = mask.numel()
     _call('shb_apply_mask', _req(u_hat, C128, 'u_hat'), _req(mask, F64, 'mask'), n, u_hat.numel()//n,
